@@ -1,0 +1,27 @@
+# Builds the C-ABI shared library (sm_100a only) and the native self-check harness.
+PKG   := vae-gan-based-model-for-image-generation-and-denoising_b200
+CSRC  := $(PKG)/csrc
+NVCC  ?= nvcc
+ARCH  := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
+SRCS  := $(wildcard $(CSRC)/*.cu)
+OBJS  := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(SRCS))
+LIB   := $(PKG)/libvaegan_b200.so
+
+all: $(LIB)
+
+build/obj/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/vaegan_b200.h
+	@mkdir -p build/obj
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+harness: $(LIB) tests/native/igemm_harness.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o build/igemm_harness tests/native/igemm_harness.cu -L$(PKG) -lvaegan_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all harness clean

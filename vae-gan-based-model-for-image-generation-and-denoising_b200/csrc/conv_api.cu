@@ -1,0 +1,361 @@
+// C-ABI for the three convolution contractions (down / up / wgrad): geometry -> tap tables + TMA tensor maps
+// -> tcgen05 implicit-GEMM launch (bf16), or the fp32 CUDA-core implicit GEMM (conv_simt.cu).
+#include <algorithm>
+#include <cstring>
+
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "igemm_umma.cuh"
+
+namespace vg {
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static int floor_mod(int a, int m) { return ((a % m) + m) % m; }
+
+// Box (tw, th, tb) with tw*th*tb == rows covering a (w, h, b) grid with as little waste as possible.
+static void pick_box(int rows, int w, int h, int* tw, int* th, int* tb) {
+    *tw = std::min(pow2_ceil(w), rows);
+    *th = std::min(pow2_ceil(h), rows / *tw);
+    *tb = rows / (*tw * *th);
+}
+
+static int pick_kchunk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+
+static int pick_n_tile(int n) {
+    for (int t = 256; t >= 16; t -= 16)
+        if (n % t == 0) return t;
+    return 0;
+}
+
+static int pick_stages(int stage_bytes, int n_tile) {
+    // two CTAs per SM when the accumulator is narrow (epilogue of one overlaps the main loop of the other)
+    const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048;
+    return std::max(2, std::min(8, budget / stage_bytes));
+}
+
+// NHWC view of `base` [B][H][W][C] decimated by `s` starting at (vy, vx); dims innermost first.
+static int make_view(CUtensorMap* m, const void* base, int B, int H, int W, int C, int s, int vy, int vx, int box_c,
+                     int tw, int th, int tb, int swizzle) {
+    const int Wv = ceil_div(W - vx, s), Hv = ceil_div(H - vy, s);
+    if (Wv <= 0 || Hv <= 0) {  // empty parity plane: never addressed in-bounds; keep a valid 1x1 window
+        const uint64_t dims[4] = {(uint64_t)C, 1, 1, (uint64_t)B};
+        const uint64_t strides[4] = {1, (uint64_t)C, (uint64_t)C, (uint64_t)H * W * C};
+        const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+        return make_tmap_bf16(m, base, 4, dims, strides, box, swizzle);
+    }
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wv, (uint64_t)Hv, (uint64_t)B};
+    const uint64_t strides[4] = {1, (uint64_t)s * C, (uint64_t)s * W * C, (uint64_t)H * W * C};
+    const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+    const char* p = static_cast<const char*>(base) + (static_cast<size_t>(vy) * W + vx) * C * 2;
+    return make_tmap_bf16(m, p, 4, dims, strides, box, swizzle);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int check_geom(const VgConvGeom* g) {
+    if (g == nullptr) return fail(VG_ERR_ARG, "null geometry");
+    if (g->batch <= 0 || g->big_h <= 0 || g->big_w <= 0 || g->big_c <= 0 || g->small_h <= 0 || g->small_w <= 0 ||
+        g->small_c <= 0 || g->kernel <= 0 || g->stride <= 0 || g->pad < 0)
+        return fail(VG_ERR_SHAPE, "non-positive extent in conv geometry");
+    const int eh = (g->big_h + 2 * g->pad - g->kernel) / g->stride + 1;
+    const int ew = (g->big_w + 2 * g->pad - g->kernel) / g->stride + 1;
+    if (g->big_h + 2 * g->pad < g->kernel || g->big_w + 2 * g->pad < g->kernel)
+        return fail(VG_ERR_SHAPE, "Kernel size can't be greater than actual input size");
+    if (eh != g->small_h || ew != g->small_w)
+        return fail(VG_ERR_SHAPE, "small extent %dx%d inconsistent with big %dx%d k%d s%d p%d (expect %dx%d)",
+                    g->small_h, g->small_w, g->big_h, g->big_w, g->kernel, g->stride, g->pad, eh, ew);
+    return VG_OK;
+}
+
+bool umma_down_ok(const VgConvGeom* g) {
+    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 64 && pick_kchunk(g->big_c) != 0 &&
+           pick_n_tile(g->small_c) != 0;
+}
+bool umma_up_ok(const VgConvGeom* g) {
+    const bool dense = g->small_h == 1 && g->small_w == 1 && g->stride == 1 && g->pad == 0;
+    if (pick_kchunk(g->small_c) == 0) return false;
+    if (dense) return pick_n_tile(g->big_c) != 0;
+    if (g->stride == 2 && (g->kernel % 2) != 0) return false;
+    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 64 && pick_n_tile(g->big_c) != 0;
+}
+bool umma_wgrad_ok(const VgConvGeom* g) {
+    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 16 && g->small_c % 64 == 0 &&
+           g->big_c % 64 == 0;
+}
+
+// ---------------------------------------------------------------------------------------------- down
+static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const float* bias, void* small,
+                     int out_f32, cudaStream_t stream) {
+    if (!aligned16(big) || !aligned16(wd) || !aligned16(small)) return fail(VG_ERR_ALIGN, "down: 16-byte alignment");
+    IgemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    const int k = g->kernel, s = g->stride, pad = g->pad;
+    p.kchunk = pick_kchunk(g->big_c);
+    p.c_chunks = g->big_c / p.kchunk;
+    p.n_tile = pick_n_tile(g->small_c);
+    p.n_tiles = g->small_c / p.n_tile;
+    pick_box(128, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
+    p.tiles_w = ceil_div(g->small_w, p.tw);
+    p.tiles_h = ceil_div(g->small_h, p.th);
+    p.tiles_b = ceil_div(g->batch, p.tb);
+    p.num_phases = 1;
+    p.taps_per_phase = k * k;
+    const int swz = p.kchunk * 2;
+    const int nviews = s * s;
+    for (int v = 0; v < 4; ++v) {
+        const int vv = v < nviews ? v : 0;
+        const int rc = make_view(&p.amap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, p.kchunk,
+                                 p.tw, p.th, p.tb, swz);
+        if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(A view %d) failed (%d)", v, rc);
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)g->big_c, (uint64_t)k * k * g->small_c};
+        const uint64_t strides[2] = {1, (uint64_t)g->big_c};
+        const uint32_t box[2] = {(uint32_t)p.kchunk, (uint32_t)p.n_tile};
+        const int rc = make_tmap_bf16(&p.bmap, wd, 2, dims, strides, box, swz);
+        if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    }
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+            IgemmTap& t = p.taps[ky * k + kx];
+            const int vy = floor_mod(ky - pad, s), vx = floor_mod(kx - pad, s);
+            t.view = static_cast<int16_t>(vy * s + vx);
+            t.dy = static_cast<int16_t>((ky - pad - vy) / s);
+            t.dx = static_cast<int16_t>((kx - pad - vx) / s);
+            t.tap_id = static_cast<int16_t>(ky * k + kx);
+            t.brow = (ky * k + kx) * g->small_c;
+        }
+    p.stages = pick_stages((128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    p.out = small;
+    p.out_fp32 = out_f32;
+    p.out_B = g->batch;
+    p.out_H = g->small_h;
+    p.out_W = g->small_w;
+    p.out_C = g->small_c;
+    p.osy = p.osx = 1;
+    p.bias = bias;
+    const int rc = launch_igemm(p, stream);
+    if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- up
+static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void* big, cudaStream_t stream) {
+    if (!aligned16(big) || !aligned16(wu) || !aligned16(small)) return fail(VG_ERR_ALIGN, "up: 16-byte alignment");
+    IgemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    const int k = g->kernel, s = g->stride, pad = g->pad;
+    const bool dense = g->small_h == 1 && g->small_w == 1 && s == 1 && pad == 0;
+    p.kchunk = pick_kchunk(g->small_c);
+    p.c_chunks = g->small_c / p.kchunk;
+    const int swz = p.kchunk * 2;
+    const int n_total = dense ? k * k * g->big_c : g->big_c;
+    p.n_tile = pick_n_tile(n_total);
+    p.n_tiles = n_total / p.n_tile;
+    const int grid_h = dense ? 1 : ceil_div(g->big_h, s), grid_w = dense ? 1 : ceil_div(g->big_w, s);
+    pick_box(128, grid_w, grid_h, &p.tw, &p.th, &p.tb);
+    p.tiles_w = ceil_div(grid_w, p.tw);
+    p.tiles_h = ceil_div(grid_h, p.th);
+    p.tiles_b = ceil_div(g->batch, p.tb);
+    for (int v = 0; v < 4; ++v) {
+        const int rc = make_view(&p.amap[v], small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.kchunk,
+                                 p.tw, p.th, p.tb, swz);
+        if (rc != 0) return fail(VG_ERR_CUDA, "up: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)g->small_c, (uint64_t)k * k * g->big_c};
+        const uint64_t strides[2] = {1, (uint64_t)g->small_c};
+        const uint32_t box[2] = {(uint32_t)p.kchunk, (uint32_t)p.n_tile};
+        const int rc = make_tmap_bf16(&p.bmap, wu, 2, dims, strides, box, swz);
+        if (rc != 0) return fail(VG_ERR_CUDA, "up: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    }
+    p.out = big;
+    p.out_fp32 = 0;
+    p.out_B = g->batch;
+    if (dense) {
+        // big[b, (ky,kx), bc] = sum_sc small[b, sc] * w[sc][bc][ky][kx]: one GEMM with N = k*k*big_c
+        p.num_phases = 1;
+        p.taps_per_phase = 1;
+        p.taps[0] = IgemmTap{0, 0, 0, 0, 0};
+        p.out_H = 1;
+        p.out_W = 1;
+        p.out_C = n_total;
+        p.osy = p.osx = 1;
+    } else {
+        p.num_phases = s * s;
+        // taps per output parity: ky with (a + pad - ky) divisible by s; every phase must have the same count
+        int per_dim = -1;
+        for (int a = 0; a < s; ++a) {
+            int n = 0;
+            for (int ky = 0; ky < k; ++ky) n += floor_mod(a + pad - ky, s) == 0;
+            if (per_dim >= 0 && n != per_dim)
+                return fail(VG_ERR_SHAPE, "up: phases with different tap counts (k%d s%d)", k, s);
+            per_dim = n;
+        }
+        const int per_phase = per_dim * per_dim;
+        if (per_phase * s * s > 64 || per_phase == 0) return fail(VG_ERR_SHAPE, "up: unsupported tap count");
+        for (int ay = 0; ay < s; ++ay)
+            for (int ax = 0; ax < s; ++ax) {
+                p.ph_ay[ay * s + ax] = ay;
+                p.ph_ax[ay * s + ax] = ax;
+            }
+        p.taps_per_phase = per_phase;
+        for (int ay = 0; ay < s; ++ay)
+            for (int ax = 0; ax < s; ++ax) {
+                const int ph = ay * s + ax;
+                int n = 0;
+                for (int ky = 0; ky < k; ++ky) {
+                    if (floor_mod(ay + pad - ky, s) != 0) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        if (floor_mod(ax + pad - kx, s) != 0) continue;
+                        IgemmTap& t = p.taps[ph * per_phase + n];
+                        t.view = 0;
+                        t.dy = static_cast<int16_t>((ay + pad - ky) / s);
+                        t.dx = static_cast<int16_t>((ax + pad - kx) / s);
+                        t.tap_id = static_cast<int16_t>(ky * k + kx);
+                        t.brow = (ky * k + kx) * g->big_c;
+                        ++n;
+                    }
+                }
+            }
+        p.out_H = g->big_h;
+        p.out_W = g->big_w;
+        p.out_C = g->big_c;
+        p.osy = p.osx = s;
+    }
+    p.stages = pick_stages((128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    const int rc = launch_igemm(p, stream);
+    if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, float* dw, cudaStream_t stream) {
+    if (!aligned16(big) || !aligned16(small)) return fail(VG_ERR_ALIGN, "wgrad: 16-byte alignment");
+    WgradParams p;
+    std::memset(&p, 0, sizeof(p));
+    const int k = g->kernel, s = g->stride, pad = g->pad;
+    pick_box(64, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
+    p.tiles_w = ceil_div(g->small_w, p.tw);
+    p.tiles_h = ceil_div(g->small_h, p.th);
+    p.tiles_b = ceil_div(g->batch, p.tb);
+    p.m_atoms = g->small_c >= 128 ? 2 : 1;
+    p.m_tiles = ceil_div(g->small_c, p.m_atoms * 64);
+    p.n_tile = g->big_c % 128 == 0 ? 128 : 64;
+    p.n_tiles = g->big_c / p.n_tile;
+    p.num_taps = k * k;
+    p.taps_per_cta = std::min(p.num_taps, 512 / p.n_tile);
+    {
+        const int rc = make_view(&p.pmap, small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, 64, p.tw, p.th,
+                                 p.tb, 128);
+        if (rc != 0) return fail(VG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(P) failed (%d)", rc);
+    }
+    const int nviews = s * s;
+    for (int v = 0; v < 4; ++v) {
+        const int vv = v < nviews ? v : 0;
+        const int rc = make_view(&p.qmap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, 64, p.tw,
+                                 p.th, p.tb, 128);
+        if (rc != 0) return fail(VG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(Q view %d) failed (%d)", v, rc);
+    }
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+            IgemmTap& t = p.taps[ky * k + kx];
+            const int vy = floor_mod(ky - pad, s), vx = floor_mod(kx - pad, s);
+            t.view = static_cast<int16_t>(vy * s + vx);
+            t.dy = static_cast<int16_t>((ky - pad - vy) / s);
+            t.dx = static_cast<int16_t>((kx - pad - vx) / s);
+            t.tap_id = static_cast<int16_t>(ky * k + kx);
+            t.brow = 0;
+        }
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int tap_groups = ceil_div(p.num_taps, p.taps_per_cta);
+    const int base_ctas = p.m_tiles * p.n_tiles * tap_groups;
+    p.splits = std::max(1, std::min(total_tiles, ceil_div(296, base_ctas)));
+    const int stage_bytes = (2 + p.n_tile / 64) * 64 * 128;
+    p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    p.dw = dw;
+    p.s_m = static_cast<long long>(g->big_c) * k * k;
+    p.s_n = k * k;
+    p.s_tap = 1;
+    p.m_valid = g->small_c;
+    p.n_valid = g->big_c;
+    const int rc = launch_wgrad(p, stream);
+    if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_wgrad_kernel");
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- packing
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd,
+                                    __nv_bfloat16* __restrict__ wu, int sc, int bc, int kk) {
+    const long long n = static_cast<long long>(sc) * bc * kk;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // i indexes the destination wd[tap][s][b] so that writes are coalesced
+        const int b = static_cast<int>(i % bc);
+        const int s = static_cast<int>((i / bc) % sc);
+        const int tap = static_cast<int>(i / (static_cast<long long>(bc) * sc));
+        const float v = w[(static_cast<long long>(s) * bc + b) * kk + tap];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        if (wd != nullptr) wd[i] = h;
+        if (wu != nullptr) wu[(static_cast<long long>(tap) * bc + b) * sc + s] = h;
+    }
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* wd, void* wu, void* stream) {
+    if (g == nullptr || w == nullptr) return fail(VG_ERR_ARG, "pack: null argument");
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    const int kk = g->kernel * g->kernel;
+    const long long n = static_cast<long long>(g->small_c) * g->big_c * kk;
+    const int threads = 256;
+    const int blocks = static_cast<int>(std::min<long long>((n + threads - 1) / threads, 148 * 16));
+    pack_weights_kernel<<<blocks, threads, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wd),
+                                                                   static_cast<__nv_bfloat16*>(wu), g->small_c,
+                                                                   g->big_c, kk);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias,
+                            void* small, int out_f32, void* stream) {
+    int rc = check_geom(g);
+    if (rc != VG_OK) return rc;
+    if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "down: null pointer");
+    rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dtype == VG_BF16 && umma_down_ok(g)) return down_umma(g, big, w, bias, small, out_f32, as_stream(stream));
+    return simt_conv_down(g, dtype, big, w, bias, small, out_f32, as_stream(stream));
+}
+
+extern "C" int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big,
+                          void* stream) {
+    int rc = check_geom(g);
+    if (rc != VG_OK) return rc;
+    if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "up: null pointer");
+    rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dtype == VG_BF16 && umma_up_ok(g)) return up_umma(g, small, w, big, as_stream(stream));
+    return simt_conv_up(g, dtype, small, w, big, as_stream(stream));
+}
+
+extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
+                             void* stream) {
+    int rc = check_geom(g);
+    if (rc != VG_OK) return rc;
+    if (big == nullptr || dw == nullptr || small == nullptr) return fail(VG_ERR_ARG, "wgrad: null pointer");
+    rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dtype == VG_BF16 && umma_wgrad_ok(g)) return wgrad_umma(g, small, big, dw, as_stream(stream));
+    return simt_conv_wgrad(g, dtype, small, big, dw, as_stream(stream));
+}

@@ -1,0 +1,376 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels (sm_100a only).  See igemm_umma.cuh for the formulation.
+//
+// Warp roles in a 192-thread CTA:
+//   warp 0 (one lane)  : TMA producer  - fills the smem ring, arms `full[s]` with expect_tx
+//   warp 1             : TMEM allocator; one lane issues tcgen05.mma and commits `empty[s]` / `tmem_full`
+//   warps 2..5         : epilogue - tcgen05.ld the fp32 accumulator (lane quadrant = warp % 4), convert, store
+#include "igemm_umma.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace vg {
+
+static constexpr int kIgemmThreads = 192;
+static constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) {
+    uint32_t c = 32;
+    while (c < static_cast<uint32_t>(n)) c <<= 1;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop-type kernel: A = activation views (K-major), B = packed weights (K-major), D -> NHWC output
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_bytes = p.kchunk * 2;
+    const int a_stage = 128 * row_bytes;
+    const int b_stage = p.n_tile * row_bytes;
+    const int stages = p.stages;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + stages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tmem_full = empty + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    int tile = blockIdx.x;
+    const int tile_w = tile % p.tiles_w;
+    tile /= p.tiles_w;
+    const int tile_h = tile % p.tiles_h;
+    const int tile_b = tile / p.tiles_h;
+    const int i0 = tile_h * p.th, j0 = tile_w * p.tw, b0 = tile_b * p.tb;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int phase = blockIdx.z;
+    const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
+    const int iters = p.taps_per_phase * p.c_chunks;
+    const uint32_t ncols = tmem_cols_for(p.n_tile);
+
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.amap[v]);
+        tma_prefetch_desc(&p.bmap);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, ncols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = 0; t < p.taps_per_phase; ++t) {
+                const IgemmTap tap = taps[t];
+                for (int c = 0; c < p.c_chunks; ++c, ++it) {
+                    const int s = it % stages;
+                    const uint32_t par = (it / stages) & 1;
+                    mbar_wait(&empty[s], par ^ 1);
+                    mbar_expect_tx(&full[s], a_stage + b_stage);
+                    tma_load_4d(sA + s * a_stage, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx, i0 + tap.dy,
+                                b0);
+                    tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
+            const uint32_t layout = p.kchunk == 64 ? 2u : (p.kchunk == 32 ? 4u : 6u);
+            const uint32_t sbo = 8 * row_bytes;
+            const int ksteps = p.kchunk / 16;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % stages;
+                const uint32_t par = (it / stages) & 1;
+                mbar_wait(&full[s], par);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * a_stage);
+                const uint32_t b_addr = smem_u32(sB + s * b_stage);
+                for (int k = 0; k < ksteps; ++k) {
+                    umma_bf16(tmem_base, make_smem_desc(a_addr + k * 32, 0, sbo, layout),
+                              make_smem_desc(b_addr + k * 32, 0, sbo, layout), idesc, (it | k) != 0);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int w_l = row % p.tw;
+        const int h_l = (row / p.tw) % p.th;
+        const int b_l = row / (p.tw * p.th);
+        const int b = b0 + b_l;
+        const int y = (i0 + h_l) * p.osy + p.ph_ay[phase];
+        const int x = (j0 + w_l) * p.osx + p.ph_ax[phase];
+        const bool valid = (b < p.out_B) && (y < p.out_H) && (x < p.out_W);
+        const size_t off = ((static_cast<size_t>(b) * p.out_H + y) * p.out_W + x) * p.out_C + n0;
+
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c = 0; c < p.n_tile; c += 32) {
+            uint32_t v[32];
+            const int cols = (p.n_tile - c) >= 32 ? 32 : 16;
+            if (cols == 32) {
+                tmem_ld_32x32(taddr + c, v);
+            } else {
+                uint32_t h[16];
+                tmem_ld_32x16(taddr + c, h);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
+            }
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < cols) f[j] += __ldg(p.bias + n0 + c + j);
+            }
+            if (valid) {
+                if (p.out_fp32) {
+                    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j * 4 < cols) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j * 8 < cols)
+                            dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                                                pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad-type kernel: both operands MN-major (pixels are the reduction dimension)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kpix = p.tw * p.th * p.tb;
+    const int atom_bytes = kpix * 128;  // one 64-channel MN atom: kpix rows of 128 B
+    const int n_atoms = p.n_tile / 64;
+    const int a_stage = 2 * atom_bytes;  // always room for M = 128 (second atom may stay unwritten)
+    const int b_stage = n_atoms * atom_bytes;
+    const int stages = p.stages;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + stages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tmem_full = empty + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int split = blockIdx.x;
+    const int m_tile = blockIdx.y / p.n_tiles, n_tile_idx = blockIdx.y % p.n_tiles;
+    const int m0 = m_tile * p.m_atoms * 64, n0 = n_tile_idx * p.n_tile;
+    const int tap0 = blockIdx.z * p.taps_per_cta;
+    const int ntap = min(p.taps_per_cta, p.num_taps - tap0);
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int pt_begin = static_cast<int>(static_cast<long long>(total_tiles) * split / p.splits);
+    const int pt_end = static_cast<int>(static_cast<long long>(total_tiles) * (split + 1) / p.splits);
+    const int iters = (pt_end - pt_begin) * ntap;
+    const uint32_t ncols = tmem_cols_for(p.taps_per_cta * p.n_tile);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.pmap);
+        for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.qmap[v]);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, ncols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                int t = pt;
+                const int j0 = (t % p.tiles_w) * p.tw;
+                t /= p.tiles_w;
+                const int i0 = (t % p.tiles_h) * p.th;
+                const int b0 = (t / p.tiles_h) * p.tb;
+                for (int tl = 0; tl < ntap; ++tl, ++it) {
+                    const IgemmTap tap = p.taps[tap0 + tl];
+                    const int s = it % stages;
+                    const uint32_t par = (it / stages) & 1;
+                    mbar_wait(&empty[s], par ^ 1);
+                    mbar_expect_tx(&full[s], (p.m_atoms + n_atoms) * atom_bytes);
+                    for (int a = 0; a < p.m_atoms; ++a)
+                        tma_load_4d(sA + s * a_stage + a * atom_bytes, &p.pmap, &full[s], m0 + a * 64, j0, i0, b0);
+                    for (int a = 0; a < n_atoms; ++a)
+                        tma_load_4d(sB + s * b_stage + a * atom_bytes, &p.qmap[tap.view], &full[s], n0 + a * 64,
+                                    j0 + tap.dx, i0 + tap.dy, b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 1, 1);
+            const int ksteps = kpix / 16;
+            int it = 0;
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                for (int tl = 0; tl < ntap; ++tl, ++it) {
+                    const int s = it % stages;
+                    const uint32_t par = (it / stages) & 1;
+                    mbar_wait(&full[s], par);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + s * a_stage);
+                    const uint32_t b_addr = smem_u32(sB + s * b_stage);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // 16 pixel rows per UMMA: 2 groups of 8 rows (SBO = 1024 B); MN atoms LBO apart
+                        umma_bf16(tmem_base + tl * p.n_tile, make_smem_desc(a_addr + k * 2048, atom_bytes, 1024, 2),
+                                  make_smem_desc(b_addr + k * 2048, atom_bytes, 1024, 2), idesc,
+                                  (pt != pt_begin || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool valid = (row < p.m_atoms * 64) && (m < p.m_valid) && (iters > 0);
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int tl = 0; tl < ntap; ++tl) {
+            const int tap_id = p.taps[tap0 + tl].tap_id;
+            float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(tap_id) * p.s_tap;
+            for (int c = 0; c < p.n_tile; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + tl * p.n_tile + c, v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c + j;
+                        if (n < p.n_valid) atomicAdd(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static constexpr int kBarrierBytes = (2 * kMaxStages + 1) * 8 + 16;
+
+static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_bytes + 1024 + kBarrierBytes; }
+
+int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
+    const int stage_bytes = (128 + p.n_tile) * p.kchunk * 2;
+    const int smem = smem_bytes_for(p.stages, stage_bytes);
+    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.n_tiles, p.num_phases);
+    igemm_fprop_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
+    const int kpix = p.tw * p.th * p.tb;
+    const int stage_bytes = (2 + p.n_tile / 64) * kpix * 128;
+    const int smem = smem_bytes_for(p.stages, stage_bytes);
+    const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
+    dim3 grid(p.splits, p.m_tiles * p.n_tiles, tap_groups);
+    igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int igemm_smem_bytes(int stages, int stage_bytes) { return smem_bytes_for(stages, stage_bytes); }
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so the library links without
+// libcuda (the build container has no driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return -1;
+    cuuint64_t gdim[5], gstride[5];
+    cuuint32_t gbox[5], estride[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        gbox[i] = box[i];
+        estride[i] = 1;
+        if (i > 0) gstride[i - 1] = strides_elems[i] * 2;  // bytes
+    }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                        : CU_TENSOR_MAP_SWIZZLE_32B;
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                          gdim, gstride, gbox, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+}  // namespace vg

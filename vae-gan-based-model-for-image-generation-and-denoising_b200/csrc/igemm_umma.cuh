@@ -1,0 +1,76 @@
+// Implicit-GEMM convolution kernels on tcgen05/TMEM fed by TMA (sm_100a).
+//
+// One "tap" of a convolution is a plain GEMM between a shifted (and, for stride 2, parity-decimated) view
+// of an NHWC bf16 activation tensor and one [N x C] slab of the packed weight tensor.  A TMA box of
+// (kchunk channels) x (tw x th x tb pixels) lands in shared memory as a 128-row K-major swizzled UMMA
+// operand; image borders / padding come for free from TMA out-of-bounds zero fill.
+//
+//   fprop-type kernel  : D[pixel, n] = sum_taps sum_c  A_tap[pixel, c] * W_tap[n, c]
+//       - Conv2d forward (k4 s2): 16 taps over the 4 (row parity, col parity) views of x
+//       - ConvTranspose2d forward / Conv2d dgrad (k4 s2): 4 output phases x 4 taps over the plain view
+//       - dense GEMM (Linear, 1x1-input ConvT): 1 tap
+//   wgrad-type kernel  : dW_tap[m, n] = sum_pixels P[pixel, m] * Q_tap[pixel, n]   (both operands MN-major)
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace vg {
+
+struct IgemmTap {
+    int16_t view;   // which A tensor map (parity view) this tap reads
+    int16_t dy;     // shift in view rows
+    int16_t dx;     // shift in view columns
+    int16_t tap_id; // wgrad: destination tap index; fprop: unused
+    int32_t brow;   // fprop: first row of this tap's [N x C] slab in the packed-weight 2D map
+};
+
+struct alignas(64) IgemmParams {
+    CUtensorMap amap[4];
+    CUtensorMap bmap;
+    IgemmTap taps[64];     // flat: taps[phase * taps_per_phase + t]
+    int num_phases, taps_per_phase;
+    int kchunk;    // channels per pipeline stage: 64 / 32 / 16  (row bytes 128 / 64 / 32)
+    int c_chunks;  // C / kchunk
+    int tw, th, tb;
+    int tiles_w, tiles_h, tiles_b;
+    int n_tile;    // UMMA N (multiple of 16, <= 256)
+    int n_tiles;   // grid.y: N_total / n_tile
+    int stages;
+    // output: NHWC tensor, element (b, y, x, n) with y = i*osy + ay[phase], x = j*osx + ax[phase]
+    void* out;
+    int out_fp32;
+    int out_B, out_H, out_W, out_C;
+    int osy, osx;
+    int ph_ay[4], ph_ax[4];
+    const float* bias;  // optional [out_C]
+};
+
+struct alignas(64) WgradParams {
+    CUtensorMap pmap;      // "P" operand (plain view), channels -> UMMA M
+    CUtensorMap qmap[4];   // "Q" operand views (taps shift these), channels -> UMMA N
+    IgemmTap taps[16];
+    int num_taps;
+    int taps_per_cta;      // accumulators resident in TMEM per CTA (taps_per_cta * n_tile <= 512)
+    int tw, th, tb;        // pixel box; tw*th*tb = kpix (multiple of 16, <= 128)
+    int tiles_w, tiles_h, tiles_b;
+    int m_atoms;           // P channels per CTA / 64 (1 or 2)
+    int n_tile;            // Q channels per CTA (multiple of 64, <= 256)
+    int m_tiles, n_tiles;
+    int splits;            // split of the pixel-tile range across CTAs
+    int stages;
+    float* dw;             // fp32, accumulated with red.global.add
+    long long s_m, s_n, s_tap;  // element strides of dw for (P channel, Q channel, tap)
+    int m_valid, n_valid;  // channel counts actually present (rows/cols beyond are dropped)
+};
+
+// Host-side launchers (return cudaError_t as int).
+int launch_igemm(const IgemmParams& p, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, cudaStream_t stream);
+
+// rank<=4 bf16 tensor map; dims/strides innermost first; strides in ELEMENTS for dims 1.. (dim 0 is contiguous).
+// swizzle_bytes in {128, 64, 32}.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box, int swizzle_bytes);
+
+}  // namespace vg
