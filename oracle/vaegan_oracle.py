@@ -265,11 +265,12 @@ class _RoundSTE(torch.autograd.Function):
         return _round_bf16(g)
 
 
-def attach_bf16_emulation(*nets: nn.Module):
+def attach_bf16_emulation(*nets: nn.Module) -> None:
     """Make fp32 CPU modules mimic the rounding points of the bf16 tensor-core path: conv / linear operands
-    (activations and weights) and conv outputs are bf16-representable, accumulation stays fp32
-    (SURVEY.md Appendix D protocol).  Returns the hook handles."""
-    handles = []
+    (activations AND weights) and their outputs are bf16-representable in forward, and the gradients that flow
+    back through those points are rounded too; accumulation stays fp32 (SURVEY.md Appendix D protocol).
+    Applies parametrizations in place - use on deep copies."""
+    import torch.nn.utils.parametrize as parametrize
 
     def pre(mod, args):
         return (_RoundSTE.apply(args[0]),)
@@ -278,18 +279,28 @@ def attach_bf16_emulation(*nets: nn.Module):
         return _RoundSTE.apply(out)
 
     for net in nets:
-        for m in net.modules():
+        for m in list(net.modules()):
             if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):
-                handles.append(m.register_forward_pre_hook(pre))
-                handles.append(m.register_forward_hook(post))
-                handles.append(torch.nn.utils.parametrize.register_parametrization(m, "weight", _RoundParam())
-                               if False else None)
-    return [h for h in handles if h is not None]
+                m.register_forward_pre_hook(pre)
+                m.register_forward_hook(post)
+                parametrize.register_parametrization(m, "weight", _RoundParam(), unsafe=True)
 
 
 class _RoundParam(nn.Module):
     def forward(self, w):
-        return _RoundSTE.apply(w)
+        return _RoundFwd.apply(w)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """bf16 rounding of a weight in forward; its fp32 gradient passes through untouched (fp32 wgrad output)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _round_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
 
 
 # --------------------------------------------------------------------------------------------- decoder-only
