@@ -83,6 +83,77 @@ int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void
 /* dw (fp32, reference layout [small_c][big_c][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient. */
 int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* stream);
 
+
+/* ---- BatchNorm2d (training statistics), activations, layout edges ---------------------------------------------
+ * All tensors NHWC viewed as [rows = B*H*W][C].  Reductions are two-stage and deterministic; the caller passes a
+ * scratch buffer of vg_reduce_workspace_bytes() / vg_bn_bwd_workspace_bytes().
+ * vg_bn_train_fwd replaces F.batch_norm(training=True) of nn.BatchNorm2d (main_vae.py:24,29; gan_code.py:22-46,
+ * 65-81): batch mean / biased variance -> mean, rstd, and the fused affine  scale = gamma*rstd,
+ * shift = beta - mean*scale;  running_mean / running_var (unbiased) / num_batches_tracked updated in place
+ * (pass NULL to skip). */
+size_t vg_reduce_workspace_bytes(long long rows, int channels);
+size_t vg_bn_bwd_workspace_bytes(long long rows, int channels);
+int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int channels, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    float* mean_out, float* rstd_out, float* scale_out, float* shift_out, float* ws, size_t ws_bytes,
+                    void* stream);
+/* eval-mode BatchNorm folded to scale/shift from the running statistics (main_vae.py:360, decoder.eval()). */
+int vg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int channels, float* scale_out, float* shift_out, void* stream);
+/* y = act(x * scale[c] + shift[c]); scale / shift may be NULL (identity).  Replaces the BN affine + nn.LeakyReLU /
+ * nn.ReLU / nn.Sigmoid / nn.Tanh element-wise passes (main_vae.py:25,30; gan_code.py:23-50,62-85). */
+int vg_scale_shift_act(const void* x, VgDType in_dt, long long rows, int channels, const float* scale,
+                       const float* shift, VgAct act, float slope, void* y, VgDType out_dt, void* stream);
+/* Backward of act(BN(x)):  dz = dy*act'(x*scale+shift);  dgamma += sum dz*xhat;  dbeta += sum dz;
+ * dx = scale*(dz - mean(dz) - xhat*mean(dz*xhat)).  dgamma / dbeta may be NULL. */
+int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long long rows, int channels, const float* scale,
+                  const float* shift, const float* mean, const float* rstd, VgAct act, float slope, float* dgamma,
+                  float* dbeta, void* dx, float* ws, size_t ws_bytes, void* stream);
+/* dx = dy * act'(x) for layers without BatchNorm. */
+int vg_act_bwd(const void* dy, const void* x, VgDType in_dt, long long n, VgAct act, float slope, void* dx,
+               VgDType out_dt, void* stream);
+/* out[c] += sum_rows x[row][c]   (bias gradient of nn.Conv2d / nn.Linear, main_vae.py:23,47-48). */
+int vg_colsum(const void* x, VgDType dt, long long rows, int channels, float* out, float* ws, size_t ws_bytes,
+              void* stream);
+/* fp32 NCHW (the reference's tensor contract, dataset_code.py:178) -> NHWC dtype.
+ *   mode 0: copy;  mode 1: clamp?(src + sigma*aux)  (instance / denoising noise, vaegan_code.py:91-92,153-154);
+ *   mode 2: src * (1 - aux^2)  (Tanh backward, aux = tanh output). */
+int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int batch, int channels, int h, int w,
+                    int mode, float sigma, int clamp, void* stream);
+/* NHWC dtype -> fp32 NCHW with an optional activation (Tanh of gan_code.py:50). */
+int vg_nhwc_to_nchw(const void* src, VgDType dt, float* dst, int batch, int channels, int h, int w, VgAct act,
+                    float slope, void* stream);
+
+/* ---- VAE-GAN losses, Adam, noise ------------------------------------------------------------------------------
+ * vg_reparam_fwd : logvar clamp [-10,10], std = exp(logvar/2), z = mu + std*eps, KL = -1/2 sum(1+lv-mu^2-e^lv)/B
+ *                  (vaegan_code.py:75-78,114).  kl_out may be NULL.
+ * vg_reparam_bwd : dmu, dlogvar from dz and the KL term weighted by kl_weight (device scalar if kl_weight_dev). */
+int vg_reparam_fwd(const float* mu, const float* logvar, const float* eps, int batch, int nz, void* z, VgDType z_dt,
+                   float* kl_out, void* stream);
+int vg_reparam_bwd(const void* dz, VgDType dz_dt, const float* mu, const float* logvar, const float* eps, int batch,
+                   int nz, const float* kl_weight_dev, float kl_weight, float* dmu, float* dlogvar, void* stream);
+/* nn.BCELoss(mean) of probabilities p[n] against a constant target (vaegan_code.py:99-100,115); logs clamped at -100.
+ * loss_out (=, or += when accumulate) ; dp = weight * dL/dp (may be NULL). */
+int vg_bce(const float* p, int n, float target, float weight, float* loss_out, int accumulate, float* dp,
+           void* stream);
+/* nn.MSELoss(mean)(a, b) (vaegan_code.py:113; also the Dis_l feature-matching form of README.md:11-14 when a, b are
+ * discriminator features).  grad_out = weight*2(a-b)/n (+ grad_in if given); grad pointers may be NULL. */
+size_t vg_mse_workspace_bytes(void);
+int vg_mse(const float* a, const float* b, long long n, float weight, const float* grad_in, float* grad_out,
+           float* loss_out, void* ws, size_t ws_bytes, void* stream);
+/* total = recon + w_kl*kl + w_adv*adv  (vaegan_code.py:117); w_kl read from the device if w_kl_dev != NULL. */
+int vg_total_loss(const float* recon, const float* kl, const float* adv, const float* w_kl_dev, float w_kl,
+                  float w_adv, float* total, void* stream);
+/* torch.optim.Adam.step (vaegan_code.py:42-44,105,134-135) over one flat fp32 buffer; *step_dev is incremented
+ * first and drives the bias corrections, so the call can be replayed from a CUDA graph.  g is multiplied by
+ * grad_scale (1/world_size under data parallelism). */
+int vg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, long long* step_dev, float grad_scale, void* stream);
+/* Standard normal noise (torch.randn_like, vaegan_code.py:77,91,92): Philox4x32-10 + Box-Muller, keyed by
+ * (seed, *offset_dev, stream_id); *offset_dev is incremented after the launch when given. */
+int vg_randn(float* out, long long n, unsigned long long seed, unsigned long long* offset_dev,
+             unsigned long long stream_id, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

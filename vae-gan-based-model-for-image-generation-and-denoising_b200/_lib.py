@@ -1,0 +1,99 @@
+"""ctypes binding of libvaegan_b200.so (the C-ABI declared in include/vaegan_b200.h).
+
+The library is the product: if it is missing or the device is not sm_100 every call raises - there is no
+PyTorch / CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_ulonglong,
+                    c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvaegan_b200.so")
+
+VG_OK = 0
+VG_F32, VG_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+class VgConvGeom(Structure):
+    _fields_ = [("batch", c_int32), ("big_h", c_int32), ("big_w", c_int32), ("big_c", c_int32),
+                ("small_h", c_int32), ("small_w", c_int32), ("small_c", c_int32),
+                ("kernel", c_int32), ("stride", c_int32), ("pad", c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
+_G = POINTER(VgConvGeom)
+_P = c_void_p
+PROTOTYPES = {
+    "vg_last_error": (c_char_p, []),
+    "vg_version": (c_int, []),
+    "vg_device_check": (c_int, []),
+    "vg_pack_weights_bf16": (c_int, [_G, _P, _P, _P, _P]),
+    "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P]),
+    "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),
+    "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P]),
+    "vg_reduce_workspace_bytes": (c_size_t, [c_longlong, c_int]),
+    "vg_bn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int]),
+    "vg_bn_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,
+                                c_size_t, _P]),
+    "vg_bn_eval_coeffs": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P]),
+    "vg_scale_shift_act": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_int, c_float, _P, c_int, _P]),
+    "vg_bn_act_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,
+                              c_size_t, _P]),
+    "vg_act_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, c_float, _P, c_int, _P]),
+    "vg_colsum": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_size_t, _P]),
+    "vg_nchw_to_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    "vg_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
+    "vg_reparam_fwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),
+    "vg_reparam_bwd": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_float, _P, _P, _P]),
+    "vg_bce": (c_int, [_P, c_int, c_float, c_float, _P, c_int, _P, _P]),
+    "vg_mse_workspace_bytes": (c_size_t, []),
+    "vg_mse": (c_int, [_P, _P, c_longlong, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "vg_total_loss": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P]),
+    "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, _P, c_float, _P]),
+    "vg_randn": (c_int, [_P, c_longlong, c_ulonglong, _P, c_ulonglong, _P]),
+}
+
+_lib = None
+
+
+class VaeganB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built - run `make` / __graft_entry__.build()."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise VaeganB200Error(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run `make` at the repo root). "
+            "This package has no fallback path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().vg_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != VG_OK:
+        raise VaeganB200Error(f"{what} failed ({rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise RuntimeError (like the reference's torch ops) on failure."""
+    rc = getattr(load(), name)(*args)
+    if rc != VG_OK:
+        raise VaeganB200Error(f"{name} failed ({rc}): {last_error()}")

@@ -1,0 +1,598 @@
+// HBM-bound kernels around the convolutions: BatchNorm (train statistics, apply, backward), activations,
+// NCHW<->NHWC edge conversions, per-channel column sums.  All vectorised 16 B per thread access, fp32 math,
+// two-stage deterministic reductions (per-block partials -> fp64 finalize), no atomics.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 4;
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+    static constexpr int N = 4;
+    __device__ static void load(const float* p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+    switch (act) {
+        case VG_ACT_RELU: return z > 0.f ? z : 0.f;
+        case VG_ACT_LEAKY: return z > 0.f ? z : z * slope;
+        case VG_ACT_TANH: return tanhf(z);
+        case VG_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+        default: return z;
+    }
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+    switch (act) {
+        case VG_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case VG_ACT_LEAKY: return z > 0.f ? 1.f : slope;
+        case VG_ACT_TANH: { const float t = tanhf(z); return 1.f - t * t; }
+        case VG_ACT_SIGMOID: { const float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
+        default: return 1.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel reductions over the rows of an NHWC [rows][C] tensor.
+//   MODE 0: (sum x, sum x^2)                              -> BatchNorm training statistics
+//   MODE 1: (sum dz, sum dz*xhat), dz = dy*act'(x*scale+shift), xhat = (x-mean)*rstd   -> BatchNorm backward
+//   MODE 2: (sum x, unused)                               -> bias gradient
+// Block b reduces rows [b*rows_per_block, ...) and writes partial[b][0..1][C].
+// ------------------------------------------------------------------------------------------------
+struct ReduceArgs {
+    const void* x;
+    const void* dy;
+    const float *scale, *shift, *mean, *rstd;
+    long long rows;
+    int C;
+    long long rows_per_block;
+    int act;
+    float slope;
+    float* partial;
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceArgs a) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float red[kThreads][2 * V + 1];
+    const int tpr = a.C / V;                       // vectors per row (power of two)
+    const int lanes = tpr < kThreads ? tpr : kThreads;
+    const int rows_per_iter = kThreads / lanes;
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    const long long r0 = blockIdx.x * a.rows_per_block;
+    const long long r1 = min(a.rows, r0 + a.rows_per_block);
+    const T* x = static_cast<const T*>(a.x);
+    const T* dy = static_cast<const T*>(a.dy);
+    float* out = a.partial + static_cast<long long>(blockIdx.x) * 2 * a.C;
+
+    for (int cg = 0; cg < tpr / lanes; ++cg) {
+        const int c0 = (cg * lanes + lane) * V;
+        float s0[V], s1[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0.f;
+        float sc[V], sh[V], mu[V], rs[V];
+        if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                sc[i] = a.scale ? a.scale[c0 + i] : 1.f;
+                sh[i] = a.shift ? a.shift[c0 + i] : 0.f;
+                mu[i] = a.mean[c0 + i];
+                rs[i] = a.rstd[c0 + i];
+            }
+        }
+        for (long long r = r0 + rsub; r < r1; r += rows_per_iter) {
+            float xv[V];
+            Vec<T>::load(x + r * a.C + c0, xv);
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+            } else if (MODE == 1) {
+                float dv[V];
+                Vec<T>::load(dy + r * a.C + c0, dv);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float z = fmaf(xv[i], sc[i], sh[i]);
+                    const float dz = dv[i] * act_grad(z, a.act, a.slope);
+                    s0[i] += dz;
+                    s1[i] = fmaf(dz, (xv[i] - mu[i]) * rs[i], s1[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) s0[i] += xv[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) { red[threadIdx.x][i] = s0[i]; red[threadIdx.x][V + i] = s1[i]; }
+        __syncthreads();
+        if (rsub == 0) {
+            for (int j = 1; j < rows_per_iter; ++j)
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    s0[i] += red[j * lanes + lane][i];
+                    s1[i] += red[j * lanes + lane][V + i];
+                }
+#pragma unroll
+            for (int i = 0; i < V; ++i) { out[c0 + i] = s0[i]; out[a.C + c0 + i] = s1[i]; }
+        }
+        __syncthreads();
+    }
+}
+
+struct ReducePlan {
+    int blocks;
+    long long rows_per_block;
+};
+ReducePlan plan_reduce(long long rows) {
+    ReducePlan p;
+    p.blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(kMaxBlocks, (rows + 31) / 32)));
+    p.rows_per_block = (rows + p.blocks - 1) / p.blocks;
+    p.blocks = static_cast<int>((rows + p.rows_per_block - 1) / p.rows_per_block);
+    return p;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int check_channels(VgDType dt, int C) {
+    const int V = dt == VG_BF16 ? 8 : 4;
+    if (C % V != 0 || !is_pow2(C / V))
+        return fail(VG_ERR_SHAPE, "channel count %d must be %d x a power of two for the per-channel kernels", C, V);
+    return VG_OK;
+}
+
+template <int MODE>
+int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
+    if (dt == VG_BF16) channel_reduce_kernel<__nv_bfloat16, MODE><<<blocks, kThreads, 0, st>>>(a);
+    else channel_reduce_kernel<float, MODE><<<blocks, kThreads, 0, st>>>(a);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+// ---- finalize kernels (one thread per channel; fp64 combination of the per-block partials)
+__global__ void bn_fwd_finalize_kernel(const float* partial, int blocks, int C, double n, const float* gamma,
+                                       const float* beta, float* running_mean, float* running_var,
+                                       long long* num_batches_tracked, float momentum, float eps, float* mean_out,
+                                       float* rstd_out, float* scale_out, float* shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < blocks; ++b) {
+        s += partial[static_cast<long long>(b) * 2 * C + c];
+        ss += partial[static_cast<long long>(b) * 2 * C + C + c];
+    }
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    mean_out[c] = static_cast<float>(mean);
+    rstd_out[c] = static_cast<float>(rstd);
+    const float scale = static_cast<float>(g * rstd);
+    scale_out[c] = scale;
+    shift_out[c] = static_cast<float>(bt - mean * g * rstd);
+    if (running_mean != nullptr) {
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                      int C, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = 1.f / sqrtf(rv[c] + eps);
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    scale[c] = g * rstd;
+    shift[c] = bt - rm[c] * g * rstd;
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* partial, int blocks, int C, double n, float* dgamma, float* dbeta,
+                                       float* c1, float* c2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, sx = 0.0;
+    for (int b = 0; b < blocks; ++b) {
+        s += partial[static_cast<long long>(b) * 2 * C + c];
+        sx += partial[static_cast<long long>(b) * 2 * C + C + c];
+    }
+    if (dbeta != nullptr) dbeta[c] += static_cast<float>(s);
+    if (dgamma != nullptr) dgamma[c] += static_cast<float>(sx);
+    c1[c] = static_cast<float>(s / n);
+    c2[c] = static_cast<float>(sx / n);
+}
+
+template <typename T>
+__global__ void colsum_generic_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (long long r = 0; r < rows; ++r) {
+        if constexpr (sizeof(T) == 4) s += x[r * C + c]; else s += __bfloat162float(x[r * C + c]);
+    }
+    out[c] += static_cast<float>(s);
+}
+
+__global__ void colsum_finalize_kernel(const float* partial, int blocks, int C, float* out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) s += partial[static_cast<long long>(b) * 2 * C + c];
+    out[c] += static_cast<float>(s);
+}
+
+// ---- elementwise passes
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads) scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+                                                                  long long n, int C, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int act, float slope) {
+    // generic scalar path (used for tiny tensors such as the [B] discriminator logits)
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        float v;
+        if constexpr (sizeof(TI) == 4) v = x[i]; else v = __bfloat162float(x[i]);
+        v = fmaf(v, scale ? scale[c] : 1.f, shift ? shift[c] : 0.f);
+        v = act_fwd(v, act, slope);
+        if constexpr (sizeof(TO) == 4) y[i] = v; else y[i] = __float2bfloat16_rn(v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) scale_shift_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                      long long nvec, int C,
+                                                                      const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, int act,
+                                                                      float slope) {
+    constexpr int V = Vec<T>::N;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>((i * V) % C);
+        float v[V];
+        Vec<T>::load(x + i * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float z = fmaf(v[j], scale ? __ldg(scale + c0 + j) : 1.f, shift ? __ldg(shift + c0 + j) : 0.f);
+            v[j] = act_fwd(z, act, slope);
+        }
+        Vec<T>::store(y + i * V, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                   T* __restrict__ dx, long long nvec, int C,
+                                                                   const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd,
+                                                                   const float* __restrict__ c1,
+                                                                   const float* __restrict__ c2, int act, float slope) {
+    constexpr int V = Vec<T>::N;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>((i * V) % C);
+        float xv[V], dv[V];
+        Vec<T>::load(x + i * V, xv);
+        Vec<T>::load(dy + i * V, dv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int c = c0 + j;
+            const float sc = __ldg(scale + c);
+            const float z = fmaf(xv[j], sc, __ldg(shift + c));
+            const float dz = dv[j] * act_grad(z, act, slope);
+            const float xhat = (xv[j] - __ldg(mean + c)) * __ldg(rstd + c);
+            dv[j] = sc * (dz - __ldg(c1 + c) - xhat * __ldg(c2 + c));
+        }
+        Vec<T>::store(dx + i * V, dv);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads) act_bwd_kernel(const TI* __restrict__ dy, const TI* __restrict__ x,
+                                                          TO* __restrict__ dx, long long n, int act, float slope) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float d, z;
+        if constexpr (sizeof(TI) == 4) { d = dy[i]; z = x[i]; }
+        else { d = __bfloat162float(dy[i]); z = __bfloat162float(x[i]); }
+        const float v = d * act_grad(z, act, slope);
+        if constexpr (sizeof(TO) == 4) dx[i] = v; else dx[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- NCHW fp32 <-> NHWC T at the module edges.  One thread per (b, h, w) pixel: reads/writes of the NCHW side are
+// coalesced along w; the NHWC side is C contiguous elements per thread.
+//   mode 0: dst = src                         mode 1: dst = clamp?(src + sigma * aux)
+//   mode 2: dst = src * (1 - aux^2)           (tanh backward; aux = tanh output, NCHW)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) nchw_to_nhwc_kernel(const float* __restrict__ src,
+                                                               const float* __restrict__ aux, T* __restrict__ dst,
+                                                               int B, int C, long long HW, int mode, float sigma,
+                                                               int clamp) {
+    const long long total = static_cast<long long>(B) * HW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / HW, p = i - b * HW;
+        for (int c = 0; c < C; ++c) {
+            const long long s = (b * C + c) * HW + p;
+            float v = src[s];
+            if (mode == 1) {
+                v = fmaf(sigma, aux[s], v);
+                if (clamp) v = fminf(1.f, fmaxf(-1.f, v));
+            } else if (mode == 2) {
+                const float y = aux[s];
+                v *= (1.f - y * y);
+            }
+            if constexpr (sizeof(T) == 4) dst[i * C + c] = v; else dst[i * C + c] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst,
+                                                               int B, int C, long long HW, int act, float slope) {
+    const long long total = static_cast<long long>(B) * HW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / HW, p = i - b * HW;
+        for (int c = 0; c < C; ++c) {
+            float v;
+            if constexpr (sizeof(T) == 4) v = src[i * C + c]; else v = __bfloat162float(src[i * C + c]);
+            dst[(b * C + c) * HW + p] = act_fwd(v, act, slope);
+        }
+    }
+}
+
+int grid_for(long long n) {
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(148 * 8, (n + kThreads - 1) / kThreads)));
+}
+
+}  // namespace
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" size_t vg_reduce_workspace_bytes(long long rows, int channels) {
+    const ReducePlan p = plan_reduce(rows);
+    return static_cast<size_t>(p.blocks) * 2 * channels * sizeof(float);
+}
+
+extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               long long* num_batches_tracked, float momentum, float eps, float* mean_out,
+                               float* rstd_out, float* scale_out, float* shift_out, float* ws, size_t ws_bytes,
+                               void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (x == nullptr || mean_out == nullptr || rstd_out == nullptr || scale_out == nullptr || shift_out == nullptr)
+        return fail(VG_ERR_ARG, "bn_train_fwd: null pointer");
+    rc = check_channels(dt, C);
+    if (rc != VG_OK) return rc;
+    if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
+    const ReducePlan p = plan_reduce(rows);
+    if (ws == nullptr || ws_bytes < vg_reduce_workspace_bytes(rows, C))
+        return fail(VG_ERR_WORKSPACE, "bn_train_fwd: workspace too small");
+    ReduceArgs a{};
+    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
+    rc = launch_reduce<0>(dt, a, p.blocks, as_stream(stream));
+    if (rc != VG_OK) return rc;
+    bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+        ws, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
+        momentum, eps, mean_out, rstd_out, scale_out, shift_out);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, float eps, int C, float* scale_out, float* shift_out,
+                                 void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps,
+                                                                          C, scale_out, shift_out);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_scale_shift_act(const void* x, VgDType in_dt, long long rows, int C, const float* scale,
+                                  const float* shift, VgAct act, float slope, void* y, VgDType out_dt, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (x == nullptr || y == nullptr) return fail(VG_ERR_ARG, "scale_shift_act: null pointer");
+    const long long n = rows * C;
+    cudaStream_t st = as_stream(stream);
+    const int V = in_dt == VG_BF16 ? 8 : 4;
+    if (in_dt == out_dt && C % V == 0) {
+        const long long nvec = n / V;
+        if (in_dt == VG_BF16)
+            scale_shift_act_vec_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, scale, shift, act, slope);
+        else
+            scale_shift_act_vec_kernel<float><<<grid_for(nvec), kThreads, 0, st>>>(
+                static_cast<const float*>(x), static_cast<float*>(y), nvec, C, scale, shift, act, slope);
+    } else if (in_dt == VG_BF16 && out_dt == VG_BF16) {
+        scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n), kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
+    } else if (in_dt == VG_BF16 && out_dt == VG_F32) {
+        scale_shift_act_kernel<__nv_bfloat16, float><<<grid_for(n), kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
+    } else if (in_dt == VG_F32 && out_dt == VG_BF16) {
+        scale_shift_act_kernel<float, __nv_bfloat16><<<grid_for(n), kThreads, 0, st>>>(
+            static_cast<const float*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
+    } else {
+        scale_shift_act_kernel<float, float><<<grid_for(n), kThreads, 0, st>>>(
+            static_cast<const float*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
+    }
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long long rows, int C, const float* scale,
+                             const float* shift, const float* mean, const float* rstd, VgAct act, float slope,
+                             float* dgamma, float* dbeta, void* dx, float* ws, size_t ws_bytes, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dy == nullptr || x == nullptr || dx == nullptr || scale == nullptr || shift == nullptr || mean == nullptr ||
+        rstd == nullptr)
+        return fail(VG_ERR_ARG, "bn_act_bwd: null pointer");
+    rc = check_channels(dt, C);
+    if (rc != VG_OK) return rc;
+    const ReducePlan p = plan_reduce(rows);
+    const size_t need = vg_reduce_workspace_bytes(rows, C) + 2 * static_cast<size_t>(C) * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) return fail(VG_ERR_WORKSPACE, "bn_act_bwd: workspace too small");
+    float* c1 = ws + static_cast<size_t>(p.blocks) * 2 * C;
+    float* c2 = c1 + C;
+    cudaStream_t st = as_stream(stream);
+    ReduceArgs a{};
+    a.x = x; a.dy = dy; a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd;
+    a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.act = act; a.slope = slope; a.partial = ws;
+    rc = launch_reduce<1>(dt, a, p.blocks, st);
+    if (rc != VG_OK) return rc;
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, p.blocks, C, static_cast<double>(rows), dgamma, dbeta,
+                                                           c1, c2);
+    VG_CUDA(cudaGetLastError());
+    const int V = dt == VG_BF16 ? 8 : 4;
+    const long long nvec = rows * C / V;
+    if (dt == VG_BF16)
+        bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
+            static_cast<__nv_bfloat16*>(dx), nvec, C, scale, shift, mean, rstd, c1, c2, act, slope);
+    else
+        bn_act_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, st>>>(
+            static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
+            mean, rstd, c1, c2, act, slope);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" size_t vg_bn_bwd_workspace_bytes(long long rows, int channels) {
+    return vg_reduce_workspace_bytes(rows, channels) + 2 * static_cast<size_t>(channels) * sizeof(float);
+}
+
+extern "C" int vg_act_bwd(const void* dy, const void* x, VgDType in_dt, long long n, VgAct act, float slope, void* dx,
+                          VgDType out_dt, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dy == nullptr || x == nullptr || dx == nullptr) return fail(VG_ERR_ARG, "act_bwd: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const int g = grid_for(n);
+    if (in_dt == VG_BF16 && out_dt == VG_BF16)
+        act_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
+            n, act, slope);
+    else if (in_dt == VG_F32 && out_dt == VG_BF16)
+        act_bwd_kernel<float, __nv_bfloat16><<<g, kThreads, 0, st>>>(static_cast<const float*>(dy),
+                                                                     static_cast<const float*>(x),
+                                                                     static_cast<__nv_bfloat16*>(dx), n, act, slope);
+    else if (in_dt == VG_F32 && out_dt == VG_F32)
+        act_bwd_kernel<float, float><<<g, kThreads, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
+                                                             static_cast<float*>(dx), n, act, slope);
+    else
+        act_bwd_kernel<__nv_bfloat16, float><<<g, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                                     static_cast<const __nv_bfloat16*>(x),
+                                                                     static_cast<float*>(dx), n, act, slope);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float* out, float* ws, size_t ws_bytes,
+                         void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (x == nullptr || out == nullptr) return fail(VG_ERR_ARG, "colsum: null pointer");
+    {
+        const int V = dt == VG_BF16 ? 8 : 4;
+        if (C % V != 0 || !is_pow2(C / V)) {  // odd channel counts (e.g. latent_dim 100): one thread per channel
+            if (dt == VG_BF16)
+                colsum_generic_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+                    static_cast<const __nv_bfloat16*>(x), rows, C, out);
+            else
+                colsum_generic_kernel<float><<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+                    static_cast<const float*>(x), rows, C, out);
+            VG_CUDA(cudaGetLastError());
+            return VG_OK;
+        }
+    }
+    const ReducePlan p = plan_reduce(rows);
+    if (ws == nullptr || ws_bytes < vg_reduce_workspace_bytes(rows, C))
+        return fail(VG_ERR_WORKSPACE, "colsum: workspace too small");
+    ReduceArgs a{};
+    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
+    rc = launch_reduce<2>(dt, a, p.blocks, as_stream(stream));
+    if (rc != VG_OK) return rc;
+    colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, p.blocks, C, out);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int B, int C, int H, int W,
+                               int mode, float sigma, int clamp, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr || (mode != 0 && aux == nullptr))
+        return fail(VG_ERR_ARG, "nchw_to_nhwc: null pointer");
+    const long long HW = static_cast<long long>(H) * W;
+    const int g = grid_for(B * HW);
+    if (dt == VG_BF16)
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
+            src, aux, static_cast<__nv_bfloat16*>(dst), B, C, HW, mode, sigma, clamp);
+    else
+        nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, HW,
+                                                                          mode, sigma, clamp);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}
+
+extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, float* dst, int B, int C, int H, int W, VgAct act,
+                               float slope, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr) return fail(VG_ERR_ARG, "nhwc_to_nchw: null pointer");
+    const long long HW = static_cast<long long>(H) * W;
+    const int g = grid_for(B * HW);
+    if (dt == VG_BF16)
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
+            static_cast<const __nv_bfloat16*>(src), dst, B, C, HW, act, slope);
+    else
+        nhwc_to_nchw_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(static_cast<const float*>(src), dst, B, C, HW,
+                                                                          act, slope);
+    VG_CUDA(cudaGetLastError());
+    return VG_OK;
+}

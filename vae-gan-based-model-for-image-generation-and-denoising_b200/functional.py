@@ -1,0 +1,345 @@
+"""Tensor-level wrappers over the C-ABI and the autograd glue that lets the reference's nn.Module call sites
+(encoder(x), decoder(z), discriminator(x), loss.backward()) run on the sm_100a kernels.
+
+PyTorch is used for device memory, streams and the autograd tape only; every arithmetic pass below is a kernel of
+libvaegan_b200.so.  Internal activations are NHWC tensors `[B, H, W, C]` in the precision's dtype.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, VG_BF16, VG_F32, VgConvGeom, call)
+
+_DT = {torch.float32: VG_F32, torch.bfloat16: VG_BF16}
+PRECISION_DTYPE = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise _lib.VaeganB200Error(f"{what}: tensor is on {t.device}; vaegan_b200 runs on sm_100 CUDA devices only "
+                                   "(no CPU fallback)")
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class ConvSpec:
+    """One reference conv layer.  kind 'down' = nn.Conv2d (and nn.Linear as a full-extent conv), 'up' =
+    nn.ConvTranspose2d.  `small_c` / `big_c` follow include/vaegan_b200.h."""
+    kind: str
+    small_c: int
+    big_c: int
+    kernel: int
+    stride: int
+    pad: int
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        k, s, p = self.kernel, self.stride, self.pad
+        if self.kind == "down":
+            if h + 2 * p < k or w + 2 * p < k:
+                raise RuntimeError(f"Calculated padded input size per channel: ({h + 2 * p} x {w + 2 * p}). "
+                                   f"Kernel size: ({k} x {k}). Kernel size can't be greater than actual input size")
+            return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        return (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+
+    def geom(self, batch: int, in_h: int, in_w: int) -> VgConvGeom:
+        oh, ow = self.out_hw(in_h, in_w)
+        if self.kind == "down":
+            return VgConvGeom(batch, in_h, in_w, self.big_c, oh, ow, self.small_c, self.kernel, self.stride, self.pad)
+        return VgConvGeom(batch, oh, ow, self.big_c, in_h, in_w, self.small_c, self.kernel, self.stride, self.pad)
+
+
+# --------------------------------------------------------------------------------------------- raw ops
+def pack_weights(w: torch.Tensor, g: VgConvGeom) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 master [small_c, big_c, k, k] -> (wd[tap, small_c, big_c], wu[tap, big_c, small_c]) bf16."""
+    kk = g.kernel * g.kernel
+    wd = torch.empty((kk, g.small_c, g.big_c), dtype=torch.bfloat16, device=w.device)
+    wu = torch.empty((kk, g.big_c, g.small_c), dtype=torch.bfloat16, device=w.device)
+    call("vg_pack_weights_bf16", ctypes.byref(g), _p(w), _p(wd), _p(wu), _stream())
+    return wd, wu
+
+
+def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[torch.Tensor] = None,
+              out_f32: bool = False) -> torch.Tensor:
+    dt = big.dtype
+    out = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=torch.float32 if out_f32 else dt,
+                      device=big.device)
+    call("vg_conv_down", ctypes.byref(g), _DT[dt], _p(big), _p(w), _p(bias), _p(out), int(out_f32), _stream())
+    return out
+
+
+def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom) -> torch.Tensor:
+    out = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
+    call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(out), _stream())
+    return out
+
+
+def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[small_c, big_c, k, k] (+)= wgrad; a fresh zeroed buffer is created when `dw` is None."""
+    if dw is None:
+        dw = torch.zeros((g.small_c, g.big_c, g.kernel, g.kernel), dtype=torch.float32, device=small.device)
+    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _stream())
+    return dw
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=device)
+
+
+def bn_train_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float,
+                 eps: float):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    stats = torch.empty((4, C), dtype=torch.float32, device=x.device)  # mean, rstd, scale, shift
+    nbytes = _lib.load().vg_reduce_workspace_bytes(rows, C)
+    ws = _ws(nbytes, x.device)
+    call("vg_bn_train_fwd", _p(x), _DT[x.dtype], rows, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         _p(num_batches_tracked), float(momentum), float(eps), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+         _p(ws), nbytes, _stream())
+    return stats
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps: float):
+    C = running_mean.numel()
+    stats = torch.zeros((4, C), dtype=torch.float32, device=running_mean.device)
+    call("vg_bn_eval_coeffs", _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), C, _p(stats[2]),
+         _p(stats[3]), _stream())
+    return stats
+
+
+def scale_shift_act(x: torch.Tensor, scale, shift, act: int, slope: float, out_dtype=None) -> torch.Tensor:
+    out_dtype = out_dtype or x.dtype
+    C = x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    call("vg_scale_shift_act", _p(x), _DT[x.dtype], x.numel() // C, C, _p(scale), _p(shift), act, float(slope), _p(y),
+         _DT[out_dtype], _stream())
+    return y
+
+
+def bn_act_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act: int, slope: float, dgamma, dbeta):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    nbytes = _lib.load().vg_bn_bwd_workspace_bytes(rows, C)
+    ws = _ws(nbytes, x.device)
+    call("vg_bn_act_bwd", _p(dy), _p(x), _DT[x.dtype], rows, C, _p(stats[2]), _p(stats[3]), _p(stats[0]), _p(stats[1]),
+         act, float(slope), _p(dgamma), _p(dbeta), _p(dx), _p(ws), nbytes, _stream())
+    return dx
+
+
+def act_bwd(dy: torch.Tensor, x: torch.Tensor, act: int, slope: float, out_dtype=None) -> torch.Tensor:
+    out_dtype = out_dtype or x.dtype
+    dx = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    call("vg_act_bwd", _p(dy), _p(x), _DT[x.dtype], x.numel(), act, float(slope), _p(dx), _DT[out_dtype], _stream())
+    return dx
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
+    C = x.shape[-1]
+    rows = x.numel() // C
+    nbytes = _lib.load().vg_reduce_workspace_bytes(rows, C)
+    ws = _ws(nbytes, x.device)
+    call("vg_colsum", _p(x), _DT[x.dtype], rows, C, _p(out), _p(ws), nbytes, _stream())
+
+
+def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, mode: int = 0, sigma: float = 0.0,
+                 clamp: bool = False) -> torch.Tensor:
+    B, C, H, W = src.shape
+    dst = torch.empty((B, H, W, C), dtype=dtype, device=src.device)
+    call("vg_nchw_to_nhwc", _p(src), _p(aux), _p(dst), _DT[dtype], B, C, H, W, mode, float(sigma), int(clamp),
+         _stream())
+    return dst
+
+
+def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0) -> torch.Tensor:
+    B, H, W, C = src.shape
+    dst = torch.empty((B, C, H, W), dtype=torch.float32, device=src.device)
+    call("vg_nhwc_to_nchw", _p(src), _DT[src.dtype], _p(dst), B, C, H, W, act, float(slope), _stream())
+    return dst
+
+
+# --------------------------------------------------------------------------------------------- weight cache
+class PackedWeights:
+    """bf16 K-major copies of one fp32 master weight, refreshed when the master changes.  L1 (drop-in modules):
+    staleness is detected through the parameter's autograd version counter (optimizer.step() bumps it);
+    L2 (fused step) invalidates explicitly after its own Adam kernel."""
+
+    def __init__(self):
+        self.version = None
+        self.key = None
+        self.wd = None
+        self.wu = None
+
+    def invalidate(self):
+        self.version = None
+
+    def get(self, w: torch.Tensor, g: VgConvGeom):
+        key = (w.data_ptr(), g.small_c, g.big_c, g.kernel)
+        if self.version != w._version or self.key != key:
+            self.wd, self.wu = pack_weights(w.detach(), g)
+            self.version, self.key = w._version, key
+        return self.wd, self.wu
+
+
+# --------------------------------------------------------------------------------------------- autograd glue
+def _accumulate_or_return(param: Optional[torch.Tensor], grad: Optional[torch.Tensor]):
+    """Megatron-style fused gradient accumulation: a parameter carrying `.main_grad` receives its gradient there
+    (the kernels already accumulated into it) and autograd sees None."""
+    return None if (param is not None and getattr(param, "main_grad", None) is not None) else grad
+
+
+class ConvLayerFn(torch.autograd.Function):
+    """conv / convT (+bias) -> [BatchNorm2d, training or eval] -> activation, on NHWC tensors.
+
+    Replaces, per layer, ConvBlock.forward (main_vae.py:27-31) and the (ConvT|Conv, BN, ReLU|LeakyReLU) triples of
+    Generator.main / Discriminator.main (gan_code.py:19-51, 59-86) together with their autograd backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, spec: ConvSpec, act: int, slope: float, bn, training: bool,
+                cache: PackedWeights, out_f32: bool):
+        _require_cuda(x, "ConvLayerFn")
+        x = _contig(x)
+        B, H, W, _ = x.shape
+        g = spec.geom(B, H, W)
+        if x.dtype == torch.bfloat16:
+            wd, wu = cache.get(weight, g)
+            w_fwd = wd if spec.kind == "down" else wu
+        else:
+            w_fwd = _contig(weight.detach())
+        if spec.kind == "down":
+            raw = conv_down(x, w_fwd, g, bias.detach() if bias is not None else None, out_f32=out_f32)
+        else:
+            raw = conv_up(x, w_fwd, g)
+        stats = None
+        if bn is not None:
+            if training:
+                rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats \
+                    else (None, None, None)
+                # F.batch_norm semantics: momentum=None means cumulative average - the reference never uses it
+                stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+            else:
+                stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
+            y = scale_shift_act(raw, stats[2], stats[3], act, slope)
+        elif act != ACT_NONE:
+            y = scale_shift_act(raw, None, None, act, slope)
+        else:
+            y = raw
+        ctx.spec, ctx.act, ctx.slope, ctx.g = spec, act, slope, g
+        ctx.has_bn, ctx.bn_training, ctx.cache, ctx.out_f32 = bn is not None, training, cache, out_f32
+        ctx.params = (weight, bias, gamma, beta)
+        ctx.save_for_backward(x, raw, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, stats = ctx.saved_tensors
+        weight, bias, gamma, beta = ctx.params
+        spec, g, act, slope = ctx.spec, ctx.g, ctx.act, ctx.slope
+        dy = _contig(dy)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dgamma = dbeta = dbias = dw = dx = None
+
+        # ---- through activation (+ BatchNorm) to the gradient of the raw conv output
+        if ctx.has_bn:
+            if ctx.bn_training:
+                want_affine = ctx.needs_input_grad[3]
+                if want_affine:
+                    dgamma = getattr(gamma, "main_grad", None)
+                    dbeta = getattr(beta, "main_grad", None)
+                    if dgamma is None:
+                        dgamma = torch.zeros_like(gamma, dtype=torch.float32)
+                        dbeta = torch.zeros_like(beta, dtype=torch.float32)
+                d_raw = bn_act_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
+            else:
+                raise _lib.VaeganB200Error("backward through eval-mode BatchNorm is not part of the VAE-GAN step")
+        elif act != ACT_NONE:
+            d_raw = act_bwd(dy, raw, act, slope, out_dtype=x.dtype)
+        else:
+            d_raw = dy if dy.dtype == x.dtype else scale_shift_act(dy, None, None, ACT_NONE, 0.0, out_dtype=x.dtype)
+
+        # ---- bias, weight and input gradients
+        if bias is not None and ctx.needs_input_grad[2]:
+            dbias = getattr(bias, "main_grad", None)
+            if dbias is None:
+                dbias = torch.zeros_like(bias, dtype=torch.float32)
+            colsum(d_raw, dbias)
+        small, big = (d_raw, x) if spec.kind == "down" else (x, d_raw)
+        if need_w:
+            dw = conv_wgrad(small, big, g, getattr(weight, "main_grad", None))
+            dw = dw.view(weight.shape)
+        if need_x:
+            if x.dtype == torch.bfloat16:
+                wd, wu = ctx.cache.get(weight, g)
+                w_bwd = wu if spec.kind == "down" else wd
+            else:
+                w_bwd = _contig(weight.detach())
+            dx = conv_up(d_raw, w_bwd, g) if spec.kind == "down" else conv_down(d_raw, w_bwd, g)
+        return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
+                _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
+                None, None, None, None, None, None, None)
+
+
+class ToNHWCFn(torch.autograd.Function):
+    """fp32 NCHW module input -> internal NHWC activation (and the reverse for its gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x, "ToNHWCFn")
+        if x.dtype != torch.float32:
+            raise _lib.VaeganB200Error(f"module inputs must be float32 (got {x.dtype}), like the reference's loaders")
+        return nchw_to_nhwc(_contig(x), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return nhwc_to_nchw(_contig(dy)), None
+
+
+class ToNCHWActFn(torch.autograd.Function):
+    """internal NHWC activation -> fp32 NCHW module output with the final Tanh / no-op fused in."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        y = nhwc_to_nchw(_contig(x), act)
+        ctx.act, ctx.dtype = act, x.dtype
+        ctx.save_for_backward(y if act == ACT_TANH else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _contig(dy)
+        if ctx.act == ACT_TANH:
+            return nchw_to_nhwc(dy, ctx.dtype, aux=y, mode=2), None
+        return nchw_to_nhwc(dy, ctx.dtype), None
+
+
+class PointwiseActFn(torch.autograd.Function):
+    """Stand-alone activation on an fp32 tensor (the discriminator's final Sigmoid, gan_code.py:85)."""
+
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        x = _contig(x)
+        ctx.act, ctx.slope = act, slope
+        ctx.save_for_backward(x)
+        return scale_shift_act(x.view(-1, 1), None, None, act, slope).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return act_bwd(_contig(dy), x, ctx.act, ctx.slope), None, None
