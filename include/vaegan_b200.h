@@ -61,6 +61,8 @@ const char* vg_last_error(void);
 int vg_version(void);
 /* 0 when the current device is sm_100 and the kernels can run, VG_ERR_ARCH / VG_ERR_CUDA otherwise. */
 int vg_device_check(void);
+/* kernels launched by this library in this process so far (host-side counter). */
+long long vg_launch_count(void);
 
 /* ---- weight packing (bf16 tensor-core path) ---------------------------------------------------------------
  * fp32 master w[small_c][big_c][k][k]  ->  wd[tap][small_c][big_c]  (operand of `down`)

@@ -1,0 +1,242 @@
+"""GPU: every C-ABI kernel family through ctypes (vaegan_b200.functional) against torch CPU fp32 references of
+the same op.  fp32 path: 1e-5..1e-4 relative; bf16 path: operands are bf16-representable so only the output rounding
+(2^-9 relative) separates the tensor-core result from the reference."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _fn():
+    from importlib import import_module
+    import vaegan_b200  # noqa: F401
+    return import_module("vaegan_b200.functional")
+
+
+def _nhwc(t):      # NCHW cpu -> NHWC contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # kind, B, H, W, Cin, Cout, k, s, p
+    ("down", 4, 16, 16, 64, 128, 4, 2, 1),      # discriminator stage
+    ("down", 3, 31, 31, 32, 64, 4, 2, 0),       # encoder stage, odd extents, SWIZZLE_64B operands
+    ("down", 5, 64, 64, 3, 64, 4, 2, 1),        # image layer (CUDA-core path in both modes)
+    ("down", 6, 2, 2, 256, 128, 2, 1, 0),       # fc head as a full-extent conv
+    ("down", 8, 4, 4, 512, 1, 4, 1, 0),         # final discriminator conv (gemv)
+    ("up", 4, 8, 8, 128, 64, 4, 2, 1),          # generator stage (4-phase)
+    ("up", 16, 1, 1, 128, 256, 4, 1, 0),        # first generator layer (dense GEMM)
+    ("up", 2, 16, 16, 64, 3, 3, 1, 1),          # last generator layer k3
+    ("up", 130, 4, 4, 256, 128, 4, 2, 1),       # batch larger than one M tile
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-k{c[6]}s{c[7]}p{c[8]}")
+def test_conv_fwd_dgrad_wgrad(case, prec):
+    fn = _fn()
+    kind, B, H, W, cin, cout, k, s, p = case
+    gen = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    rb = (lambda t: t.bfloat16().float()) if prec == "bf16" else (lambda t: t)
+    x = rb(torch.randn(B, cin, H, W, generator=gen))
+    if kind == "down":
+        w = rb(torch.randn(cout, cin, k, k, generator=gen) * 0.1)
+        spec = fn.ConvSpec("down", cout, cin, k, s, p)
+        y_ref = F.conv2d(x, w, None, s, p)
+    else:
+        w = rb(torch.randn(cin, cout, k, k, generator=gen) * 0.1)
+        spec = fn.ConvSpec("up", cin, cout, k, s, p)
+        y_ref = F.conv_transpose2d(x, w, None, s, p)
+    dy = rb(torch.randn(y_ref.shape, generator=gen))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    (F.conv2d(xr, wr, None, s, p) if kind == "down" else F.conv_transpose2d(xr, wr, None, s, p)).backward(dy)
+
+    dt = fn.PRECISION_DTYPE[prec]
+    g = spec.geom(B, H, W)
+    xd, dyd, wdv = _nhwc(x).cuda().to(dt), _nhwc(dy).cuda().to(dt), w.cuda()
+    if prec == "bf16":
+        wd, wu = fn.pack_weights(wdv, g)
+        w_fwd, w_bwd = (wd, wu) if kind == "down" else (wu, wd)
+    else:
+        w_fwd = w_bwd = wdv
+    if kind == "down":
+        y = fn.conv_down(xd, w_fwd, g)
+        dx = fn.conv_up(dyd, w_bwd, g)
+        dw = fn.conv_wgrad(dyd, xd, g)
+    else:
+        y = fn.conv_up(xd, w_fwd, g)
+        dx = fn.conv_down(dyd, w_bwd, g)
+        dw = fn.conv_wgrad(xd, dyd, g)
+    torch.cuda.synchronize()
+    tol_out = 1e-5 if prec == "fp32" else 6e-3      # bf16: output rounding only
+    assert rel_err(_nchw(y.float().cpu()), y_ref) < tol_out
+    assert rel_err(_nchw(dx.float().cpu()), xr.grad) < tol_out
+    assert rel_err(dw.cpu(), wr.grad) < 2e-5           # fp32 accumulate + fp32 output in both modes
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2), (2, 0.01)])
+@pytest.mark.parametrize("rows,C", [(4 * 31 * 31, 32), (7 * 4 * 4, 512), (2 * 64 * 64, 64), (3, 2048)])
+def test_batchnorm_act_fwd_bwd(rows, C, act, slope, prec):
+    fn = _fn()
+    gen = torch.Generator().manual_seed(rows + C)
+    dt = fn.PRECISION_DTYPE[prec]
+    rb = (lambda t: t.to(dt).float())
+    x = rb(torch.randn(rows, C, generator=gen) * 2 + 0.5)
+    dy = rb(torch.randn(rows, C, generator=gen))
+    gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen)
+    rm, rv = torch.randn(C, generator=gen), torch.rand(C, generator=gen) + 0.5
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    z = F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    y_ref = F.relu(z) if act == 1 else F.leaky_relu(z, slope)
+    y_ref.backward(dy)
+
+    xd = x.cuda().to(dt).view(1, 1, rows, C)
+    rmd, rvd, nbt = rm.cuda(), rv.cuda(), torch.zeros((), dtype=torch.int64, device="cuda")
+    stats = fn.bn_train_fwd(xd, gamma.cuda(), beta.cuda(), rmd, rvd, nbt, 0.1, 1e-5)
+    y = fn.scale_shift_act(xd, stats[2], stats[3], act, slope)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = fn.bn_act_bwd(dy.cuda().to(dt).view(1, 1, rows, C), xd, stats, act, slope, dg, db)
+    torch.cuda.synchronize()
+    out_tol = 1e-5 if prec == "fp32" else 6e-3
+    assert int(nbt) == 1
+    assert rel_err(rmd, rm_ref) < 1e-5 and rel_err(rvd, rv_ref) < 1e-5
+    assert rel_err(y.float().view(rows, C), y_ref) < out_tol
+    assert rel_err(dx.float().view(rows, C), xr.grad) < (2e-4 if prec == "fp32" else 1e-2) * (10 if rows < 16 else 1)
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+def test_bn_eval_and_single_value_error():
+    fn = _fn()
+    C = 64
+    g, b, rm, rv = (torch.rand(C) + 0.5, torch.randn(C), torch.randn(C), torch.rand(C) + 0.5)
+    x = torch.randn(10, C)
+    ref = F.batch_norm(x, rm, rv, g, b, False, 0.1, 1e-5)
+    st = fn.bn_eval_coeffs(g.cuda(), b.cuda(), rm.cuda(), rv.cuda(), 1e-5)
+    y = fn.scale_shift_act(x.cuda().view(1, 1, 10, C), st[2], st[3], 0, 0.0)
+    assert rel_err(y.view(10, C), ref) < 1e-5
+    with pytest.raises(RuntimeError, match="more than 1 value per channel"):
+        fn.bn_train_fwd(torch.zeros(1, 1, 1, C, device="cuda"), g.cuda(), b.cuda(), None, None, None, 0.1, 1e-5)
+
+
+def test_layout_edges_and_noise_modes():
+    fn = _fn()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 3, 20, 12, generator=gen) * 2 - 1
+    n = torch.randn(3, 3, 20, 12, generator=gen)
+    for dt in (torch.float32, torch.bfloat16):
+        a = fn.nchw_to_nhwc(x.cuda(), dt)
+        assert torch.equal(a.float().cpu(), _nhwc(x).to(dt).float())
+        b = fn.nchw_to_nhwc(x.cuda(), dt, aux=n.cuda(), mode=1, sigma=0.3, clamp=True)
+        assert rel_err(b.float(), _nhwc(torch.clamp(x + 0.3 * n, -1, 1)).to(dt).float()) < 1e-6
+        back = fn.nhwc_to_nchw(a, 3)      # tanh
+        assert rel_err(back, torch.tanh(x.to(dt).float())) < 1e-6
+        c = fn.nchw_to_nhwc(n.cuda(), dt, aux=back, mode=2)
+        assert rel_err(c.float(), _nhwc(n * (1 - torch.tanh(x.to(dt).float()) ** 2)).to(dt).float()) < 1e-5
+
+
+def test_reparam_kl_bce_mse_against_torch():
+    fn = _fn()
+    lib = __import__("vaegan_b200").load_library()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    B, nz = 12, 128
+    gen = torch.Generator().manual_seed(5)
+    mu = torch.randn(B, nz, generator=gen)
+    lv = torch.randn(B, nz, generator=gen) * 6          # some entries beyond the +-10 clamp
+    eps = torch.randn(B, nz, generator=gen)
+    dz = torch.randn(B, nz, generator=gen)
+    mur, lvr = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    lvc = torch.clamp(lvr, min=-10, max=10)
+    z_ref = mur + torch.exp(0.5 * lvc) * eps
+    kl_ref = -0.5 * torch.sum(1 + lvc - mur.pow(2) - lvc.exp()) / B
+    ((z_ref * dz).sum() + 0.07 * kl_ref).backward()
+    mud, lvd, epsd = mu.cuda(), lv.cuda(), eps.cuda()
+    z, kl = torch.empty(B, nz, device="cuda"), torch.zeros((), device="cuda")
+    assert lib.vg_reparam_fwd(P(mud), P(lvd), P(epsd), B, nz, P(z), 0, P(kl), None) == 0
+    dmu, dlv = torch.empty_like(mud), torch.empty_like(lvd)
+    assert lib.vg_reparam_bwd(P(dz.cuda()), 0, P(mud), P(lvd), P(epsd), B, nz, None, 0.07, P(dmu), P(dlv), None) == 0
+    assert rel_err(z, z_ref) < 1e-6 and abs(float(kl) - float(kl_ref)) < 1e-5 * abs(float(kl_ref))
+    assert rel_err(dmu, mur.grad) < 1e-5 and rel_err(dlv, lvr.grad) < 1e-5
+
+    p = torch.rand(B, generator=gen).clamp(1e-4, 1 - 1e-4)
+    p[0], p[1] = 0.0, 1.0                                  # log clamp at -100 (nn.BCELoss)
+    for target in (0.9, 0.1):
+        pr = p.clone().requires_grad_(True)
+        l_ref = F.binary_cross_entropy(pr, torch.full((B,), target))
+        (0.1 * l_ref).backward()
+        loss, dp = torch.zeros((), device="cuda"), torch.empty(B, device="cuda")
+        assert lib.vg_bce(P(p.cuda()), B, target, 0.1, P(loss), 0, P(dp), None) == 0
+        assert abs(float(loss) - float(l_ref)) < 1e-5 * abs(float(l_ref))
+        assert rel_err(dp[2:], pr.grad[2:]) < 1e-5
+
+    a, b = torch.randn(3, 3, 17, 19, generator=gen), torch.randn(3, 3, 17, 19, generator=gen)
+    gi = torch.randn(3, 3, 17, 19, generator=gen)
+    ar = a.clone().requires_grad_(True)
+    l_ref = F.mse_loss(ar, b)
+    l_ref.backward()
+    ws = torch.empty(lib.vg_mse_workspace_bytes() // 4, device="cuda")
+    loss, go = torch.zeros((), device="cuda"), torch.empty(a.shape, device="cuda")
+    assert lib.vg_mse(P(a.cuda()), P(b.cuda()), a.numel(), 1.0, P(gi.cuda()), P(go), P(loss), P(ws), ws.numel() * 4, None) == 0
+    assert abs(float(loss) - float(l_ref)) < 1e-6 * abs(float(l_ref))
+    assert rel_err(go, ar.grad + gi) < 1e-6
+
+
+def test_adam_matches_torch_optim():
+    lib = __import__("vaegan_b200").load_library()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    n = 10007
+    gen = torch.Generator().manual_seed(9)
+    p0 = torch.randn(n, generator=gen)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=2e-4)
+    pd, m, v = p0.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros((), dtype=torch.int64, device="cuda")
+    for it in range(5):
+        g = torch.randn(n, generator=gen) * (10.0 ** (it - 2))
+        pr.grad = g.clone()
+        opt.step()
+        assert lib.vg_adam_step(P(pd), P((2 * g).cuda()), P(m), P(v), n, 2e-4, 0.9, 0.999, 1e-8, P(step), 0.5, None) == 0
+    assert int(step) == 5
+    assert float((pd.cpu() - pr.detach()).abs().max()) < 1e-6      # |p| ~ 4: a couple of fp32 ulps
+    assert rel_err(m, opt.state[pr]["exp_avg"]) < 1e-6 and rel_err(v, opt.state[pr]["exp_avg_sq"]) < 1e-6
+
+
+def test_randn_statistics_and_streams():
+    lib = __import__("vaegan_b200").load_library()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    n = 1 << 20
+    a, b = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    off = torch.zeros((), dtype=torch.int64, device="cuda")
+    assert lib.vg_randn(P(a), n, 123, P(off), 1, None) == 0
+    assert lib.vg_randn(P(b), n, 123, P(off), 1, None) == 0
+    assert int(off) == 2 and not torch.equal(a, b)
+    for t in (a, b):
+        assert abs(float(t.mean())) < 5e-3 and abs(float(t.std()) - 1) < 5e-3
+        assert abs(float((t ** 4).mean()) - 3.0) < 0.05
+    c = torch.empty(n, device="cuda")
+    off2 = torch.zeros((), dtype=torch.int64, device="cuda")
+    assert lib.vg_randn(P(c), n, 123, P(off2), 1, None) == 0
+    assert torch.equal(a, c)                      # counter-based: same (seed, offset, stream) -> same draw
+
+
+def test_error_convention():
+    fn = _fn()
+    from importlib import import_module
+    err = import_module("vaegan_b200._lib").VaeganB200Error
+    spec = fn.ConvSpec("down", 8, 8, 4, 1, 0)
+    with pytest.raises(RuntimeError, match="Kernel size can't be greater than actual input size"):
+        spec.geom(1, 2, 2)
+    g = fn.ConvSpec("down", 8, 8, 4, 2, 1).geom(2, 8, 8)
+    g.small_h = 7                                    # inconsistent geometry -> VG_ERR_SHAPE, message via vg_last_error
+    with pytest.raises(err, match="inconsistent"):
+        fn.conv_down(torch.zeros(2, 8, 8, 8, device="cuda"), torch.zeros(8, 8, 4, 4, device="cuda"), g)

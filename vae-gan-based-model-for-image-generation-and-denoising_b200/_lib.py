@@ -31,6 +31,7 @@ PROTOTYPES = {
     "vg_last_error": (c_char_p, []),
     "vg_version": (c_int, []),
     "vg_device_check": (c_int, []),
+    "vg_launch_count": (c_longlong, []),
     "vg_pack_weights_bf16": (c_int, [_G, _P, _P, _P, _P]),
     "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P]),
     "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),

@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace vg {
@@ -8,6 +9,10 @@ char* last_error_buffer() {
     static thread_local char buf[512] = {0};
     return buf;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_check() {
     static std::mutex mu;
@@ -38,6 +43,9 @@ int device_check() {
 
 }  // namespace vg
 
+namespace vg { long long launch_count(); }
+
 extern "C" const char* vg_last_error(void) { return vg::last_error_buffer(); }
 extern "C" int vg_version(void) { return 100; }
+extern "C" long long vg_launch_count(void) { return vg::launch_count(); }
 extern "C" int vg_device_check(void) { return vg::device_check(); }

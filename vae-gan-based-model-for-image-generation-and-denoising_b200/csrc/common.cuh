@@ -22,6 +22,14 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     return fail(VG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// Use right after a kernel launch: checks the launch and counts it.
+#define VG_LAUNCHED()                                          \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return ::vg::cuda_fail(e__, "kernel launch"); \
+        ::vg::note_launch();                                   \
+    } while (0)
+
 #define VG_CUDA(call)                                          \
     do {                                                       \
         cudaError_t e__ = (call);                              \
@@ -32,5 +40,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // sm_100 check, cached per device.
 int device_check();
+
+// Number of kernels this library has launched in this process (bench.py reports it as gpu_launches).
+void note_launch(int n = 1);
 
 }  // namespace vg

@@ -143,6 +143,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     p.bias = bias;
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
+    note_launch();
     return VG_OK;
 }
 
@@ -233,6 +234,7 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
     p.stages = pick_stages((128 + p.n_tile) * p.kchunk * 2, p.n_tile);
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
+    note_launch();
     return VG_OK;
 }
 
@@ -288,6 +290,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.n_valid = g->big_c;
     const int rc = launch_wgrad(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_wgrad_kernel");
+    note_launch();
     return VG_OK;
 }
 
@@ -323,7 +326,7 @@ extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* w
     pack_weights_kernel<<<blocks, threads, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wd),
                                                                    static_cast<__nv_bfloat16*>(wu), g->small_c,
                                                                    g->big_c, kk);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 

@@ -221,7 +221,7 @@ int run_down(const VgConvGeom* g, const void* big, const void* w, const float* b
     const long long M = static_cast<long long>(g->batch) * g->small_h * g->small_w;
     dim3 grid(cdiv(M, TM), cdiv(g->small_c, TN), 1);
     simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -239,7 +239,7 @@ int run_up(const VgConvGeom* g, const void* small, const void* w, void* big, boo
     const long long M = static_cast<long long>(g->batch) * ((g->big_h + s - 1) / s) * ((g->big_w + s - 1) / s);
     dim3 grid(cdiv(M, TM), cdiv(g->big_c, TN), s * s);
     simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -258,7 +258,7 @@ int run_wgrad(const VgConvGeom* g, const void* small, const void* big, float* dw
     op.splits = splits;
     dim3 grid(cdiv(g->small_c, TM), cdiv(g->big_c, TN), kk * splits);
     simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 

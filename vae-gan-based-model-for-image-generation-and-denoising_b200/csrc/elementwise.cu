@@ -179,7 +179,7 @@ template <int MODE>
 int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
     if (dt == VG_BF16) channel_reduce_kernel<__nv_bfloat16, MODE><<<blocks, kThreads, 0, st>>>(a);
     else channel_reduce_kernel<float, MODE><<<blocks, kThreads, 0, st>>>(a);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -416,7 +416,7 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
     bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
         ws, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
         momentum, eps, mean_out, rstd_out, scale_out, shift_out);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -427,7 +427,7 @@ extern "C" int vg_bn_eval_coeffs(const float* gamma, const float* beta, const fl
     if (rc != VG_OK) return rc;
     bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps,
                                                                           C, scale_out, shift_out);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -460,7 +460,7 @@ extern "C" int vg_scale_shift_act(const void* x, VgDType in_dt, long long rows, 
         scale_shift_act_kernel<float, float><<<grid_for(n), kThreads, 0, st>>>(
             static_cast<const float*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
     }
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -487,7 +487,7 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     if (rc != VG_OK) return rc;
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, p.blocks, C, static_cast<double>(rows), dgamma, dbeta,
                                                            c1, c2);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     const int V = dt == VG_BF16 ? 8 : 4;
     const long long nvec = rows * C / V;
     if (dt == VG_BF16)
@@ -498,7 +498,7 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
         bn_act_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, st>>>(
             static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
             mean, rstd, c1, c2, act, slope);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -528,7 +528,7 @@ extern "C" int vg_act_bwd(const void* dy, const void* x, VgDType in_dt, long lon
         act_bwd_kernel<__nv_bfloat16, float><<<g, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
                                                                      static_cast<const __nv_bfloat16*>(x),
                                                                      static_cast<float*>(dx), n, act, slope);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -546,7 +546,7 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
             else
                 colsum_generic_kernel<float><<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
                     static_cast<const float*>(x), rows, C, out);
-            VG_CUDA(cudaGetLastError());
+            VG_LAUNCHED();
             return VG_OK;
         }
     }
@@ -558,7 +558,7 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
     rc = launch_reduce<2>(dt, a, p.blocks, as_stream(stream));
     if (rc != VG_OK) return rc;
     colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, p.blocks, C, out);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -576,7 +576,7 @@ extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, Vg
     else
         nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, HW,
                                                                           mode, sigma, clamp);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -593,6 +593,6 @@ extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, float* dst, int B, i
     else
         nhwc_to_nchw_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(static_cast<const float*>(src), dst, B, C, HW,
                                                                           act, slope);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }

@@ -249,7 +249,7 @@ extern "C" int vg_reparam_fwd(const float* mu, const float* logvar, const float*
     else
         reparam_fwd_kernel<float><<<1, 1024, 0, as_stream(stream)>>>(mu, logvar, eps, n, batch, static_cast<float*>(z),
                                                                      kl_out);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -267,7 +267,7 @@ extern "C" int vg_reparam_bwd(const void* dz, VgDType dz_dt, const float* mu, co
     else
         reparam_bwd_kernel<float><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(
             static_cast<const float*>(dz), mu, logvar, eps, n, batch, kl_weight_dev, kl_weight, dmu, dlogvar);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -277,7 +277,7 @@ extern "C" int vg_bce(const float* p, int n, float target, float weight, float* 
     if (rc != VG_OK) return rc;
     if (p == nullptr) return fail(VG_ERR_ARG, "bce: null pointer");
     bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(p, n, target, weight, loss_out, accumulate, dp);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -295,9 +295,9 @@ extern "C" int vg_mse(const float* a, const float* b, long long n, float weight,
     const int blocks = grid_for(n / 4 + 1);
     mse_partial_kernel<<<blocks, kThreads, 0, as_stream(stream)>>>(a, b, n, weight, grad_in, grad_out,
                                                                    static_cast<double*>(ws));
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     mse_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(static_cast<const double*>(ws), blocks, n, loss_out);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -306,7 +306,7 @@ extern "C" int vg_total_loss(const float* recon, const float* kl, const float* a
     int rc = device_check();
     if (rc != VG_OK) return rc;
     total_loss_kernel<<<1, 1, 0, as_stream(stream)>>>(recon, kl, adv, w_kl_dev, w_kl, w_adv, total);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -320,10 +320,10 @@ extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long l
          reinterpret_cast<uintptr_t>(v)) & 15)
         return fail(VG_ERR_ALIGN, "adam: 16-byte alignment");
     adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     adam_kernel<<<grid_for(n / 4 + 1), kThreads, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
                                                                          grad_scale);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     return VG_OK;
 }
 
@@ -333,10 +333,10 @@ extern "C" int vg_randn(float* out, long long n, unsigned long long seed, unsign
     if (rc != VG_OK) return rc;
     if (out == nullptr) return fail(VG_ERR_ARG, "randn: null pointer");
     randn_kernel<<<grid_for((n + 3) / 4), kThreads, 0, as_stream(stream)>>>(out, n, seed, offset_dev, stream_id);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCHED();
     if (offset_dev != nullptr) {
         counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(offset_dev, 1ull);
-        VG_CUDA(cudaGetLastError());
+        VG_LAUNCHED();
     }
     return VG_OK;
 }

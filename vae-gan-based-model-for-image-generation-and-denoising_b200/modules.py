@@ -171,7 +171,10 @@ class Encoder(_KernelModule):
     def forward(self, x):
         if x.dim() != 4:
             raise RuntimeError(f"Expected 4D (batched) input to conv2d, but got input of size: {list(x.shape)}")
-        h = F_.ToNHWCFn.apply(x, self._dtype())
+        return self.forward_nhwc(F_.ToNHWCFn.apply(x, self._dtype()))
+
+    def forward_nhwc(self, h):
+        """Same as forward for an input that is already an internal NHWC activation (used by the fused step)."""
         for blk in self.cnn:
             h = blk._layer()(h, self.training)
         if (h.shape[1], h.shape[2]) != self._feat_hw:
@@ -222,13 +225,14 @@ class Generator(_KernelModule):
         return self._plan[1]
 
     def forward(self, input):
+        return F_.ToNCHWActFn.apply(self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype())), self._layers()[-1].act)
+
+    def forward_nhwc(self, h):
+        """z as NHWC [B,1,1,nz] -> RAW last-conv output NHWC [B,H,W,nc]; the final Tanh rides the NCHW store."""
         layers = self._layers()
-        h = F_.ToNHWCFn.apply(input, self._dtype())
         for layer in layers[:-1]:
             h = layer(h, self.training)
-        last = layers[-1]
-        h = last(h, self.training, fuse_act=False)          # raw conv output; the final Tanh rides the NCHW store
-        return F_.ToNCHWActFn.apply(h, last.act)
+        return layers[-1](h, self.training, fuse_act=False)
 
 
 Decoder = Generator   # main_vae.py:10
@@ -259,8 +263,10 @@ class Discriminator(_KernelModule):
     _layers = Generator._layers
 
     def forward(self, input):
+        return self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype()))
+
+    def forward_nhwc(self, h):
         layers = self._layers()
-        h = F_.ToNHWCFn.apply(input, self._dtype())
         for layer in layers[:-1]:
             h = layer(h, self.training)
         last = layers[-1]

@@ -1,0 +1,281 @@
+"""VAEGANStep - the fused training step (integration level 2).
+
+Reproduces one iteration of the reference hot loop, vaegan_code.py:66-135, on the drop-in modules with
+  * the fused loss-side kernels (reparameterisation + KL, BCE, MSE with gradient seeds; no ATen arithmetic),
+  * gradients accumulated by the wgrad / BatchNorm kernels straight into flat fp32 buffers (`param.main_grad`),
+  * one fused Adam launch per optimizer over its flat buffer (torch.optim.Adam defaults of vaegan_code.py:42-44),
+  * the discriminator's weight gradients skipped in the generator step (the reference computes and discards them:
+    vaegan_code.py:110-135 never steps opt_Dis after `total.backward()`),
+  * data parallelism: one process per GPU, gradient all-reduce (NCCL) per optimizer update, 1/world folded into Adam,
+  * the whole schedule captured in ONE CUDA graph and replayed per step; losses stay on the device.
+
+    step = VAEGANStep(encoder, decoder, discriminator)        # same modules the reference loop would use
+    losses = step.step(real_images, epoch)                    # dict of 0-d device tensors
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from ._lib import ACT_TANH, call
+from .functional import _p, _stream
+
+LOSS_KEYS = ("d_loss_0", "d_loss_1", "recon", "kl", "adv", "total")
+
+
+class _FlatAdam:
+    """All parameters of one network in one fp32 buffer + matching gradient / moment buffers."""
+
+    def __init__(self, net: nn.Module, lr, betas, eps):
+        params = [p for p in net.parameters()]
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4        # keep every view 16-byte aligned
+        self.n = total
+        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
+        for p, o in zip(params, offs):
+            view = self.params[o:o + p.numel()].view_as(p)
+            view.copy_(p.detach())
+            p.data = view
+            p.main_grad = self.grads[o:o + p.numel()].view_as(p)
+            p.grad = None
+        self.lr, self.betas, self.eps = lr, betas, eps
+
+    def zero_grad(self):
+        self.grads.zero_()      # cudaMemsetAsync
+
+    def step(self, grad_scale: float):
+        call("vg_adam_step", _p(self.params), _p(self.grads), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
+             float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), _p(self.step_count),
+             float(grad_scale), _stream())
+
+
+class _ReparamFn(torch.autograd.Function):
+    """vaegan_code.py:75-78 + the KL prior of :114; backward adds w_kl * dKL to the gradients of mu / logvar."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, kl_out, kl_weight_dev, dtype):
+        B, nz = mu.shape
+        z = torch.empty((B, 1, 1, nz), dtype=dtype, device=mu.device)
+        call("vg_reparam_fwd", _p(mu), _p(logvar), _p(eps), B, nz, _p(z), F_._DT[dtype], _p(kl_out), _stream())
+        ctx.save_for_backward(mu, logvar, eps, kl_weight_dev)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        mu, logvar, eps, klw = ctx.saved_tensors
+        B, nz = mu.shape
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
+        dz = dz.contiguous()
+        call("vg_reparam_bwd", _p(dz), F_._DT[dz.dtype], _p(mu), _p(logvar), _p(eps), B, nz, _p(klw), 0.0, _p(dmu),
+             _p(dlv), _stream())
+        return dmu, dlv, None, None, None, None
+
+
+class _ReconHubFn(torch.autograd.Function):
+    """recon (fp32 NCHW) -> recon + sigma*n_fake as the discriminator's NHWC input (vaegan_code.py:92).
+    Backward folds in the pixel-MSE term of :113: d_recon = d(adv path) + 2 (recon - real) / N, and writes the
+    reconstruction loss."""
+
+    @staticmethod
+    def forward(ctx, recon, real, n_fake, sigma, dtype, recon_loss_out, mse_ws):
+        ctx.save_for_backward(recon, real, recon_loss_out, mse_ws)
+        return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma)
+
+    @staticmethod
+    def backward(ctx, dy):
+        recon, real, loss_out, ws = ctx.saved_tensors
+        d_adv = F_.nhwc_to_nchw(dy.contiguous())
+        d_total = torch.empty_like(recon)
+        call("vg_mse", _p(recon), _p(real), recon.numel(), 1.0, _p(d_adv), _p(d_total), _p(loss_out), _p(ws),
+             ws.numel() * 4, _stream())
+        return d_total, None, None, None, None, None, None
+
+
+class VAEGANStep:
+    def __init__(self, encoder, decoder, discriminator, *, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 alpha_kl: float = 0.1, alpha_adv: float = 0.1, kl_warmup_epochs: int = 50, sigma_inst: float = 0.05,
+                 denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
+                 process_group=None, use_cuda_graph: bool = True, seed: int = 0):
+        self.E, self.G, self.D = encoder, decoder, discriminator
+        self.dtype = encoder._dtype()
+        self.dev = next(encoder.parameters()).device
+        if self.dev.type != "cuda":
+            raise F_._lib.VaeganB200Error("VAEGANStep needs the modules on a CUDA (sm_100) device; no CPU fallback")
+        self.alpha_kl, self.alpha_adv, self.kl_warmup = alpha_kl, alpha_adv, kl_warmup_epochs
+        self.sigma_inst, self.denoise_sigma, self.n_dis = sigma_inst, denoise_sigma, n_dis
+        self.real_label, self.fake_label = real_label, fake_label
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.opt_E = _FlatAdam(encoder, lr, betas, eps)
+        self.opt_G = _FlatAdam(decoder, lr, betas, eps)
+        self.opt_D = _FlatAdam(discriminator, lr, betas, eps)
+        self.use_graph = use_cuda_graph
+        self.seed = seed
+        self._graph = None
+        self._static = None
+        self.launches_per_step = None
+        for net in (encoder, decoder, discriminator):
+            net.train()
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _alloc_static(self, batch, hw, nz):
+        dev = self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        s = {
+            "real": torch.zeros((batch, 3, hw, hw), **f32), "eps": torch.zeros((batch, nz), **f32),
+            "n_real": torch.zeros((batch, 3, hw, hw), **f32), "n_fake": torch.zeros((batch, 3, hw, hw), **f32),
+            "n_den": torch.zeros((batch, 3, hw, hw), **f32) if self.denoise_sigma > 0 else None,
+            "kl_w": torch.zeros((), **f32), "losses": torch.zeros((len(LOSS_KEYS),), **f32),
+            "rng_offset": torch.zeros((), dtype=torch.int64, device=dev),
+            "mse_ws": torch.empty((F_._lib.load().vg_mse_workspace_bytes() // 4,), **f32),
+            "dp_a": torch.empty((batch,), **f32), "dp_b": torch.empty((batch,), **f32),
+        }
+        return s
+
+    def _randn_into(self, t: torch.Tensor, stream_id: int):
+        call("vg_randn", _p(t), t.numel(), ctypes.c_ulonglong(self.seed), _p(self._static["rng_offset"]),
+             ctypes.c_ulonglong(stream_id), _stream())
+
+    def _allreduce(self, opt: _FlatAdam):
+        if self.world > 1:
+            torch.distributed.all_reduce(opt.grads, group=self.pg)
+
+    # ------------------------------------------------------------------------------------------ the schedule
+    def _run(self, gen_noise: bool):
+        s = self._static
+        E, G, D = self.E, self.G, self.D
+        real, loss = s["real"], s["losses"]
+        B = real.shape[0]
+        for net in (E, G, D):          # every replay starts from freshly packed bf16 weights
+            net.invalidate_packed_weights()
+        if gen_noise:                  # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
+            self._randn_into(s["eps"], 1)
+            self._randn_into(s["n_real"], 2)
+            self._randn_into(s["n_fake"], 3)
+            if s["n_den"] is not None:
+                self._randn_into(s["n_den"], 4)
+
+        # ---- encode, reparameterise, decode                                         (:74-83)
+        if self.denoise_sigma > 0:
+            enc_in = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_den"], mode=1, sigma=self.denoise_sigma, clamp=True)
+        else:
+            enc_in = F_.nchw_to_nhwc(real, self.dtype)
+        mu, logvar = E.forward_nhwc(enc_in)
+        z = _ReparamFn.apply(mu, logvar, s["eps"], loss[3:4], s["kl_w"], self.dtype)
+        recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH)
+
+        # ---- instance noise                                                           (:88-92)
+        real_noisy = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst)
+        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype, loss[2:3], s["mse_ws"])
+        recon_noisy_d = recon_noisy.detach()
+
+        # ---- discriminator updates                                                    (:95-105)
+        for it in range(self.n_dis):
+            self.opt_D.zero_grad()
+            p_real = D.forward_nhwc(real_noisy)
+            p_fake = D.forward_nhwc(recon_noisy_d)
+            slot = loss[it:it + 1] if it < 2 else None
+            call("vg_bce", _p(p_real), B, self.real_label, 1.0, _p(slot), 0, _p(s["dp_a"]), _stream())
+            call("vg_bce", _p(p_fake), B, self.fake_label, 1.0, _p(slot), 1, _p(s["dp_b"]), _stream())
+            torch.autograd.backward([p_real, p_fake], [s["dp_a"], s["dp_b"]])
+            self._allreduce(self.opt_D)
+            self.opt_D.step(1.0 / self.world)
+            D.invalidate_packed_weights()
+
+        # ---- generator / encoder update                                               (:110-135)
+        self.opt_E.zero_grad()
+        self.opt_G.zero_grad()
+        d_params = list(D.parameters())
+        for p in d_params:             # weight gradients of D are never used in this phase (reference discards them)
+            p.requires_grad_(False)
+        try:
+            p_fake = D.forward_nhwc(recon_noisy)
+            call("vg_bce", _p(p_fake), B, self.real_label, self.alpha_adv, _p(loss[4:5]), 0, _p(s["dp_a"]), _stream())
+            torch.autograd.backward([p_fake], [s["dp_a"]])
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
+             _p(loss[5:6]), _stream())
+        self._allreduce(self.opt_E)
+        self._allreduce(self.opt_G)
+        self.opt_E.step(1.0 / self.world)
+        self.opt_G.step(1.0 / self.world)
+        self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
+
+    # ------------------------------------------------------------------------------------------ public API
+    def step(self, real: torch.Tensor, epoch: int, eps: Optional[torch.Tensor] = None,
+             n_real: Optional[torch.Tensor] = None, n_fake: Optional[torch.Tensor] = None,
+             n_denoise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """One training step on `real` (fp32 NCHW in [-1, 1], device or pinned host tensor).  Noise tensors may be
+        injected (parity tests) - otherwise they are drawn on the device.  Returns 0-d device tensors."""
+        batch, _, hw, _ = real.shape
+        nz = self.E.fc_mu.out_features
+        injected = eps is not None
+        if self._static is None or self._static["real"].shape != real.shape:
+            self._static = self._alloc_static(batch, hw, nz)
+            self._graph = None
+        s = self._static
+        s["real"].copy_(real, non_blocking=True)
+        s["kl_w"].fill_(self.alpha_kl * min(1.0, epoch / self.kl_warmup) if self.kl_warmup > 0 else self.alpha_kl)
+        if injected:
+            s["eps"].copy_(eps, non_blocking=True)
+            s["n_real"].copy_(n_real, non_blocking=True)
+            s["n_fake"].copy_(n_fake, non_blocking=True)
+            if s["n_den"] is not None:
+                s["n_den"].copy_(n_denoise, non_blocking=True)
+        if not self.use_graph:
+            self._run(gen_noise=not injected)
+        else:
+            key = (not injected)
+            if self._graph is None or self._graph[0] != key:
+                # warm-up run outside capture (allocator, lazy module plans), then capture
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._snapshot = self._save_state()
+                    self._run(gen_noise=key)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self._restore_state(self._snapshot)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(gen_noise=key)
+                self._graph = (key, g)
+                self._restore_state(self._snapshot)
+                self._snapshot = None
+            self._graph[1].replay()
+        return {k: s["losses"][i] for i, k in enumerate(LOSS_KEYS)}
+
+    # state save / restore so that warm-up + capture do not advance training
+    def _save_state(self):
+        st = {"opt": [(o.params.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_count.clone())
+                      for o in (self.opt_E, self.opt_G, self.opt_D)],
+              "buf": [[b.clone() for b in net.buffers()] for net in (self.E, self.G, self.D)],
+              "rng": self._static["rng_offset"].clone()}
+        return st
+
+    def _restore_state(self, st):
+        for o, (p, m, v, c) in zip((self.opt_E, self.opt_G, self.opt_D), st["opt"]):
+            o.params.copy_(p); o.exp_avg.copy_(m); o.exp_avg_sq.copy_(v); o.step_count.copy_(c)
+        for net, bufs in zip((self.E, self.G, self.D), st["buf"]):
+            for b, saved in zip(net.buffers(), bufs):
+                b.copy_(saved)
+        self._static["rng_offset"].copy_(st["rng"])
+
+    def last_outputs(self):
+        """mu, logvar, recon of the most recent step (device tensors; static under CUDA-graph replay)."""
+        return self._last
