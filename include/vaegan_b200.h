@@ -149,8 +149,8 @@ int vg_total_loss(const float* recon, const float* kl, const float* adv, const f
 /* torch.optim.Adam.step (vaegan_code.py:42-44,105,134-135) over one flat fp32 buffer; *step_dev is incremented
  * first and drives the bias corrections, so the call can be replayed from a CUDA graph.  g is multiplied by
  * grad_scale (1/world_size under data parallelism). */
-int vg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                 float eps, long long* step_dev, float grad_scale, void* stream);
+int vg_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                 double eps, long long* step_dev, float grad_scale, void* stream);
 /* Standard normal noise (torch.randn_like, vaegan_code.py:77,91,92): Philox4x32-10 + Box-Muller, keyed by
  * (seed, *offset_dev, stream_id); *offset_dev is incremented after the launch when given. */
 int vg_randn(float* out, long long n, unsigned long long seed, unsigned long long* offset_dev,

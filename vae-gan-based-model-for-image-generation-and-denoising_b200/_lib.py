@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_ulonglong,
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_longlong, c_size_t, c_ulonglong,
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -54,7 +54,7 @@ PROTOTYPES = {
     "vg_mse_workspace_bytes": (c_size_t, []),
     "vg_mse": (c_int, [_P, _P, c_longlong, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "vg_total_loss": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P]),
-    "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, _P, c_float, _P]),
+    "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_double, c_double, c_double, c_double, _P, c_float, _P]),
     "vg_randn": (c_int, [_P, c_longlong, c_ulonglong, _P, c_ulonglong, _P]),
 }
 

@@ -85,6 +85,7 @@ struct ReduceArgs {
     int act;
     float slope;
     float* partial;
+    float* pivot;   // MODE 0: [C] per-channel pivot (row 0 of x), written by block 0, consumed by the finalize kernel
 };
 
 template <typename T, int MODE>
@@ -107,6 +108,16 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
 #pragma unroll
         for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0.f;
         float sc[V], sh[V], mu[V], rs[V];
+        float piv[V];
+        if (MODE == 0) {
+            // shifted-data sums: accumulate (x - K) and (x - K)^2 with K = the channel's first value, so that
+            // var = E[d^2] - E[d]^2 does not cancel catastrophically when |mean| >> std or rows are few
+            Vec<T>::load(x + c0, piv);
+            if (blockIdx.x == 0 && rsub == 0) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) a.pivot[c0 + i] = piv[i];
+            }
+        }
         if (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < V; ++i) {
@@ -121,7 +132,11 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
             Vec<T>::load(x + r * a.C + c0, xv);
             if (MODE == 0) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+                for (int i = 0; i < V; ++i) {
+                    const float d = xv[i] - piv[i];
+                    s0[i] += d;
+                    s1[i] = fmaf(d, d, s1[i]);
+                }
             } else if (MODE == 1) {
                 float dv[V];
                 Vec<T>::load(dy + r * a.C + c0, dv);
@@ -184,7 +199,8 @@ int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
 }
 
 // ---- finalize kernels (one thread per channel; fp64 combination of the per-block partials)
-__global__ void bn_fwd_finalize_kernel(const float* partial, int blocks, int C, double n, const float* gamma,
+__global__ void bn_fwd_finalize_kernel(const float* partial, const float* pivot, int blocks, int C, double n,
+                                       const float* gamma,
                                        const float* beta, float* running_mean, float* running_var,
                                        long long* num_batches_tracked, float momentum, float eps, float* mean_out,
                                        float* rstd_out, float* scale_out, float* shift_out) {
@@ -196,8 +212,9 @@ __global__ void bn_fwd_finalize_kernel(const float* partial, int blocks, int C, 
         s += partial[static_cast<long long>(b) * 2 * C + c];
         ss += partial[static_cast<long long>(b) * 2 * C + C + c];
     }
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
+    const double dmean = s / n;
+    const double mean = static_cast<double>(pivot[c]) + dmean;
+    double var = ss / n - dmean * dmean;
     if (var < 0.0) var = 0.0;
     const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
     const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
@@ -391,7 +408,7 @@ using namespace vg;
 
 extern "C" size_t vg_reduce_workspace_bytes(long long rows, int channels) {
     const ReducePlan p = plan_reduce(rows);
-    return static_cast<size_t>(p.blocks) * 2 * channels * sizeof(float);
+    return (static_cast<size_t>(p.blocks) * 2 + 1) * channels * sizeof(float);   // partials + pivot row
 }
 
 extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C, const float* gamma,
@@ -411,10 +428,11 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
         return fail(VG_ERR_WORKSPACE, "bn_train_fwd: workspace too small");
     ReduceArgs a{};
     a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
+    a.pivot = ws + static_cast<size_t>(p.blocks) * 2 * C;
     rc = launch_reduce<0>(dt, a, p.blocks, as_stream(stream));
     if (rc != VG_OK) return rc;
     bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
-        ws, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
+        ws, a.pivot, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
         momentum, eps, mean_out, rstd_out, scale_out, shift_out);
     VG_LAUNCHED();
     return VG_OK;
@@ -477,7 +495,7 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     const ReducePlan p = plan_reduce(rows);
     const size_t need = vg_reduce_workspace_bytes(rows, C) + 2 * static_cast<size_t>(C) * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return fail(VG_ERR_WORKSPACE, "bn_act_bwd: workspace too small");
-    float* c1 = ws + static_cast<size_t>(p.blocks) * 2 * C;
+    float* c1 = ws + (static_cast<size_t>(p.blocks) * 2 + 1) * C;
     float* c2 = c1 + C;
     cudaStream_t st = as_stream(stream);
     ReduceArgs a{};

@@ -151,12 +151,14 @@ __global__ void adam_tick_kernel(long long* step) { *step += 1; }
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, long long n,
-                                                       float lr, float b1, float b2, float eps,
+                                                       double lr_d, double b1_d, double b2_d, double eps_d,
                                                        const long long* __restrict__ step_ptr, float grad_scale) {
+    // hyper-parameters arrive as doubles and are narrowed exactly where torch narrows its Python floats
     const double t = static_cast<double>(*step_ptr);
-    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), t));
-    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), t)));
-    const float step_size = lr / bc1;
+    const float b1 = static_cast<float>(b1_d), b2 = static_cast<float>(b2_d), eps = static_cast<float>(eps_d);
+    const float omb1 = static_cast<float>(1.0 - b1_d), omb2 = static_cast<float>(1.0 - b2_d);
+    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(b2_d, t)));
+    const float step_size = static_cast<float>(lr_d / (1.0 - pow(b1_d, t)));
     const long long nvec = n / 4;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
         const float gg[4] = {gv.x * grad_scale, gv.y * grad_scale, gv.z * grad_scale, gv.w * grad_scale};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            mm[j] = mm[j] + (gg[j] - mm[j]) * (1.f - b1);          // exp_avg.lerp_(grad, 1-beta1)
-            vq[j] = vq[j] * b2 + (1.f - b2) * gg[j] * gg[j];       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+            mm[j] = mm[j] + (gg[j] - mm[j]) * omb1;                // exp_avg.lerp_(grad, 1-beta1)
+            vq[j] = vq[j] * b2 + omb2 * gg[j] * gg[j];             // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
             const float denom = sqrtf(vq[j]) / bc2_sqrt + eps;
             pp[j] = pp[j] - step_size * (mm[j] / denom);
         }
@@ -179,8 +181,8 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
     if (blockIdx.x == 0) {
         for (long long i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) {
             const float gi = g[i] * grad_scale;
-            const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-            const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+            const float mi = m[i] + (gi - m[i]) * omb1;
+            const float vi = v[i] * b2 + omb2 * gi * gi;
             m[i] = mi;
             v[i] = vi;
             p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
@@ -310,8 +312,8 @@ extern "C" int vg_total_loss(const float* recon, const float* kl, const float* a
     return VG_OK;
 }
 
-extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                            float beta2, float eps, long long* step_dev, float grad_scale, void* stream) {
+extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                            double beta2, double eps, long long* step_dev, float grad_scale, void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || step_dev == nullptr)
