@@ -37,6 +37,7 @@ CONV_CASES = [
     ("up", 16, 1, 1, 128, 256, 4, 1, 0),        # first generator layer (dense GEMM)
     ("up", 2, 16, 16, 64, 3, 3, 1, 1),          # last generator layer k3
     ("up", 130, 4, 4, 256, 128, 4, 2, 1),       # batch larger than one M tile
+    ("up", 8, 32, 32, 128, 64, 4, 2, 1),        # last BN'd generator stage: 32-wide tiles, 8 row tiles per image
 ]
 
 
