@@ -55,6 +55,10 @@ typedef struct VgConvGeom {
     int32_t big_h, big_w, big_c;       /* Conv2d input  / ConvTranspose2d output */
     int32_t small_h, small_w, small_c; /* Conv2d output / ConvTranspose2d input  */
     int32_t kernel, stride, pad;
+    /* Channel padding of the big side: the big TENSOR has big_c channels per pixel of which the first big_c_valid
+     * exist in the weight tensor w[small_c][big_c_valid][k][k] (0 means big_c).  The bf16 path stores the 3-channel
+     * image tensors with 16 channels (zeros above 3) so that they are legal TMA / UMMA operands. */
+    int32_t big_c_valid;
 } VgConvGeom;
 
 const char* vg_last_error(void);
@@ -65,8 +69,9 @@ int vg_device_check(void);
 long long vg_launch_count(void);
 
 /* ---- weight packing (bf16 tensor-core path) ---------------------------------------------------------------
- * fp32 master w[small_c][big_c][k][k]  ->  wd[tap][small_c][big_c]  (operand of `down`)
- *                                      and wu[tap][big_c][small_c]  (operand of `up`),  tap = ky*k+kx, bf16.
+ * fp32 master w[small_c][big_c_valid][k][k]  ->  wd[tap][small_c][big_c]  (operand of `down`)
+ *                                            and wu[tap][big_c][small_c]  (operand of `up`),  tap = ky*k+kx, bf16,
+ * zero-filled for the padded channels big_c_valid <= c < big_c.
  * Either output may be NULL.  Replaces the implicit weight reads of nn.Conv2d / nn.ConvTranspose2d
  * (main_vae.py:23, gan_code.py:21-49, 61-84). */
 int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* wd, void* wu, void* stream);
@@ -119,12 +124,13 @@ int vg_colsum(const void* x, VgDType dt, long long rows, int channels, float* ou
               void* stream);
 /* fp32 NCHW (the reference's tensor contract, dataset_code.py:178) -> NHWC dtype.
  *   mode 0: copy;  mode 1: clamp?(src + sigma*aux)  (instance / denoising noise, vaegan_code.py:91-92,153-154);
- *   mode 2: src * (1 - aux^2)  (Tanh backward, aux = tanh output). */
+ *   mode 2: src * (1 - aux^2)  (Tanh backward, aux = tanh output).
+ * The NHWC side may carry dst_channels >= channels per pixel (extra channels are written as zeros / ignored). */
 int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int batch, int channels, int h, int w,
-                    int mode, float sigma, int clamp, void* stream);
+                    int dst_channels, int mode, float sigma, int clamp, void* stream);
 /* NHWC dtype -> fp32 NCHW with an optional activation (Tanh of gan_code.py:50). */
-int vg_nhwc_to_nchw(const void* src, VgDType dt, float* dst, int batch, int channels, int h, int w, VgAct act,
-                    float slope, void* stream);
+int vg_nhwc_to_nchw(const void* src, VgDType dt, int src_channels, float* dst, int batch, int channels, int h, int w,
+                    VgAct act, float slope, void* stream);
 
 /* ---- VAE-GAN losses, Adam, noise ------------------------------------------------------------------------------
  * vg_reparam_fwd : logvar clamp [-10,10], std = exp(logvar/2), z = mu + std*eps, KL = -1/2 sum(1+lv-mu^2-e^lv)/B

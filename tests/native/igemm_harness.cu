@@ -46,6 +46,7 @@ static VgConvGeom geom(int B, int bh, int bw, int bc, int sc, int k, int s, int 
     g.kernel = k;
     g.stride = s;
     g.pad = p;
+    g.big_c_valid = 0;
     return g;
 }
 

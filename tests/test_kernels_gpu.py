@@ -38,6 +38,9 @@ CONV_CASES = [
     ("up", 2, 16, 16, 64, 3, 3, 1, 1),          # last generator layer k3
     ("up", 130, 4, 4, 256, 128, 4, 2, 1),       # batch larger than one M tile
     ("up", 8, 32, 32, 128, 64, 4, 2, 1),        # last BN'd generator stage: 32-wide tiles, 8 row tiles per image
+    ("down", 4, 64, 64, 3, 32, 4, 2, 0),        # first encoder layer (p=0), 32 output channels
+    ("down", 3, 16, 16, 16, 32, 4, 2, 1),       # native-256 discriminator widths (16 / 32 channels)
+    ("up", 4, 16, 16, 32, 16, 4, 2, 1),         # native-256 generator tail
 ]
 
 
@@ -62,8 +65,19 @@ def test_conv_fwd_dgrad_wgrad(case, prec):
     (F.conv2d(xr, wr, None, s, p) if kind == "down" else F.conv_transpose2d(xr, wr, None, s, p)).backward(dy)
 
     dt = fn.PRECISION_DTYPE[prec]
-    g = spec.geom(B, H, W)
-    xd, dyd, wdv = _nhwc(x).cuda().to(dt), _nhwc(dy).cuda().to(dt), w.cuda()
+    big_c = cin if kind == "down" else cout
+    cpad = fn.padded_channels(big_c, dt)           # bf16: 3-channel image tensors are stored with 16 channels
+    g = spec.geom(B, H, W, cpad)
+
+    def dev(t_nchw, pad_to=None):                  # NCHW cpu -> NHWC device tensor, optionally channel-padded
+        t = _nhwc(t_nchw)
+        if pad_to is not None and pad_to != t.shape[-1]:
+            t = torch.cat([t, torch.zeros(*t.shape[:-1], pad_to - t.shape[-1])], dim=-1)
+        return t.contiguous().cuda().to(dt)
+
+    xd = dev(x, cpad if kind == "down" else None)
+    dyd = dev(dy, cpad if kind == "up" else None)
+    wdv = w.cuda()
     if prec == "bf16":
         wd, wu = fn.pack_weights(wdv, g)
         w_fwd, w_bwd = (wd, wu) if kind == "down" else (wu, wd)
@@ -78,9 +92,14 @@ def test_conv_fwd_dgrad_wgrad(case, prec):
         dx = fn.conv_down(dyd, w_bwd, g)
         dw = fn.conv_wgrad(xd, dyd, g)
     torch.cuda.synchronize()
+    big_out = dx if kind == "down" else y          # the tensor living on the (possibly padded) big side
+    if cpad != big_c:
+        assert float(big_out[..., big_c:].float().abs().max()) == 0.0     # padded channels stay exactly zero
+    crop = lambda t, is_big: t[..., :big_c] if (is_big and cpad != big_c) else t
     tol_out = 1e-5 if prec == "fp32" else 6e-3      # bf16: output rounding only
-    assert rel_err(_nchw(y.float().cpu()), y_ref) < tol_out
-    assert rel_err(_nchw(dx.float().cpu()), xr.grad) < tol_out
+    assert rel_err(_nchw(crop(y, kind == "up").float().cpu()), y_ref) < tol_out
+    assert rel_err(_nchw(crop(dx, kind == "down").float().cpu()), xr.grad) < tol_out
+    assert dw.shape == wr.grad.shape
     assert rel_err(dw.cpu(), wr.grad) < 2e-5           # fp32 accumulate + fp32 output in both modes
 
 
@@ -136,14 +155,18 @@ def test_layout_edges_and_noise_modes():
     x = torch.rand(3, 3, 20, 12, generator=gen) * 2 - 1
     n = torch.randn(3, 3, 20, 12, generator=gen)
     for dt in (torch.float32, torch.bfloat16):
+        cp = fn.padded_channels(3, dt)
         a = fn.nchw_to_nhwc(x.cuda(), dt)
-        assert torch.equal(a.float().cpu(), _nhwc(x).to(dt).float())
+        assert a.shape == (3, 20, 12, cp)
+        assert torch.equal(a[..., :3].float().cpu(), _nhwc(x).to(dt).float())
+        assert float(a[..., 3:].float().abs().sum()) == 0.0 if cp > 3 else True
         b = fn.nchw_to_nhwc(x.cuda(), dt, aux=n.cuda(), mode=1, sigma=0.3, clamp=True)
-        assert rel_err(b.float(), _nhwc(torch.clamp(x + 0.3 * n, -1, 1)).to(dt).float()) < 1e-6
-        back = fn.nhwc_to_nchw(a, 3)      # tanh
+        assert rel_err(b[..., :3].float(), _nhwc(torch.clamp(x + 0.3 * n, -1, 1)).to(dt).float()) < 1e-6
+        back = fn.nhwc_to_nchw(a, 3, channels=3)      # tanh
+        assert back.shape == x.shape
         assert rel_err(back, torch.tanh(x.to(dt).float())) < 1e-6
         c = fn.nchw_to_nhwc(n.cuda(), dt, aux=back, mode=2)
-        assert rel_err(c.float(), _nhwc(n * (1 - torch.tanh(x.to(dt).float()) ** 2)).to(dt).float()) < 1e-5
+        assert rel_err(c[..., :3].float(), _nhwc(n * (1 - torch.tanh(x.to(dt).float()) ** 2)).to(dt).float()) < 1e-5
 
 
 def test_reparam_kl_bce_mse_against_torch():

@@ -21,7 +21,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 class VgConvGeom(Structure):
     _fields_ = [("batch", c_int32), ("big_h", c_int32), ("big_w", c_int32), ("big_c", c_int32),
                 ("small_h", c_int32), ("small_w", c_int32), ("small_c", c_int32),
-                ("kernel", c_int32), ("stride", c_int32), ("pad", c_int32)]
+                ("kernel", c_int32), ("stride", c_int32), ("pad", c_int32), ("big_c_valid", c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
@@ -46,8 +46,8 @@ PROTOTYPES = {
                               c_size_t, _P]),
     "vg_act_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, c_float, _P, c_int, _P]),
     "vg_colsum": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_size_t, _P]),
-    "vg_nchw_to_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
-    "vg_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
+    "vg_nchw_to_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    "vg_nhwc_to_nchw": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "vg_reparam_fwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),
     "vg_reparam_bwd": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, _P, c_float, _P, _P, _P]),
     "vg_bce": (c_int, [_P, c_int, c_float, c_float, _P, c_int, _P, _P]),

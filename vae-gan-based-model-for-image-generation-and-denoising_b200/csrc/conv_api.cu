@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "conv_simt.cuh"
+#include "gemv.cuh"
 #include "igemm_umma.cuh"
 
 namespace vg {
@@ -57,6 +58,8 @@ static int make_view(CUtensorMap* m, const void* base, int B, int H, int W, int 
     return make_tmap_bf16(m, p, 4, dims, strides, box, swizzle);
 }
 
+static int bc_valid(const VgConvGeom* g) { return g->big_c_valid > 0 ? g->big_c_valid : g->big_c; }
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int check_geom(const VgConvGeom* g) {
@@ -68,6 +71,7 @@ static int check_geom(const VgConvGeom* g) {
     const int ew = (g->big_w + 2 * g->pad - g->kernel) / g->stride + 1;
     if (g->big_h + 2 * g->pad < g->kernel || g->big_w + 2 * g->pad < g->kernel)
         return fail(VG_ERR_SHAPE, "Kernel size can't be greater than actual input size");
+    if (g->big_c_valid < 0 || g->big_c_valid > g->big_c) return fail(VG_ERR_SHAPE, "big_c_valid out of range");
     if (eh != g->small_h || ew != g->small_w)
         return fail(VG_ERR_SHAPE, "small extent %dx%d inconsistent with big %dx%d k%d s%d p%d (expect %dx%d)",
                     g->small_h, g->small_w, g->big_h, g->big_w, g->kernel, g->stride, g->pad, eh, ew);
@@ -85,9 +89,14 @@ bool umma_up_ok(const VgConvGeom* g) {
     if (g->stride == 2 && (g->kernel % 2) != 0) return false;
     return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 64 && pick_n_tile(g->big_c) != 0;
 }
+static int wgrad_n_tile(int big_c) {
+    for (int t : {128, 64, 32, 16})
+        if (big_c % t == 0) return t;
+    return 0;
+}
 bool umma_wgrad_ok(const VgConvGeom* g) {
-    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 16 && g->small_c % 64 == 0 &&
-           g->big_c % 64 == 0;
+    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 16 && g->small_c % 32 == 0 &&
+           wgrad_n_tile(g->big_c) != 0;
 }
 
 // ---------------------------------------------------------------------------------------------- down
@@ -248,22 +257,26 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
     p.tiles_b = ceil_div(g->batch, p.tb);
-    p.m_atoms = g->small_c >= 128 ? 2 : 1;
-    p.m_tiles = ceil_div(g->small_c, p.m_atoms * 64);
-    p.n_tile = g->big_c % 128 == 0 ? 128 : 64;
+    p.p_atom_c = g->small_c % 64 == 0 ? 64 : 32;
+    p.m_atoms = std::min(128, g->small_c) / p.p_atom_c;
+    p.m_tiles = ceil_div(g->small_c, p.m_atoms * p.p_atom_c);
+    p.n_tile = wgrad_n_tile(g->big_c);
+    p.q_atom_c = std::min(64, p.n_tile);
     p.n_tiles = g->big_c / p.n_tile;
     p.num_taps = k * k;
     p.taps_per_cta = std::min(p.num_taps, 512 / p.n_tile);
+    if (p.num_taps % 4 == 0) p.taps_per_cta = std::max(4, p.taps_per_cta / 4 * 4);
+    p.taps_per_cta = std::min(p.taps_per_cta, 16);
     {
-        const int rc = make_view(&p.pmap, small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, 64, p.tw, p.th,
-                                 p.tb, 128);
+        const int rc = make_view(&p.pmap, small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.p_atom_c, p.tw,
+                                 p.th, p.tb, p.p_atom_c * 2);
         if (rc != 0) return fail(VG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(P) failed (%d)", rc);
     }
     const int nviews = s * s;
     for (int v = 0; v < 4; ++v) {
         const int vv = v < nviews ? v : 0;
-        const int rc = make_view(&p.qmap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, 64, p.tw,
-                                 p.th, p.tb, 128);
+        const int rc = make_view(&p.qmap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, p.q_atom_c,
+                                 p.tw, p.th, p.tb, p.q_atom_c * 2);
         if (rc != 0) return fail(VG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(Q view %d) failed (%d)", v, rc);
     }
     for (int ky = 0; ky < k; ++ky)
@@ -280,14 +293,19 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     const int tap_groups = ceil_div(p.num_taps, p.taps_per_cta);
     const int base_ctas = p.m_tiles * p.n_tiles * tap_groups;
     p.splits = std::max(1, std::min(total_tiles, ceil_div(296, base_ctas)));
-    const int stage_bytes = (2 + p.n_tile / 64) * 64 * 128;
-    p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    const int kpix = 64;
+    const int a_stage = kpix * 256, b_stage = p.n_tile * kpix * 2;
+    p.stages_a = 3;
+    p.stages_b = std::max(2, std::min(8, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;
-    p.s_m = static_cast<long long>(g->big_c) * k * k;
+    const int bcv = bc_valid(g);
+    p.s_m = static_cast<long long>(bcv) * k * k;
     p.s_n = k * k;
     p.s_tap = 1;
     p.m_valid = g->small_c;
-    p.n_valid = g->big_c;
+    p.n_valid = bcv;
+    // dw[m][n][tap..tap+3] contiguous and 16-byte aligned when k*k is a multiple of 4
+    p.vec4_taps = (k * k) % 4 == 0 && p.taps_per_cta % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0;
     const int rc = launch_wgrad(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_wgrad_kernel");
     note_launch();
@@ -296,7 +314,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
 
 // ---------------------------------------------------------------------------------------------- packing
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd,
-                                    __nv_bfloat16* __restrict__ wu, int sc, int bc, int kk) {
+                                    __nv_bfloat16* __restrict__ wu, int sc, int bc, int bcv, int kk) {
     const long long n = static_cast<long long>(sc) * bc * kk;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -304,7 +322,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
         const int b = static_cast<int>(i % bc);
         const int s = static_cast<int>((i / bc) % sc);
         const int tap = static_cast<int>(i / (static_cast<long long>(bc) * sc));
-        const float v = w[(static_cast<long long>(s) * bc + b) * kk + tap];
+        const float v = b < bcv ? w[(static_cast<long long>(s) * bcv + b) * kk + tap] : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         if (wd != nullptr) wd[i] = h;
         if (wu != nullptr) wu[(static_cast<long long>(tap) * bc + b) * sc + s] = h;
@@ -325,7 +343,7 @@ extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* w
     const int blocks = static_cast<int>(std::min<long long>((n + threads - 1) / threads, 148 * 16));
     pack_weights_kernel<<<blocks, threads, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wd),
                                                                    static_cast<__nv_bfloat16*>(wu), g->small_c,
-                                                                   g->big_c, kk);
+                                                                   g->big_c, bc_valid(g), kk);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -337,6 +355,7 @@ extern "C" int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big,
     if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "down: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
+    if (is_gemv(g)) return gemv_down(g, dtype, big, w, bias, small, out_f32, as_stream(stream));
     if (dtype == VG_BF16 && umma_down_ok(g)) return down_umma(g, big, w, bias, small, out_f32, as_stream(stream));
     return simt_conv_down(g, dtype, big, w, bias, small, out_f32, as_stream(stream));
 }
@@ -348,6 +367,7 @@ extern "C" int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small,
     if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "up: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
+    if (is_gemv(g)) return gemv_up(g, dtype, small, w, big, as_stream(stream));
     if (dtype == VG_BF16 && umma_up_ok(g)) return up_umma(g, small, w, big, as_stream(stream));
     return simt_conv_up(g, dtype, small, w, big, as_stream(stream));
 }
@@ -359,6 +379,7 @@ extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* sma
     if (big == nullptr || dw == nullptr || small == nullptr) return fail(VG_ERR_ARG, "wgrad: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
+    if (is_gemv(g)) return gemv_wgrad(g, dtype, small, big, dw, as_stream(stream));
     if (dtype == VG_BF16 && umma_wgrad_ok(g)) return wgrad_umma(g, small, big, dw, as_stream(stream));
     return simt_conv_wgrad(g, dtype, small, big, dw, as_stream(stream));
 }

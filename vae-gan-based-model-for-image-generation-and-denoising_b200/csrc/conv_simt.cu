@@ -23,6 +23,7 @@ __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bf
 
 struct Geo {
     int B, bh, bw, bc, sh, sw, sc, k, s, p;
+    int bcv;  // big-side channels present in the weight tensor (bc may be padded)
 };
 
 // ---- down: small[m=(b,oy,ox)][n=sc] = sum_{k=(tap,bc)} big(...) * w(sc, bc, tap)
@@ -52,6 +53,7 @@ struct DownOp {
     }
     __device__ float b(int kk, int n, int) const {
         const int tap = kk / g.bc, c = kk - tap * g.bc;
+        if (c >= g.bcv) return 0.f;
         return ldf(w + n * ws_sc + c * ws_bc + tap * ws_tap);
     }
     __device__ void store(int m, int n, float v, int) const {
@@ -104,6 +106,7 @@ struct UpOp {
         phase(z, &ay, &ax, &ky0, &kx0, &nky, &nkx);
         const int t = kk / g.sc, c = kk - t * g.sc;
         const int ky = ky0 + (t / nkx) * g.s, kx = kx0 + (t % nkx) * g.s;
+        if (n >= g.bcv) return 0.f;
         return ldf(w + c * ws_sc + n * ws_bc + (ky * g.k + kx) * ws_tap);
     }
     __device__ void store(int m, int n, float v, int z) const {
@@ -143,7 +146,7 @@ struct WgradOp {
     }
     __device__ void store(int m, int n, float v, int z) const {
         const int tap = z / splits;
-        atomicAdd(dw + (static_cast<long long>(m) * g.bc + n) * (g.k * g.k) + tap, v);
+        if (n < g.bcv) atomicAdd(dw + (static_cast<long long>(m) * g.bcv + n) * (g.k * g.k) + tap, v);
     }
 };
 
@@ -200,7 +203,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const Op op) {
 }
 
 Geo to_geo(const VgConvGeom* g) {
-    return Geo{g->batch, g->big_h, g->big_w, g->big_c, g->small_h, g->small_w, g->small_c, g->kernel, g->stride, g->pad};
+    return Geo{g->batch, g->big_h, g->big_w, g->big_c, g->small_h, g->small_w, g->small_c, g->kernel, g->stride, g->pad,
+               g->big_c_valid > 0 ? g->big_c_valid : g->big_c};
 }
 
 int cdiv(long long a, int b) { return static_cast<int>((a + b - 1) / b); }
@@ -217,7 +221,7 @@ int run_down(const VgConvGeom* g, const void* big, const void* w, const float* b
     op.out_f32 = out_f32;
     const long long kk = g->kernel * g->kernel;
     if (packed) { op.ws_tap = static_cast<long long>(g->small_c) * g->big_c; op.ws_sc = g->big_c; op.ws_bc = 1; }
-    else        { op.ws_sc = g->big_c * kk; op.ws_bc = kk; op.ws_tap = 1; }
+    else        { op.ws_sc = op.g.bcv * kk; op.ws_bc = kk; op.ws_tap = 1; }
     const long long M = static_cast<long long>(g->batch) * g->small_h * g->small_w;
     dim3 grid(cdiv(M, TM), cdiv(g->small_c, TN), 1);
     simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
@@ -234,7 +238,7 @@ int run_up(const VgConvGeom* g, const void* small, const void* w, void* big, boo
     op.out = static_cast<T*>(big);
     const long long kk = g->kernel * g->kernel;
     if (packed) { op.ws_tap = static_cast<long long>(g->small_c) * g->big_c; op.ws_bc = g->small_c; op.ws_sc = 1; }
-    else        { op.ws_sc = g->big_c * kk; op.ws_bc = kk; op.ws_tap = 1; }
+    else        { op.ws_sc = op.g.bcv * kk; op.ws_bc = kk; op.ws_tap = 1; }
     const int s = g->stride;
     const long long M = static_cast<long long>(g->batch) * ((g->big_h + s - 1) / s) * ((g->big_w + s - 1) / s);
     dim3 grid(cdiv(M, TM), cdiv(g->big_c, TN), s * s);

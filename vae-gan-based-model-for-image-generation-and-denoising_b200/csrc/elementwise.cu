@@ -198,20 +198,34 @@ int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
     return VG_OK;
 }
 
-// ---- finalize kernels (one thread per channel; fp64 combination of the per-block partials)
-__global__ void bn_fwd_finalize_kernel(const float* partial, const float* pivot, int blocks, int C, double n,
-                                       const float* gamma,
-                                       const float* beta, float* running_mean, float* running_var,
-                                       long long* num_batches_tracked, float momentum, float eps, float* mean_out,
-                                       float* rstd_out, float* scale_out, float* shift_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
-    if (c >= C) return;
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < blocks; ++b) {
-        s += partial[static_cast<long long>(b) * 2 * C + c];
-        ss += partial[static_cast<long long>(b) * 2 * C + C + c];
+// ---- finalize kernels: one WARP per channel, lanes stride over the per-block partials, fp64 shuffle reduction
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void gather_partials(const float* partial, int blocks, int C, int c, double* s, double* ss) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x & 31; i < blocks; i += 32) {
+        a += partial[static_cast<long long>(i) * 2 * C + c];
+        b += partial[static_cast<long long>(i) * 2 * C + C + c];
     }
+    *s = warp_sum_d(a);
+    *ss = warp_sum_d(b);
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* partial, const float* pivot, int blocks,
+                                                             int C, double n, const float* gamma, const float* beta,
+                                                             float* running_mean, float* running_var,
+                                                             long long* num_batches_tracked, float momentum, float eps,
+                                                             float* mean_out, float* rstd_out, float* scale_out,
+                                                             float* shift_out) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    if (c >= C) return;
+    double s, ss;
+    gather_partials(partial, blocks, C, c, &s, &ss);
+    if ((threadIdx.x & 31) != 0) return;
     const double dmean = s / n;
     const double mean = static_cast<double>(pivot[c]) + dmean;
     double var = ss / n - dmean * dmean;
@@ -220,8 +234,7 @@ __global__ void bn_fwd_finalize_kernel(const float* partial, const float* pivot,
     const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
     mean_out[c] = static_cast<float>(mean);
     rstd_out[c] = static_cast<float>(rstd);
-    const float scale = static_cast<float>(g * rstd);
-    scale_out[c] = scale;
+    scale_out[c] = static_cast<float>(g * rstd);
     shift_out[c] = static_cast<float>(bt - mean * g * rstd);
     if (running_mean != nullptr) {
         const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
@@ -240,15 +253,13 @@ __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, con
     shift[c] = bt - rm[c] * g * rstd;
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* partial, int blocks, int C, double n, float* dgamma, float* dbeta,
-                                       float* c1, float* c2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* partial, int blocks, int C, double n,
+                                                             float* dgamma, float* dbeta, float* c1, float* c2) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0, sx = 0.0;
-    for (int b = 0; b < blocks; ++b) {
-        s += partial[static_cast<long long>(b) * 2 * C + c];
-        sx += partial[static_cast<long long>(b) * 2 * C + C + c];
-    }
+    double s, sx;
+    gather_partials(partial, blocks, C, c, &s, &sx);
+    if ((threadIdx.x & 31) != 0) return;
     if (dbeta != nullptr) dbeta[c] += static_cast<float>(s);
     if (dgamma != nullptr) dgamma[c] += static_cast<float>(sx);
     c1[c] = static_cast<float>(s / n);
@@ -266,12 +277,12 @@ __global__ void colsum_generic_kernel(const T* __restrict__ x, long long rows, i
     out[c] += static_cast<float>(s);
 }
 
-__global__ void colsum_finalize_kernel(const float* partial, int blocks, int C, float* out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* partial, int blocks, int C, float* out) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0;
-    for (int b = 0; b < blocks; ++b) s += partial[static_cast<long long>(b) * 2 * C + c];
-    out[c] += static_cast<float>(s);
+    double s, unused;
+    gather_partials(partial, blocks, C, c, &s, &unused);
+    if ((threadIdx.x & 31) == 0) out[c] += static_cast<float>(s);
 }
 
 // ---- elementwise passes
@@ -361,37 +372,67 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const TI* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_kernel(const float* __restrict__ src,
                                                                const float* __restrict__ aux, T* __restrict__ dst,
-                                                               int B, int C, long long HW, int mode, float sigma,
-                                                               int clamp) {
+                                                               int B, int C, int Cd, long long HW, int mode,
+                                                               float sigma, int clamp) {
     const long long total = static_cast<long long>(B) * HW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long b = i / HW, p = i - b * HW;
-        for (int c = 0; c < C; ++c) {
-            const long long s = (b * C + c) * HW + p;
-            float v = src[s];
-            if (mode == 1) {
-                v = fmaf(sigma, aux[s], v);
-                if (clamp) v = fminf(1.f, fmaxf(-1.f, v));
-            } else if (mode == 2) {
-                const float y = aux[s];
-                v *= (1.f - y * y);
+        if (sizeof(T) == 2 && Cd == 16 && C <= 16) {
+            // padded 16-channel bf16 pixel: 32 contiguous bytes, two 16-byte stores
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = 0.f;
+                if (c < C) {
+                    const long long s = (b * C + c) * HW + p;
+                    float t = src[s];
+                    if (mode == 1) {
+                        t = fmaf(sigma, aux[s], t);
+                        if (clamp) t = fminf(1.f, fmaxf(-1.f, t));
+                    } else if (mode == 2) {
+                        const float y = aux[s];
+                        t *= (1.f - y * y);
+                    }
+                    v[c] = t;
+                }
             }
-            if constexpr (sizeof(T) == 4) dst[i * C + c] = v; else dst[i * C + c] = __float2bfloat16_rn(v);
+            float lo[8], hi[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
+            Vec<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(dst) + i * 16, lo);
+            Vec<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(dst) + i * 16 + 8, hi);
+            continue;
+        }
+        for (int c = 0; c < Cd; ++c) {
+            float v = 0.f;
+            if (c < C) {
+                const long long s = (b * C + c) * HW + p;
+                v = src[s];
+                if (mode == 1) {
+                    v = fmaf(sigma, aux[s], v);
+                    if (clamp) v = fminf(1.f, fmaxf(-1.f, v));
+                } else if (mode == 2) {
+                    const float y = aux[s];
+                    v *= (1.f - y * y);
+                }
+            }
+            if constexpr (sizeof(T) == 4) dst[i * Cd + c] = v; else dst[i * Cd + c] = __float2bfloat16_rn(v);
         }
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst,
-                                                               int B, int C, long long HW, int act, float slope) {
+                                                               int B, int C, int Cs, long long HW, int act,
+                                                               float slope) {
     const long long total = static_cast<long long>(B) * HW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long b = i / HW, p = i - b * HW;
         for (int c = 0; c < C; ++c) {
             float v;
-            if constexpr (sizeof(T) == 4) v = src[i * C + c]; else v = __bfloat162float(src[i * C + c]);
+            if constexpr (sizeof(T) == 4) v = src[i * Cs + c]; else v = __bfloat162float(src[i * Cs + c]);
             dst[(b * C + c) * HW + p] = act_fwd(v, act, slope);
         }
     }
@@ -431,7 +472,7 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
     a.pivot = ws + static_cast<size_t>(p.blocks) * 2 * C;
     rc = launch_reduce<0>(dt, a, p.blocks, as_stream(stream));
     if (rc != VG_OK) return rc;
-    bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+    bn_fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
         ws, a.pivot, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
         momentum, eps, mean_out, rstd_out, scale_out, shift_out);
     VG_LAUNCHED();
@@ -503,7 +544,7 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.act = act; a.slope = slope; a.partial = ws;
     rc = launch_reduce<1>(dt, a, p.blocks, st);
     if (rc != VG_OK) return rc;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, p.blocks, C, static_cast<double>(rows), dgamma, dbeta,
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(ws, p.blocks, C, static_cast<double>(rows), dgamma, dbeta,
                                                            c1, c2);
     VG_LAUNCHED();
     const int V = dt == VG_BF16 ? 8 : 4;
@@ -575,42 +616,44 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
     a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
     rc = launch_reduce<2>(dt, a, p.blocks, as_stream(stream));
     if (rc != VG_OK) return rc;
-    colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(ws, p.blocks, C, out);
+    colsum_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, p.blocks, C, out);
     VG_LAUNCHED();
     return VG_OK;
 }
 
 extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int B, int C, int H, int W,
-                               int mode, float sigma, int clamp, void* stream) {
+                               int Cd, int mode, float sigma, int clamp, void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (src == nullptr || dst == nullptr || (mode != 0 && aux == nullptr))
         return fail(VG_ERR_ARG, "nchw_to_nhwc: null pointer");
+    if (Cd < C) return fail(VG_ERR_SHAPE, "nchw_to_nhwc: dst_channels %d < channels %d", Cd, C);
     const long long HW = static_cast<long long>(H) * W;
     const int g = grid_for(B * HW);
     if (dt == VG_BF16)
         nchw_to_nhwc_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
-            src, aux, static_cast<__nv_bfloat16*>(dst), B, C, HW, mode, sigma, clamp);
+            src, aux, static_cast<__nv_bfloat16*>(dst), B, C, Cd, HW, mode, sigma, clamp);
     else
-        nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, HW,
-                                                                          mode, sigma, clamp);
+        nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, Cd,
+                                                                          HW, mode, sigma, clamp);
     VG_LAUNCHED();
     return VG_OK;
 }
 
-extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, float* dst, int B, int C, int H, int W, VgAct act,
+extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, int Cs, float* dst, int B, int C, int H, int W, VgAct act,
                                float slope, void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (src == nullptr || dst == nullptr) return fail(VG_ERR_ARG, "nhwc_to_nchw: null pointer");
+    if (Cs < C) return fail(VG_ERR_SHAPE, "nhwc_to_nchw: src_channels %d < channels %d", Cs, C);
     const long long HW = static_cast<long long>(H) * W;
     const int g = grid_for(B * HW);
     if (dt == VG_BF16)
         nhwc_to_nchw_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
-            static_cast<const __nv_bfloat16*>(src), dst, B, C, HW, act, slope);
+            static_cast<const __nv_bfloat16*>(src), dst, B, C, Cs, HW, act, slope);
     else
-        nhwc_to_nchw_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(static_cast<const float*>(src), dst, B, C, HW,
-                                                                          act, slope);
+        nhwc_to_nchw_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(static_cast<const float*>(src), dst, B, C, Cs,
+                                                                          HW, act, slope);
     VG_LAUNCHED();
     return VG_OK;
 }

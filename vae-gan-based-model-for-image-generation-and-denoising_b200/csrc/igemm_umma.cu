@@ -167,44 +167,51 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// wgrad-type kernel: both operands MN-major (pixels are the reduction dimension)
+// wgrad-type kernel: both operands MN-major (pixels are the reduction dimension).
+// Two smem rings: the P tile of a pixel block is loaded ONCE and reused by every tap of the CTA's tap group,
+// the shifted Q tiles stream through their own ring.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpix = p.tw * p.th * p.tb;
-    const int atom_bytes = kpix * 128;  // one 64-channel MN atom: kpix rows of 128 B
-    const int n_atoms = p.n_tile / 64;
-    const int a_stage = 2 * atom_bytes;  // always room for M = 128 (second atom may stay unwritten)
-    const int b_stage = n_atoms * atom_bytes;
-    const int stages = p.stages;
+    const int p_row = p.p_atom_c * 2, q_row = p.q_atom_c * 2;       // bytes per pixel row inside one atom
+    const int p_atom_bytes = kpix * p_row, q_atom_bytes = kpix * q_row;
+    const int n_atoms = p.n_tile / p.q_atom_c;
+    const int a_stage = kpix * 256;                                  // room for all 128 M rows (128 ch x 2 B) per pixel
+    const int b_stage = n_atoms * q_atom_bytes;
+    const int SA = p.stages_a, SB = p.stages_b;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + stages * a_stage;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
-    uint64_t* empty = full + kMaxStages;
-    uint64_t* tmem_full = empty + kMaxStages;
+    uint8_t* sB = smem + SA * a_stage;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(sB + SB * b_stage);
+    uint64_t* empty_a = full_a + kMaxStages;
+    uint64_t* full_b = empty_a + kMaxStages;
+    uint64_t* empty_b = full_b + kMaxStages;
+    uint64_t* tmem_full = empty_b + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int split = blockIdx.x;
     const int m_tile = blockIdx.y / p.n_tiles, n_tile_idx = blockIdx.y % p.n_tiles;
-    const int m0 = m_tile * p.m_atoms * 64, n0 = n_tile_idx * p.n_tile;
+    const int m0 = m_tile * p.m_atoms * p.p_atom_c, n0 = n_tile_idx * p.n_tile;
     const int tap0 = blockIdx.z * p.taps_per_cta;
     const int ntap = min(p.taps_per_cta, p.num_taps - tap0);
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pt_begin = static_cast<int>(static_cast<long long>(total_tiles) * split / p.splits);
     const int pt_end = static_cast<int>(static_cast<long long>(total_tiles) * (split + 1) / p.splits);
-    const int iters = (pt_end - pt_begin) * ntap;
     const uint32_t ncols = tmem_cols_for(p.taps_per_cta * p.n_tile);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.pmap);
         for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.qmap[v]);
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
+        for (int s = 0; s < SA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
@@ -219,48 +226,56 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int pt = pt_begin; pt < pt_end; ++pt) {
+            int ia = 0, ib = 0;
+            for (int pt = pt_begin; pt < pt_end; ++pt, ++ia) {
                 int t = pt;
                 const int j0 = (t % p.tiles_w) * p.tw;
                 t /= p.tiles_w;
                 const int i0 = (t % p.tiles_h) * p.th;
                 const int b0 = (t / p.tiles_h) * p.tb;
-                for (int tl = 0; tl < ntap; ++tl, ++it) {
+                const int sa = ia % SA;
+                mbar_wait(&empty_a[sa], ((ia / SA) & 1) ^ 1);
+                mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
+                for (int a = 0; a < p.m_atoms; ++a)
+                    tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0, i0,
+                                b0);
+                for (int tl = 0; tl < ntap; ++tl, ++ib) {
                     const IgemmTap tap = p.taps[tap0 + tl];
-                    const int s = it % stages;
-                    const uint32_t par = (it / stages) & 1;
-                    mbar_wait(&empty[s], par ^ 1);
-                    mbar_expect_tx(&full[s], (p.m_atoms + n_atoms) * atom_bytes);
-                    for (int a = 0; a < p.m_atoms; ++a)
-                        tma_load_4d(sA + s * a_stage + a * atom_bytes, &p.pmap, &full[s], m0 + a * 64, j0, i0, b0);
+                    const int sb = ib % SB;
+                    mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
+                    mbar_expect_tx(&full_b[sb], b_stage);
                     for (int a = 0; a < n_atoms; ++a)
-                        tma_load_4d(sB + s * b_stage + a * atom_bytes, &p.qmap[tap.view], &full[s], n0 + a * 64,
-                                    j0 + tap.dx, i0 + tap.dy, b0);
+                        tma_load_4d(sB + sb * b_stage + a * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
+                                    n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 1, 1);
+            const uint32_t p_layout = p.p_atom_c == 64 ? 2u : 4u;
+            const uint32_t q_layout = p.q_atom_c == 64 ? 2u : (p.q_atom_c == 32 ? 4u : 6u);
             const int ksteps = kpix / 16;
-            int it = 0;
-            for (int pt = pt_begin; pt < pt_end; ++pt) {
-                for (int tl = 0; tl < ntap; ++tl, ++it) {
-                    const int s = it % stages;
-                    const uint32_t par = (it / stages) & 1;
-                    mbar_wait(&full[s], par);
+            int ia = 0, ib = 0;
+            for (int pt = pt_begin; pt < pt_end; ++pt, ++ia) {
+                const int sa = ia % SA;
+                mbar_wait(&full_a[sa], (ia / SA) & 1);
+                const uint32_t a_addr = smem_u32(sA + sa * a_stage);
+                for (int tl = 0; tl < ntap; ++tl, ++ib) {
+                    const int sb = ib % SB;
+                    mbar_wait(&full_b[sb], (ib / SB) & 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + s * a_stage);
-                    const uint32_t b_addr = smem_u32(sB + s * b_stage);
+                    const uint32_t b_addr = smem_u32(sB + sb * b_stage);
                     for (int k = 0; k < ksteps; ++k) {
-                        // 16 pixel rows per UMMA: 2 groups of 8 rows (SBO = 1024 B); MN atoms LBO apart
-                        umma_bf16(tmem_base + tl * p.n_tile, make_smem_desc(a_addr + k * 2048, atom_bytes, 1024, 2),
-                                  make_smem_desc(b_addr + k * 2048, atom_bytes, 1024, 2), idesc,
+                        // one UMMA consumes 16 pixel rows: two 8-row groups (SBO apart); MN atoms are LBO apart
+                        umma_bf16(tmem_base + tl * p.n_tile,
+                                  make_smem_desc(a_addr + k * 16 * p_row, p_atom_bytes, 8 * p_row, p_layout),
+                                  make_smem_desc(b_addr + k * 16 * q_row, q_atom_bytes, 8 * q_row, q_layout), idesc,
                                   (pt != pt_begin || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&empty_b[sb]);
                 }
+                umma_commit(&empty_a[sa]);
             }
             umma_commit(tmem_full);
         }
@@ -268,22 +283,46 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const bool valid = (row < p.m_atoms * 64) && (m < p.m_valid) && (iters > 0);
+        const bool valid = (row < p.m_atoms * p.p_atom_c) && (m < p.m_valid) && (pt_end > pt_begin);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int tl = 0; tl < ntap; ++tl) {
-            const int tap_id = p.taps[tap0 + tl].tap_id;
-            float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(tap_id) * p.s_tap;
-            for (int c = 0; c < p.n_tile; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + tl * p.n_tile + c, v);
-                tmem_ld_wait();
-                if (valid) {
+        if (p.vec4_taps) {
+            // dw[m][n][tap0 + 4g .. +3] is 16 contiguous bytes: one vector reduction per (n, group of 4 taps)
+            for (int g = 0; g < ntap; g += 4) {
+                float* dst = p.dw + static_cast<long long>(m) * p.s_m + (tap0 + g);
+                for (int c = 0; c < p.n_tile; c += 16) {
+                    uint32_t v0[16], v1[16], v2[16], v3[16];
+                    tmem_ld_32x16(taddr + (g + 0) * p.n_tile + c, v0);
+                    tmem_ld_32x16(taddr + (g + 1) * p.n_tile + c, v1);
+                    tmem_ld_32x16(taddr + (g + 2) * p.n_tile + c, v2);
+                    tmem_ld_32x16(taddr + (g + 3) * p.n_tile + c, v3);
+                    tmem_ld_wait();
+                    if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + c + j;
-                        if (n < p.n_valid) atomicAdd(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.n_valid)
+                                red_add_v4(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v0[j]),
+                                           __uint_as_float(v1[j]), __uint_as_float(v2[j]), __uint_as_float(v3[j]));
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int tl = 0; tl < ntap; ++tl) {
+                const int tap_id = p.taps[tap0 + tl].tap_id;
+                float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(tap_id) * p.s_tap;
+                for (int c = 0; c < p.n_tile; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + tl * p.n_tile + c, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.n_valid) atomicAdd(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static constexpr int kBarrierBytes = (2 * kMaxStages + 1) * 8 + 16;
+static constexpr int kBarrierBytes = (4 * kMaxStages + 1) * 8 + 16;
 
 static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_bytes + 1024 + kBarrierBytes; }
 
@@ -323,8 +362,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int kpix = p.tw * p.th * p.tb;
-    const int stage_bytes = (2 + p.n_tile / 64) * kpix * 128;
-    const int smem = smem_bytes_for(p.stages, stage_bytes);
+    const int smem = p.stages_a * kpix * 256 + p.stages_b * p.n_tile * kpix * 2 + 1024 + kBarrierBytes;
     const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
     dim3 grid(p.splits, p.m_tiles * p.n_tiles, tap_groups);
     igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);

@@ -54,14 +54,17 @@ struct alignas(64) WgradParams {
     int taps_per_cta;      // accumulators resident in TMEM per CTA (taps_per_cta * n_tile <= 512)
     int tw, th, tb;        // pixel box; tw*th*tb = kpix (multiple of 16, <= 128)
     int tiles_w, tiles_h, tiles_b;
-    int m_atoms;           // P channels per CTA / 64 (1 or 2)
-    int n_tile;            // Q channels per CTA (multiple of 64, <= 256)
+    int p_atom_c;          // channels per MN-major atom of P: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int m_atoms;           // P atoms actually loaded per CTA (UMMA M is always 128; missing atoms are ignored rows)
+    int q_atom_c;          // channels per MN-major atom of Q: 64 / 32 / 16
+    int n_tile;            // Q channels per CTA = UMMA N (multiple of q_atom_c and of 16, <= 256)
     int m_tiles, n_tiles;
     int splits;            // split of the pixel-tile range across CTAs
-    int stages;
+    int stages_a, stages_b;
     float* dw;             // fp32, accumulated with red.global.add
     long long s_m, s_n, s_tap;  // element strides of dw for (P channel, Q channel, tap)
     int m_valid, n_valid;  // channel counts actually present (rows/cols beyond are dropped)
+    int vec4_taps;         // 1: taps of a CTA are 4-aligned and contiguous in dw -> 16-byte vector reductions
 };
 
 // Host-side launchers (return cudaError_t as int).

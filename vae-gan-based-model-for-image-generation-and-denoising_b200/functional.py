@@ -37,6 +37,12 @@ def _contig(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def padded_channels(c: int, dtype) -> int:
+    """Channels per pixel of an internal NHWC tensor.  The bf16 path stores narrow (3-channel image) tensors with 16
+    channels, zeros above the real ones, so that they are legal TMA / tcgen05 operands (32-byte rows)."""
+    return 16 if (dtype == torch.bfloat16 and c < 16) else c
+
+
 # --------------------------------------------------------------------------------------------- geometry
 @dataclass(frozen=True)
 class ConvSpec:
@@ -58,16 +64,20 @@ class ConvSpec:
             return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
         return (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
 
-    def geom(self, batch: int, in_h: int, in_w: int) -> VgConvGeom:
+    def geom(self, batch: int, in_h: int, in_w: int, big_c_tensor: Optional[int] = None) -> VgConvGeom:
+        """`big_c_tensor`: channels per pixel of the big-side tensor when it is channel-padded (>= self.big_c)."""
         oh, ow = self.out_hw(in_h, in_w)
+        bc = big_c_tensor or self.big_c
+        valid = self.big_c if bc != self.big_c else 0
         if self.kind == "down":
-            return VgConvGeom(batch, in_h, in_w, self.big_c, oh, ow, self.small_c, self.kernel, self.stride, self.pad)
-        return VgConvGeom(batch, oh, ow, self.big_c, in_h, in_w, self.small_c, self.kernel, self.stride, self.pad)
+            return VgConvGeom(batch, in_h, in_w, bc, oh, ow, self.small_c, self.kernel, self.stride, self.pad, valid)
+        return VgConvGeom(batch, oh, ow, bc, in_h, in_w, self.small_c, self.kernel, self.stride, self.pad, valid)
 
 
 # --------------------------------------------------------------------------------------------- raw ops
 def pack_weights(w: torch.Tensor, g: VgConvGeom) -> Tuple[torch.Tensor, torch.Tensor]:
-    """fp32 master [small_c, big_c, k, k] -> (wd[tap, small_c, big_c], wu[tap, big_c, small_c]) bf16."""
+    """fp32 master [small_c, big_c_valid, k, k] -> (wd[tap, small_c, big_c], wu[tap, big_c, small_c]) bf16
+    (zero-filled for padded big-side channels)."""
     kk = g.kernel * g.kernel
     wd = torch.empty((kk, g.small_c, g.big_c), dtype=torch.bfloat16, device=w.device)
     wu = torch.empty((kk, g.big_c, g.small_c), dtype=torch.bfloat16, device=w.device)
@@ -93,7 +103,8 @@ def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom) -> torch.Tensor
 def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dw[small_c, big_c, k, k] (+)= wgrad; a fresh zeroed buffer is created when `dw` is None."""
     if dw is None:
-        dw = torch.zeros((g.small_c, g.big_c, g.kernel, g.kernel), dtype=torch.float32, device=small.device)
+        dw = torch.zeros((g.small_c, g.big_c_valid or g.big_c, g.kernel, g.kernel), dtype=torch.float32,
+                         device=small.device)
     call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _stream())
     return dw
 
@@ -160,17 +171,21 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
 
 def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, mode: int = 0, sigma: float = 0.0,
                  clamp: bool = False) -> torch.Tensor:
+    """fp32 NCHW -> internal NHWC (channel-padded per `padded_channels`)."""
     B, C, H, W = src.shape
-    dst = torch.empty((B, H, W, C), dtype=dtype, device=src.device)
-    call("vg_nchw_to_nhwc", _p(src), _p(aux), _p(dst), _DT[dtype], B, C, H, W, mode, float(sigma), int(clamp),
+    Cd = padded_channels(C, dtype)
+    dst = torch.empty((B, H, W, Cd), dtype=dtype, device=src.device)
+    call("vg_nchw_to_nhwc", _p(src), _p(aux), _p(dst), _DT[dtype], B, C, H, W, Cd, mode, float(sigma), int(clamp),
          _stream())
     return dst
 
 
-def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0) -> torch.Tensor:
-    B, H, W, C = src.shape
+def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0, channels: Optional[int] = None) -> torch.Tensor:
+    """internal NHWC -> fp32 NCHW, keeping the first `channels` channels of a padded tensor."""
+    B, H, W, Cs = src.shape
+    C = channels or Cs
     dst = torch.empty((B, C, H, W), dtype=torch.float32, device=src.device)
-    call("vg_nhwc_to_nchw", _p(src), _DT[src.dtype], _p(dst), B, C, H, W, act, float(slope), _stream())
+    call("vg_nhwc_to_nchw", _p(src), _DT[src.dtype], Cs, _p(dst), B, C, H, W, act, float(slope), _stream())
     return dst
 
 
@@ -215,8 +230,17 @@ class ConvLayerFn(torch.autograd.Function):
                 cache: PackedWeights, out_f32: bool):
         _require_cuda(x, "ConvLayerFn")
         x = _contig(x)
-        B, H, W, _ = x.shape
-        g = spec.geom(B, H, W)
+        B, H, W, Cx = x.shape
+        if spec.kind == "down":
+            if Cx != padded_channels(spec.big_c, x.dtype):
+                raise RuntimeError(f"Given groups=1, weight of size {list(weight.shape)}, expected input with "
+                                   f"{spec.big_c} channels, but got {Cx} channels instead")
+            g = spec.geom(B, H, W, Cx)
+        else:
+            if Cx != spec.small_c:
+                raise RuntimeError(f"Given transposed=1, weight of size {list(weight.shape)}, expected input with "
+                                   f"{spec.small_c} channels, but got {Cx} channels instead")
+            g = spec.geom(B, H, W, padded_channels(spec.big_c, x.dtype))
         if x.dtype == torch.bfloat16:
             wd, wu = cache.get(weight, g)
             w_fwd = wd if spec.kind == "down" else wu
@@ -303,19 +327,20 @@ class ToNHWCFn(torch.autograd.Function):
         _require_cuda(x, "ToNHWCFn")
         if x.dtype != torch.float32:
             raise _lib.VaeganB200Error(f"module inputs must be float32 (got {x.dtype}), like the reference's loaders")
+        ctx.channels = x.shape[1]
         return nchw_to_nhwc(_contig(x), dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        return nhwc_to_nchw(_contig(dy)), None
+        return nhwc_to_nchw(_contig(dy), channels=ctx.channels), None
 
 
 class ToNCHWActFn(torch.autograd.Function):
     """internal NHWC activation -> fp32 NCHW module output with the final Tanh / no-op fused in."""
 
     @staticmethod
-    def forward(ctx, x, act):
-        y = nhwc_to_nchw(_contig(x), act)
+    def forward(ctx, x, act, channels=None):
+        y = nhwc_to_nchw(_contig(x), act, channels=channels)
         ctx.act, ctx.dtype = act, x.dtype
         ctx.save_for_backward(y if act == ACT_TANH else None)
         return y
@@ -325,8 +350,8 @@ class ToNCHWActFn(torch.autograd.Function):
         (y,) = ctx.saved_tensors
         dy = _contig(dy)
         if ctx.act == ACT_TANH:
-            return nchw_to_nhwc(dy, ctx.dtype, aux=y, mode=2), None
-        return nchw_to_nhwc(dy, ctx.dtype), None
+            return nchw_to_nhwc(dy, ctx.dtype, aux=y, mode=2), None, None
+        return nchw_to_nhwc(dy, ctx.dtype), None, None
 
 
 class PointwiseActFn(torch.autograd.Function):

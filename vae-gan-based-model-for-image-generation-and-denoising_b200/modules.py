@@ -128,7 +128,7 @@ class ConvBlock(nn.Module):
         """Stand-alone use takes / returns fp32 NCHW like the reference; Encoder chains blocks in NHWC instead."""
         dtype = F_.PRECISION_DTYPE[_DEFAULT_PRECISION]
         y = self._layer()(F_.ToNHWCFn.apply(x, dtype), self.training)
-        return F_.ToNCHWActFn.apply(y, ACT_NONE)
+        return F_.ToNCHWActFn.apply(y, ACT_NONE, self.conv.out_channels)
 
 
 class Encoder(_KernelModule):
@@ -225,7 +225,9 @@ class Generator(_KernelModule):
         return self._plan[1]
 
     def forward(self, input):
-        return F_.ToNCHWActFn.apply(self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype())), self._layers()[-1].act)
+        last = self._layers()[-1]
+        return F_.ToNCHWActFn.apply(self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype())), last.act,
+                                    last.conv.out_channels)
 
     def forward_nhwc(self, h):
         """z as NHWC [B,1,1,nz] -> RAW last-conv output NHWC [B,H,W,nc]; the final Tanh rides the NCHW store."""

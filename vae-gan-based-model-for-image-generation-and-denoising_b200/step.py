@@ -95,7 +95,7 @@ class _ReconHubFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         recon, real, loss_out, ws = ctx.saved_tensors
-        d_adv = F_.nhwc_to_nchw(dy.contiguous())
+        d_adv = F_.nhwc_to_nchw(dy.contiguous(), channels=recon.shape[1])
         d_total = torch.empty_like(recon)
         call("vg_mse", _p(recon), _p(real), recon.numel(), 1.0, _p(d_adv), _p(d_total), _p(loss_out), _p(ws),
              ws.numel() * 4, _stream())
@@ -175,7 +175,7 @@ class VAEGANStep:
             enc_in = F_.nchw_to_nhwc(real, self.dtype)
         mu, logvar = E.forward_nhwc(enc_in)
         z = _ReparamFn.apply(mu, logvar, s["eps"], loss[3:4], s["kl_w"], self.dtype)
-        recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH)
+        recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH, 3)
 
         # ---- instance noise                                                           (:88-92)
         real_noisy = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst)
@@ -238,7 +238,10 @@ class VAEGANStep:
             if s["n_den"] is not None:
                 s["n_den"].copy_(n_denoise, non_blocking=True)
         if not self.use_graph:
+            lib = F_._lib.load()
+            n0 = lib.vg_launch_count()
             self._run(gen_noise=not injected)
+            self.launches_per_step = int(lib.vg_launch_count() - n0)
         else:
             key = (not injected)
             if self._graph is None or self._graph[0] != key:
@@ -252,8 +255,11 @@ class VAEGANStep:
                 torch.cuda.synchronize()
                 self._restore_state(self._snapshot)
                 g = torch.cuda.CUDAGraph()
+                lib = F_._lib.load()
+                n0 = lib.vg_launch_count()
                 with torch.cuda.graph(g):
                     self._run(gen_noise=key)
+                self.launches_per_step = int(lib.vg_launch_count() - n0)   # kernel nodes of ours in the graph
                 self._graph = (key, g)
                 self._restore_state(self._snapshot)
                 self._snapshot = None
