@@ -207,8 +207,7 @@ def run_gpu_arm(args):
     e2e_value = world * B * args.steps / float(t)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return 0
 
     peaks = _peaks()
@@ -242,10 +241,18 @@ def run_gpu_arm(args):
         "cpu_baseline": cpu,
         "final_total_loss": final_total,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _finish(world)
     return 0
+
+
+def _finish(world: int):
+    """Leave without tearing the NCCL communicator down: destroy_process_group() after NCCL collectives were captured
+    into a CUDA graph was observed to hang on this stack; the processes are about to exit anyway."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _kernel_microbench(torch, vb, dev):

@@ -84,8 +84,12 @@ int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* wd, void* wu
  * down  replaces F.conv2d            (main_vae.py:28, gan_code.py:89) and the dgrad of F.conv_transpose2d
  * up    replaces F.conv_transpose2d  (gan_code.py:54)               and the dgrad of F.conv2d
  * wgrad replaces the weight gradient of both (autograd of vaegan_code.py:104,133) */
+/* Optional scratch for vg_conv_down (ws may be NULL): with a buffer of vg_conv_down_workspace_bytes() the tensor-core
+ * path splits a long reduction over many CTAs when the output has only a few tiles (e.g. the dgrad of the
+ * generator's first ConvTranspose2d: batch x 16384 -> batch x nz). */
+size_t vg_conv_down_workspace_bytes(const VgConvGeom* g);
 int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias, void* small,
-                 int out_f32, void* stream);
+                 int out_f32, void* ws, size_t ws_bytes, void* stream);
 int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big, void* stream);
 /* dw (fp32, reference layout [small_c][big_c][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient. */
 int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* stream);

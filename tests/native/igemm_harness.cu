@@ -129,13 +129,16 @@ static bool run_case(const Case& c, bool verbose_fail) {
         CK(cudaMalloc(&d_out_small, n_small * 4));
         CK(cudaMalloc(&d_out_big, n_big * 4));
         CK(cudaMalloc(&d_dw, n_w * 4));
+        void* d_ws = nullptr;
+        const size_t ws_bytes = vg_conv_down_workspace_bytes(&g);
+        CK(cudaMalloc(&d_ws, ws_bytes));
         CK(cudaMemset(d_out_small, 0xFF, n_small * 4));
         CK(cudaMemset(d_out_big, 0xFF, n_big * 4));
         CK(cudaMemset(d_dw, 0, n_w * 4));
         const void* w_down = mode == 0 ? (const void*)d_w : d_wd;
         const void* w_up = mode == 0 ? (const void*)d_w : d_wu;
         int rc;
-        rc = vg_conv_down(&g, dt, d_big, w_down, d_bias, d_out_small, 0, nullptr);
+        rc = vg_conv_down(&g, dt, d_big, w_down, d_bias, d_out_small, 0, d_ws, ws_bytes, nullptr);
         if (rc != VG_OK) { printf("  down failed (%d): %s\n", rc, vg_last_error()); ok = false; }
         rc = vg_conv_up(&g, dt, d_small, w_up, d_out_big, nullptr);
         if (rc != VG_OK) { printf("  up failed (%d): %s\n", rc, vg_last_error()); ok = false; }
@@ -185,7 +188,7 @@ static bool run_case(const Case& c, bool verbose_fail) {
         }
         ok = ok && o1 && o2 && o3;
         cudaFree(d_big); cudaFree(d_small); cudaFree(d_out_small); cudaFree(d_out_big); cudaFree(d_w);
-        cudaFree(d_bias); cudaFree(d_dw);
+        cudaFree(d_bias); cudaFree(d_dw); cudaFree(d_ws);
         if (d_wd) cudaFree(d_wd);
         if (d_wu) cudaFree(d_wu);
     }
@@ -216,7 +219,7 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
     CK(cudaEventCreate(&e1));
     for (int op = 0; op < 3; ++op) {
         auto run = [&]() {
-            if (op == 0) return vg_conv_down(&g, VG_BF16, d_big, d_wd, nullptr, d_small, 0, nullptr);
+            if (op == 0) return vg_conv_down(&g, VG_BF16, d_big, d_wd, nullptr, d_small, 0, nullptr, 0, nullptr);
             if (op == 1) return vg_conv_up(&g, VG_BF16, d_small, d_wu, d_big, nullptr);
             return vg_conv_wgrad(&g, VG_BF16, d_small, d_big, d_dw, nullptr);
         };
@@ -257,6 +260,8 @@ int main(int argc, char** argv) {
         {"k3s1p1 16x16 c3<-64 B2 (image)", geom(2, 16, 16, 3, 64, 3, 1, 1)},
         {"k4s1p0 4x4 c512->1 B8 (gemv)", geom(8, 4, 4, 512, 1, 4, 1, 0)},
         {"k4s2p1 16x16 c16->32 B4", geom(4, 16, 16, 16, 32, 4, 2, 1)},
+        {"k4s1p0 4x4 c1024->128 B64 (splitK)", geom(64, 4, 4, 1024, 128, 4, 1, 0)},
+        {"k4s2p1 64x64 c16->64 B2 (padded)", geom(2, 64, 64, 16, 64, 4, 2, 1)},
     };
     bool all = true;
     for (const Case& c : cases) {

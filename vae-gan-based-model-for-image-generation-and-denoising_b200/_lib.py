@@ -33,7 +33,8 @@ PROTOTYPES = {
     "vg_device_check": (c_int, []),
     "vg_launch_count": (c_longlong, []),
     "vg_pack_weights_bf16": (c_int, [_G, _P, _P, _P, _P]),
-    "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P]),
+    "vg_conv_down_workspace_bytes": (c_size_t, [_G]),
+    "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),
     "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P]),
     "vg_reduce_workspace_bytes": (c_size_t, [c_longlong, c_int]),

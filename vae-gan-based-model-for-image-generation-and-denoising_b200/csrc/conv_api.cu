@@ -100,8 +100,14 @@ bool umma_wgrad_ok(const VgConvGeom* g) {
 }
 
 // ---------------------------------------------------------------------------------------------- down
+static int pick_ksplit(int tiles, int iters) {
+    // few output tiles and a long (tap, channel-chunk) loop: spread the reduction over ~one wave of CTAs
+    if (tiles >= 74 || iters < 32) return 1;
+    return std::max(1, std::min(iters / 8, 148 / tiles));
+}
+
 static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const float* bias, void* small,
-                     int out_f32, cudaStream_t stream) {
+                     int out_f32, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (!aligned16(big) || !aligned16(wd) || !aligned16(small)) return fail(VG_ERR_ALIGN, "down: 16-byte alignment");
     IgemmParams p;
     std::memset(&p, 0, sizeof(p));
@@ -150,9 +156,15 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     p.out_C = g->small_c;
     p.osy = p.osx = 1;
     p.bias = bias;
+    const size_t acc_bytes = static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
+    const int ks = pick_ksplit(p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles, p.taps_per_phase * p.c_chunks);
+    if (ks > 1 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        p.ksplit = ks;
+        p.splitk_acc = static_cast<float*>(ws);
+    }
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
-    note_launch();
+    note_launch(p.ksplit > 1 ? 2 : 1);
     return VG_OK;
 }
 
@@ -348,15 +360,21 @@ extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* w
     return VG_OK;
 }
 
+extern "C" size_t vg_conv_down_workspace_bytes(const VgConvGeom* g) {
+    if (g == nullptr) return 0;
+    return static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
+}
+
 extern "C" int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias,
-                            void* small, int out_f32, void* stream) {
+                            void* small, int out_f32, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_geom(g);
     if (rc != VG_OK) return rc;
     if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "down: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
     if (is_gemv(g)) return gemv_down(g, dtype, big, w, bias, small, out_f32, as_stream(stream));
-    if (dtype == VG_BF16 && umma_down_ok(g)) return down_umma(g, big, w, bias, small, out_f32, as_stream(stream));
+    if (dtype == VG_BF16 && umma_down_ok(g))
+        return down_umma(g, big, w, bias, small, out_f32, ws, ws_bytes, as_stream(stream));
     return simt_conv_down(g, dtype, big, w, bias, small, out_f32, as_stream(stream));
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -69,12 +70,19 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-channel reductions over the rows of an NHWC [rows][C] tensor.
-//   MODE 0: (sum x, sum x^2)                              -> BatchNorm training statistics
+// Per-channel reductions over the rows of an NHWC [rows][C] tensor, finalized in the SAME launch.
+//   MODE 0: (sum d, sum d^2), d = x - pivot            -> BatchNorm training statistics (+ running stats, affine)
 //   MODE 1: (sum dz, sum dz*xhat), dz = dy*act'(x*scale+shift), xhat = (x-mean)*rstd   -> BatchNorm backward
-//   MODE 2: (sum x, unused)                               -> bias gradient
-// Block b reduces rows [b*rows_per_block, ...) and writes partial[b][0..1][C].
+//   MODE 2: (sum x)                                    -> bias gradient
+// Every block reduces its row range in registers / shared memory and adds its per-channel partials (fp64 atomics) to
+// a zero-initialised accumulator slot; the block that arrives last (atomic ticket) turns the totals into the
+// per-channel outputs and re-zeroes the slot, so no separate finalize kernel and no memset is needed.
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxChannels = 4096;
+constexpr int kSlots = 64;
+__device__ double g_acc[kSlots][2 * kMaxChannels];   // zero at module load; every launch leaves its slot zero again
+__device__ unsigned int g_ticket[kSlots];
+
 struct ReduceArgs {
     const void* x;
     const void* dy;
@@ -84,14 +92,29 @@ struct ReduceArgs {
     long long rows_per_block;
     int act;
     float slope;
-    float* partial;
-    float* pivot;   // MODE 0: [C] per-channel pivot (row 0 of x), written by block 0, consumed by the finalize kernel
+    int slot;
+    // finalize, MODE 0
+    const float *gamma, *beta;
+    float *running_mean, *running_var;
+    long long* num_batches_tracked;
+    float momentum, eps;
+    float *mean_out, *rstd_out, *scale_out, *shift_out;
+    // finalize, MODE 1
+    float *dgamma, *dbeta, *c1, *c2;
+    // finalize, MODE 2
+    float* colsum_out;
 };
+
+template <typename T>
+__device__ __forceinline__ float load1(const T* p) {
+    if constexpr (sizeof(T) == 4) return *p; else return __bfloat162float(*p);
+}
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceArgs a) {
     constexpr int V = Vec<T>::N;
     __shared__ float red[kThreads][2 * V + 1];
+    __shared__ bool is_last;
     const int tpr = a.C / V;                       // vectors per row (power of two)
     const int lanes = tpr < kThreads ? tpr : kThreads;
     const int rows_per_iter = kThreads / lanes;
@@ -100,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     const long long r1 = min(a.rows, r0 + a.rows_per_block);
     const T* x = static_cast<const T*>(a.x);
     const T* dy = static_cast<const T*>(a.dy);
-    float* out = a.partial + static_cast<long long>(blockIdx.x) * 2 * a.C;
+    double* acc = g_acc[a.slot];
 
     for (int cg = 0; cg < tpr / lanes; ++cg) {
         const int c0 = (cg * lanes + lane) * V;
@@ -113,10 +136,6 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
             // shifted-data sums: accumulate (x - K) and (x - K)^2 with K = the channel's first value, so that
             // var = E[d^2] - E[d]^2 does not cancel catastrophically when |mean| >> std or rows are few
             Vec<T>::load(x + c0, piv);
-            if (blockIdx.x == 0 && rsub == 0) {
-#pragma unroll
-                for (int i = 0; i < V; ++i) a.pivot[c0 + i] = piv[i];
-            }
         }
         if (MODE == 1) {
 #pragma unroll
@@ -163,9 +182,54 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
                     s1[i] += red[j * lanes + lane][V + i];
                 }
 #pragma unroll
-            for (int i = 0; i < V; ++i) { out[c0 + i] = s0[i]; out[a.C + c0 + i] = s1[i]; }
+            for (int i = 0; i < V; ++i) {
+                atomicAdd(acc + c0 + i, static_cast<double>(s0[i]));
+                if (MODE != 2) atomicAdd(acc + a.C + c0 + i, static_cast<double>(s1[i]));
+            }
         }
         __syncthreads();
+    }
+
+    // ---- ticket: the last block to arrive finalizes
+    __threadfence();
+    if (threadIdx.x == 0) is_last = atomicAdd(&g_ticket[a.slot], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double n = static_cast<double>(a.rows);
+    for (int c = threadIdx.x; c < a.C; c += kThreads) {
+        const double s = __ldcg(acc + c);
+        const double ss = MODE != 2 ? __ldcg(acc + a.C + c) : 0.0;
+        acc[c] = 0.0;
+        if (MODE != 2) acc[a.C + c] = 0.0;
+        if (MODE == 0) {
+            const double dmean = s / n;
+            const double mean = static_cast<double>(load1(x + c)) + dmean;
+            double var = ss / n - dmean * dmean;
+            if (var < 0.0) var = 0.0;
+            const double rstd = 1.0 / sqrt(var + static_cast<double>(a.eps));
+            const float g = a.gamma ? a.gamma[c] : 1.f, bt = a.beta ? a.beta[c] : 0.f;
+            a.mean_out[c] = static_cast<float>(mean);
+            a.rstd_out[c] = static_cast<float>(rstd);
+            a.scale_out[c] = static_cast<float>(g * rstd);
+            a.shift_out[c] = static_cast<float>(bt - mean * g * rstd);
+            if (a.running_mean != nullptr) {
+                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                a.running_mean[c] = static_cast<float>((1.0 - a.momentum) * a.running_mean[c] + a.momentum * mean);
+                a.running_var[c] = static_cast<float>((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+            }
+        } else if (MODE == 1) {
+            if (a.dbeta != nullptr) a.dbeta[c] += static_cast<float>(s);
+            if (a.dgamma != nullptr) a.dgamma[c] += static_cast<float>(ss);
+            a.c1[c] = static_cast<float>(s / n);
+            a.c2[c] = static_cast<float>(ss / n);
+        } else {
+            a.colsum_out[c] += static_cast<float>(s);
+        }
+    }
+    if (threadIdx.x == 0) {
+        g_ticket[a.slot] = 0;
+        if (MODE == 0 && a.num_batches_tracked != nullptr) *a.num_batches_tracked += 1;
     }
 }
 
@@ -185,62 +249,24 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int check_channels(VgDType dt, int C) {
     const int V = dt == VG_BF16 ? 8 : 4;
-    if (C % V != 0 || !is_pow2(C / V))
-        return fail(VG_ERR_SHAPE, "channel count %d must be %d x a power of two for the per-channel kernels", C, V);
+    if (C % V != 0 || !is_pow2(C / V) || C > kMaxChannels)
+        return fail(VG_ERR_SHAPE, "channel count %d must be %d x a power of two (<= %d) for the per-channel kernels", C,
+                    V, kMaxChannels);
     return VG_OK;
+}
+
+int next_slot() {
+    static std::atomic<unsigned> counter{0};
+    return static_cast<int>(counter.fetch_add(1, std::memory_order_relaxed) % kSlots);
 }
 
 template <int MODE>
 int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
+    a.slot = next_slot();
     if (dt == VG_BF16) channel_reduce_kernel<__nv_bfloat16, MODE><<<blocks, kThreads, 0, st>>>(a);
     else channel_reduce_kernel<float, MODE><<<blocks, kThreads, 0, st>>>(a);
     VG_LAUNCHED();
     return VG_OK;
-}
-
-// ---- finalize kernels: one WARP per channel, lanes stride over the per-block partials, fp64 shuffle reduction
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ void gather_partials(const float* partial, int blocks, int C, int c, double* s, double* ss) {
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x & 31; i < blocks; i += 32) {
-        a += partial[static_cast<long long>(i) * 2 * C + c];
-        b += partial[static_cast<long long>(i) * 2 * C + C + c];
-    }
-    *s = warp_sum_d(a);
-    *ss = warp_sum_d(b);
-}
-
-__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* partial, const float* pivot, int blocks,
-                                                             int C, double n, const float* gamma, const float* beta,
-                                                             float* running_mean, float* running_var,
-                                                             long long* num_batches_tracked, float momentum, float eps,
-                                                             float* mean_out, float* rstd_out, float* scale_out,
-                                                             float* shift_out) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
-    if (c >= C) return;
-    double s, ss;
-    gather_partials(partial, blocks, C, c, &s, &ss);
-    if ((threadIdx.x & 31) != 0) return;
-    const double dmean = s / n;
-    const double mean = static_cast<double>(pivot[c]) + dmean;
-    double var = ss / n - dmean * dmean;
-    if (var < 0.0) var = 0.0;
-    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
-    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
-    mean_out[c] = static_cast<float>(mean);
-    rstd_out[c] = static_cast<float>(rstd);
-    scale_out[c] = static_cast<float>(g * rstd);
-    shift_out[c] = static_cast<float>(bt - mean * g * rstd);
-    if (running_mean != nullptr) {
-        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
-        running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
-        running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
-    }
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
@@ -253,19 +279,6 @@ __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, con
     shift[c] = bt - rm[c] * g * rstd;
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* partial, int blocks, int C, double n,
-                                                             float* dgamma, float* dbeta, float* c1, float* c2) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
-    double s, sx;
-    gather_partials(partial, blocks, C, c, &s, &sx);
-    if ((threadIdx.x & 31) != 0) return;
-    if (dbeta != nullptr) dbeta[c] += static_cast<float>(s);
-    if (dgamma != nullptr) dgamma[c] += static_cast<float>(sx);
-    c1[c] = static_cast<float>(s / n);
-    c2[c] = static_cast<float>(sx / n);
-}
-
 template <typename T>
 __global__ void colsum_generic_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,14 +288,6 @@ __global__ void colsum_generic_kernel(const T* __restrict__ x, long long rows, i
         if constexpr (sizeof(T) == 4) s += x[r * C + c]; else s += __bfloat162float(x[r * C + c]);
     }
     out[c] += static_cast<float>(s);
-}
-
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* partial, int blocks, int C, float* out) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
-    double s, unused;
-    gather_partials(partial, blocks, C, c, &s, &unused);
-    if ((threadIdx.x & 31) == 0) out[c] += static_cast<float>(s);
 }
 
 // ---- elementwise passes
@@ -448,8 +453,8 @@ int grid_for(long long n) {
 using namespace vg;
 
 extern "C" size_t vg_reduce_workspace_bytes(long long rows, int channels) {
-    const ReducePlan p = plan_reduce(rows);
-    return (static_cast<size_t>(p.blocks) * 2 + 1) * channels * sizeof(float);   // partials + pivot row
+    (void)rows;
+    return static_cast<size_t>(channels) * sizeof(float);   // kept for ABI stability; the reductions need no scratch
 }
 
 extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C, const float* gamma,
@@ -457,6 +462,8 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
                                long long* num_batches_tracked, float momentum, float eps, float* mean_out,
                                float* rstd_out, float* scale_out, float* shift_out, float* ws, size_t ws_bytes,
                                void* stream) {
+    (void)ws;
+    (void)ws_bytes;
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (x == nullptr || mean_out == nullptr || rstd_out == nullptr || scale_out == nullptr || shift_out == nullptr)
@@ -465,18 +472,12 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
     if (rc != VG_OK) return rc;
     if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
     const ReducePlan p = plan_reduce(rows);
-    if (ws == nullptr || ws_bytes < vg_reduce_workspace_bytes(rows, C))
-        return fail(VG_ERR_WORKSPACE, "bn_train_fwd: workspace too small");
     ReduceArgs a{};
-    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
-    a.pivot = ws + static_cast<size_t>(p.blocks) * 2 * C;
-    rc = launch_reduce<0>(dt, a, p.blocks, as_stream(stream));
-    if (rc != VG_OK) return rc;
-    bn_fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
-        ws, a.pivot, p.blocks, C, static_cast<double>(rows), gamma, beta, running_mean, running_var, num_batches_tracked,
-        momentum, eps, mean_out, rstd_out, scale_out, shift_out);
-    VG_LAUNCHED();
-    return VG_OK;
+    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block;
+    a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
+    a.num_batches_tracked = num_batches_tracked; a.momentum = momentum; a.eps = eps;
+    a.mean_out = mean_out; a.rstd_out = rstd_out; a.scale_out = scale_out; a.shift_out = shift_out;
+    return launch_reduce<0>(dt, a, p.blocks, as_stream(stream));
 }
 
 extern "C" int vg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
@@ -534,19 +535,17 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     rc = check_channels(dt, C);
     if (rc != VG_OK) return rc;
     const ReducePlan p = plan_reduce(rows);
-    const size_t need = vg_reduce_workspace_bytes(rows, C) + 2 * static_cast<size_t>(C) * sizeof(float);
+    const size_t need = 2 * static_cast<size_t>(C) * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return fail(VG_ERR_WORKSPACE, "bn_act_bwd: workspace too small");
-    float* c1 = ws + (static_cast<size_t>(p.blocks) * 2 + 1) * C;
+    float* c1 = ws;
     float* c2 = c1 + C;
     cudaStream_t st = as_stream(stream);
     ReduceArgs a{};
     a.x = x; a.dy = dy; a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd;
-    a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.act = act; a.slope = slope; a.partial = ws;
+    a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.act = act; a.slope = slope;
+    a.dgamma = dgamma; a.dbeta = dbeta; a.c1 = c1; a.c2 = c2;
     rc = launch_reduce<1>(dt, a, p.blocks, st);
     if (rc != VG_OK) return rc;
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(ws, p.blocks, C, static_cast<double>(rows), dgamma, dbeta,
-                                                           c1, c2);
-    VG_LAUNCHED();
     const int V = dt == VG_BF16 ? 8 : 4;
     const long long nvec = rows * C / V;
     if (dt == VG_BF16)
@@ -562,7 +561,8 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
 }
 
 extern "C" size_t vg_bn_bwd_workspace_bytes(long long rows, int channels) {
-    return vg_reduce_workspace_bytes(rows, channels) + 2 * static_cast<size_t>(channels) * sizeof(float);
+    (void)rows;
+    return 2 * static_cast<size_t>(channels) * sizeof(float);   // the two per-channel projection coefficients
 }
 
 extern "C" int vg_act_bwd(const void* dy, const void* x, VgDType in_dt, long long n, VgAct act, float slope, void* dx,
@@ -609,16 +609,13 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
             return VG_OK;
         }
     }
+    (void)ws;
+    (void)ws_bytes;
+    if (C > kMaxChannels) return fail(VG_ERR_SHAPE, "colsum: more than %d channels", kMaxChannels);
     const ReducePlan p = plan_reduce(rows);
-    if (ws == nullptr || ws_bytes < vg_reduce_workspace_bytes(rows, C))
-        return fail(VG_ERR_WORKSPACE, "colsum: workspace too small");
     ReduceArgs a{};
-    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.partial = ws;
-    rc = launch_reduce<2>(dt, a, p.blocks, as_stream(stream));
-    if (rc != VG_OK) return rc;
-    colsum_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(ws, p.blocks, C, out);
-    VG_LAUNCHED();
-    return VG_OK;
+    a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.colsum_out = out;
+    return launch_reduce<2>(dt, a, p.blocks, as_stream(stream));
 }
 
 extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int B, int C, int H, int W,

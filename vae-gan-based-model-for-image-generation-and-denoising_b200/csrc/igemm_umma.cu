@@ -7,6 +7,7 @@
 #include "igemm_umma.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
 
@@ -47,9 +48,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int tile_b = tile / p.tiles_h;
     const int i0 = tile_h * p.th, j0 = tile_w * p.tw, b0 = tile_b * p.tb;
     const int n0 = blockIdx.y * p.n_tile;
-    const int phase = blockIdx.z;
+    const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+    const int phase = blockIdx.z / ksplit, kslice = blockIdx.z % ksplit;
     const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
-    const int iters = p.taps_per_phase * p.c_chunks;
+    const int total_iters = p.taps_per_phase * p.c_chunks;
+    const int it_begin = static_cast<int>(static_cast<long long>(total_iters) * kslice / ksplit);
+    const int it_end = static_cast<int>(static_cast<long long>(total_iters) * (kslice + 1) / ksplit);
+    const int iters = it_end - it_begin;
     const uint32_t ncols = tmem_cols_for(p.n_tile);
 
     if (warp == 0 && lane == 0) {
@@ -73,18 +78,16 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int t = 0; t < p.taps_per_phase; ++t) {
-                const IgemmTap tap = taps[t];
-                for (int c = 0; c < p.c_chunks; ++c, ++it) {
-                    const int s = it % stages;
-                    const uint32_t par = (it / stages) & 1;
-                    mbar_wait(&empty[s], par ^ 1);
-                    mbar_expect_tx(&full[s], a_stage + b_stage);
-                    tma_load_4d(sA + s * a_stage, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx, i0 + tap.dy,
-                                b0);
-                    tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
-                }
+            for (int it = 0; it < iters; ++it) {
+                const int g = it_begin + it;
+                const IgemmTap tap = taps[g / p.c_chunks];
+                const int c = g % p.c_chunks;
+                const int s = it % stages;
+                const uint32_t par = (it / stages) & 1;
+                mbar_wait(&empty[s], par ^ 1);
+                mbar_expect_tx(&full[s], a_stage + b_stage);
+                tma_load_4d(sA + s * a_stage, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx, i0 + tap.dy, b0);
+                tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
             }
         }
     } else if (warp == 1) {
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 }
                 umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);
+            umma_commit(tmem_full);   // (with zero iterations this arrives immediately: nothing is pending)
         }
     } else {
         const int q = warp & 3;
@@ -138,6 +141,15 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (ksplit > 1) {
+                if (valid && iters > 0) {
+                    float* dst = p.splitk_acc + off + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cols) atomicAdd(dst + j, f[j]);
+                }
+                continue;
+            }
             if (p.bias != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -333,6 +345,17 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+__global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, void* out,
+                                     int out_fp32, size_t n, int C) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float v = acc[i];
+        if (bias != nullptr) v += bias[i % C];
+        if (out_fp32) static_cast<float*>(out)[i] = v;
+        else static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -349,9 +372,22 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int stage_bytes = (128 + p.n_tile) * p.kchunk * 2;
     const int smem = smem_bytes_for(p.stages, stage_bytes);
-    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.n_tiles, p.num_phases);
+    const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.n_tiles, p.num_phases * ksplit);
+    const size_t out_elems = static_cast<size_t>(p.out_B) * p.out_H * p.out_W * p.out_C;
+    if (ksplit > 1) {
+        cudaError_t e = cudaMemsetAsync(p.splitk_acc, 0, out_elems * sizeof(float), stream);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
     igemm_fprop_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
-    return static_cast<int>(cudaGetLastError());
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (ksplit > 1) {
+        const int blocks = static_cast<int>(std::min<size_t>((out_elems + 255) / 256, 148 * 8));
+        splitk_finish_kernel<<<blocks, 256, 0, stream>>>(p.splitk_acc, p.bias, p.out, p.out_fp32, out_elems, p.out_C);
+        e = cudaGetLastError();
+    }
+    return static_cast<int>(e);
 }
 
 int launch_wgrad(const WgradParams& p, cudaStream_t stream) {

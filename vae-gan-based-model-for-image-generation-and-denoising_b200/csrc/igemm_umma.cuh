@@ -44,6 +44,10 @@ struct alignas(64) IgemmParams {
     int osy, osx;
     int ph_ay[4], ph_ax[4];
     const float* bias;  // optional [out_C]
+    // split-K (single-phase launches with few output tiles and a long reduction): blockIdx.z = K slice; slices add
+    // their fp32 partial tiles into `splitk_acc` (zeroed by the launcher) and a finishing kernel converts / adds bias
+    int ksplit;
+    float* splitk_acc;
 };
 
 struct alignas(64) WgradParams {

@@ -90,7 +90,12 @@ def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[
     dt = big.dtype
     out = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=torch.float32 if out_f32 else dt,
                       device=big.device)
-    call("vg_conv_down", ctypes.byref(g), _DT[dt], _p(big), _p(w), _p(bias), _p(out), int(out_f32), _stream())
+    ws, nbytes = None, 0
+    if dt == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
+        nbytes = _lib.load().vg_conv_down_workspace_bytes(ctypes.byref(g))
+        ws = _ws(nbytes, big.device)
+    call("vg_conv_down", ctypes.byref(g), _DT[dt], _p(big), _p(w), _p(bias), _p(out), int(out_f32), _p(ws), nbytes,
+         _stream())
     return out
 
 
@@ -134,19 +139,20 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps: float):
     return stats
 
 
-def scale_shift_act(x: torch.Tensor, scale, shift, act: int, slope: float, out_dtype=None) -> torch.Tensor:
-    out_dtype = out_dtype or x.dtype
+def scale_shift_act(x: torch.Tensor, scale, shift, act: int, slope: float, out_dtype=None, out=None) -> torch.Tensor:
+    out_dtype = out_dtype or (out.dtype if out is not None else x.dtype)
     C = x.shape[-1]
-    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    y = out if out is not None else torch.empty(x.shape, dtype=out_dtype, device=x.device)
     call("vg_scale_shift_act", _p(x), _DT[x.dtype], x.numel() // C, C, _p(scale), _p(shift), act, float(slope), _p(y),
          _DT[out_dtype], _stream())
     return y
 
 
-def bn_act_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act: int, slope: float, dgamma, dbeta):
+def bn_act_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act: int, slope: float, dgamma, dbeta,
+               out=None):
     C = x.shape[-1]
     rows = x.numel() // C
-    dx = torch.empty_like(x)
+    dx = out if out is not None else torch.empty_like(x)
     nbytes = _lib.load().vg_bn_bwd_workspace_bytes(rows, C)
     ws = _ws(nbytes, x.device)
     call("vg_bn_act_bwd", _p(dy), _p(x), _DT[x.dtype], rows, C, _p(stats[2]), _p(stats[3]), _p(stats[0]), _p(stats[1]),
@@ -170,11 +176,11 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, mode: int = 0, sigma: float = 0.0,
-                 clamp: bool = False) -> torch.Tensor:
+                 clamp: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 NCHW -> internal NHWC (channel-padded per `padded_channels`)."""
     B, C, H, W = src.shape
     Cd = padded_channels(C, dtype)
-    dst = torch.empty((B, H, W, Cd), dtype=dtype, device=src.device)
+    dst = out if out is not None else torch.empty((B, H, W, Cd), dtype=dtype, device=src.device)
     call("vg_nchw_to_nhwc", _p(src), _p(aux), _p(dst), _DT[dtype], B, C, H, W, Cd, mode, float(sigma), int(clamp),
          _stream())
     return dst
@@ -227,7 +233,10 @@ class ConvLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, spec: ConvSpec, act: int, slope: float, bn, training: bool,
-                cache: PackedWeights, out_f32: bool):
+                cache: PackedWeights, out_f32: bool, groups: int = 1):
+        """`groups` > 1: the batch holds that many independent sub-batches (e.g. the discriminator's real and fake
+        batches of vaegan_code.py:96-97 run through ONE convolution launch); BatchNorm statistics, running-stat
+        updates and the BN backward stay per sub-batch, in order, exactly as separate forward calls would."""
         _require_cuda(x, "ConvLayerFn")
         x = _contig(x)
         B, H, W, Cx = x.shape
@@ -256,16 +265,29 @@ class ConvLayerFn(torch.autograd.Function):
                 rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats \
                     else (None, None, None)
                 # F.batch_norm semantics: momentum=None means cumulative average - the reference never uses it
-                stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+                if groups == 1:
+                    stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+                    y = scale_shift_act(raw, stats[2], stats[3], act, slope)
+                else:
+                    if B % groups:
+                        raise RuntimeError(f"batch {B} is not divisible into {groups} sub-batches")
+                    rg, y = raw.view(groups, -1, raw.shape[-1]), torch.empty_like(raw)
+                    yg = y.view(groups, -1, raw.shape[-1])
+                    per = [bn_train_fwd(rg[i], gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+                           for i in range(groups)]
+                    for i in range(groups):
+                        scale_shift_act(rg[i], per[i][2], per[i][3], act, slope, out=yg[i])
+                    stats = torch.stack(per)
             else:
                 stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
-            y = scale_shift_act(raw, stats[2], stats[3], act, slope)
+                y = scale_shift_act(raw, stats[2], stats[3], act, slope)
         elif act != ACT_NONE:
             y = scale_shift_act(raw, None, None, act, slope)
         else:
             y = raw
         ctx.spec, ctx.act, ctx.slope, ctx.g = spec, act, slope, g
         ctx.has_bn, ctx.bn_training, ctx.cache, ctx.out_f32 = bn is not None, training, cache, out_f32
+        ctx.groups = groups
         ctx.params = (weight, bias, gamma, beta)
         ctx.save_for_backward(x, raw, stats)
         return y
@@ -289,7 +311,14 @@ class ConvLayerFn(torch.autograd.Function):
                     if dgamma is None:
                         dgamma = torch.zeros_like(gamma, dtype=torch.float32)
                         dbeta = torch.zeros_like(beta, dtype=torch.float32)
-                d_raw = bn_act_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
+                if ctx.groups == 1:
+                    d_raw = bn_act_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
+                else:
+                    C = raw.shape[-1]
+                    d_raw = torch.empty_like(raw)
+                    dyg, rg, dg = dy.view(ctx.groups, -1, C), raw.view(ctx.groups, -1, C), d_raw.view(ctx.groups, -1, C)
+                    for i in range(ctx.groups):
+                        bn_act_bwd(dyg[i], rg[i], stats[i], act, slope, dgamma, dbeta, out=dg[i])
             else:
                 raise _lib.VaeganB200Error("backward through eval-mode BatchNorm is not part of the VAE-GAN step")
         elif act != ACT_NONE:
@@ -316,7 +345,7 @@ class ConvLayerFn(torch.autograd.Function):
             dx = conv_up(d_raw, w_bwd, g) if spec.kind == "down" else conv_down(d_raw, w_bwd, g)
         return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
                 _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 class ToNHWCFn(torch.autograd.Function):

@@ -67,12 +67,12 @@ class _Layer:
         self.spec = _spec_of(conv)
         self.cache = F_.PackedWeights()
 
-    def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True):
+    def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1):
         bn = self.bn
         act = self.act if fuse_act else ACT_NONE
         return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, bn.weight if bn is not None else None,
                                     bn.bias if bn is not None else None, self.spec, act, self.slope, bn, training,
-                                    self.cache, out_f32)
+                                    self.cache, out_f32, groups)
 
 
 def _group_layers(seq: nn.Sequential) -> List[_Layer]:
@@ -267,10 +267,12 @@ class Discriminator(_KernelModule):
     def forward(self, input):
         return self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype()))
 
-    def forward_nhwc(self, h):
+    def forward_nhwc(self, h, groups: int = 1):
+        """`groups` independent sub-batches stacked along the batch axis share every convolution launch while
+        BatchNorm treats them separately (the fused step runs D(real) and D(fake) of vaegan_code.py:96-97 this way)."""
         layers = self._layers()
         for layer in layers[:-1]:
-            h = layer(h, self.training)
+            h = layer(h, self.training, groups=groups)
         last = layers[-1]
         logits = last(h, self.training, out_f32=True, fuse_act=False)     # [B, 1, 1, 1] fp32
         return F_.PointwiseActFn.apply(logits, last.act, last.slope).view(-1)

@@ -141,7 +141,7 @@ class VAEGANStep:
             "kl_w": torch.zeros((), **f32), "losses": torch.zeros((len(LOSS_KEYS),), **f32),
             "rng_offset": torch.zeros((), dtype=torch.int64, device=dev),
             "mse_ws": torch.empty((F_._lib.load().vg_mse_workspace_bytes() // 4,), **f32),
-            "dp_a": torch.empty((batch,), **f32), "dp_b": torch.empty((batch,), **f32),
+            "dp_a": torch.empty((batch,), **f32), "dp_pair": torch.empty((2 * batch,), **f32),
         }
         return s
 
@@ -178,19 +178,22 @@ class VAEGANStep:
         recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH, 3)
 
         # ---- instance noise                                                           (:88-92)
-        real_noisy = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst)
         recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype, loss[2:3], s["mse_ws"])
-        recon_noisy_d = recon_noisy.detach()
+        # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
+        # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2)
+        pair = torch.empty((2 * B,) + tuple(recon_noisy.shape[1:]), dtype=self.dtype, device=self.dev)
+        F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B])
+        pair[B:].copy_(recon_noisy.detach())
+        dp = s["dp_pair"]
 
         # ---- discriminator updates                                                    (:95-105)
         for it in range(self.n_dis):
             self.opt_D.zero_grad()
-            p_real = D.forward_nhwc(real_noisy)
-            p_fake = D.forward_nhwc(recon_noisy_d)
+            p_pair = D.forward_nhwc(pair, groups=2)
             slot = loss[it:it + 1] if it < 2 else None
-            call("vg_bce", _p(p_real), B, self.real_label, 1.0, _p(slot), 0, _p(s["dp_a"]), _stream())
-            call("vg_bce", _p(p_fake), B, self.fake_label, 1.0, _p(slot), 1, _p(s["dp_b"]), _stream())
-            torch.autograd.backward([p_real, p_fake], [s["dp_a"], s["dp_b"]])
+            call("vg_bce", _p(p_pair[:B]), B, self.real_label, 1.0, _p(slot), 0, _p(dp[:B]), _stream())
+            call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
+            torch.autograd.backward([p_pair], [dp])
             self._allreduce(self.opt_D)
             self.opt_D.step(1.0 / self.world)
             D.invalidate_packed_weights()
