@@ -91,8 +91,12 @@ size_t vg_conv_down_workspace_bytes(const VgConvGeom* g);
 int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias, void* small,
                  int out_f32, void* ws, size_t ws_bytes, void* stream);
 int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big, void* stream);
-/* dw (fp32, reference layout [small_c][big_c][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient. */
-int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* stream);
+/* dw (fp32, reference layout [small_c][big_c_valid][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient.
+ * Optional scratch (ws may be NULL): with vg_conv_wgrad_workspace_bytes() the tensor-core path splits the pixel
+ * reduction across SMs and combines the partial tiles in a second kernel (no atomics are used either way). */
+size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dtype);
+int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* ws,
+                  size_t ws_bytes, void* stream);
 
 
 /* ---- BatchNorm2d (training statistics), activations, layout edges ---------------------------------------------

@@ -1,0 +1,40 @@
+"""Kernel timeline of the CUDA-graph-replayed step via torch.profiler (CUPTI): per-kernel totals + GPU busy fraction."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from importlib import import_module
+import vaegan_b200 as vb
+VAEGANStep = import_module("vaegan_b200.step").VAEGANStep
+HW, NZ, B = 64, 128, int(os.environ.get("BATCH", "256"))
+torch.manual_seed(42)
+enc = vb.Encoder([3, HW, HW], NZ); gen = vb.Generator(nz=NZ, hw=HW); dis = vb.Discriminator(hw=HW)
+gen.apply(vb.weights_init); dis.apply(vb.weights_init)
+for m in (enc, gen, dis): m.cuda()
+step = VAEGANStep(enc, gen, dis, use_cuda_graph=True)
+real = (torch.rand(B, 3, HW, HW) * 2 - 1).cuda()
+for _ in range(5): step.step(real, 50)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): step.step(real, 50)
+e1.record(); torch.cuda.synchronize()
+print(f"graph replay: {e0.elapsed_time(e1)/10:.3f} ms/step, launches/step {step.launches_per_step}")
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3): step.step(real, 50)
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+tot = {}
+for e in evs:
+    k = e.name[:90]
+    t = tot.setdefault(k, [0.0, 0]); t[0] += e.time_range.elapsed_us(); t[1] += 1
+span = evs[-1].time_range.end - evs[0].time_range.start
+busy = sum(v[0] for v in tot.values())
+print(f"3 steps: span {span/1e3:.2f} ms, kernel-busy {busy/1e3:.2f} ms ({100*busy/span:.1f}%), {len(evs)} device events")
+for k, (us, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:28]:
+    print(f"{us/3:9.1f} us/step  n/step {n/3:6.1f}  avg {us/n:8.1f}  {k}")
+# gaps
+gaps = [(evs[i+1].time_range.start - evs[i].time_range.end) for i in range(len(evs)-1)]
+big = sorted(gaps, reverse=True)[:8]
+print("largest gaps (us):", [round(g,1) for g in big], " sum of gaps >2us:", round(sum(g for g in gaps if g > 2)/3,1), "us/step")

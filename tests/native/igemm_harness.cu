@@ -132,6 +132,9 @@ static bool run_case(const Case& c, bool verbose_fail) {
         void* d_ws = nullptr;
         const size_t ws_bytes = vg_conv_down_workspace_bytes(&g);
         CK(cudaMalloc(&d_ws, ws_bytes));
+        void* d_wws = nullptr;
+        const size_t wws_bytes = vg_conv_wgrad_workspace_bytes(&g, dt);
+        CK(cudaMalloc(&d_wws, wws_bytes + 16));
         CK(cudaMemset(d_out_small, 0xFF, n_small * 4));
         CK(cudaMemset(d_out_big, 0xFF, n_big * 4));
         CK(cudaMemset(d_dw, 0, n_w * 4));
@@ -142,7 +145,7 @@ static bool run_case(const Case& c, bool verbose_fail) {
         if (rc != VG_OK) { printf("  down failed (%d): %s\n", rc, vg_last_error()); ok = false; }
         rc = vg_conv_up(&g, dt, d_small, w_up, d_out_big, nullptr);
         if (rc != VG_OK) { printf("  up failed (%d): %s\n", rc, vg_last_error()); ok = false; }
-        rc = vg_conv_wgrad(&g, dt, d_small, d_big, d_dw, nullptr);
+        rc = vg_conv_wgrad(&g, dt, d_small, d_big, d_dw, d_wws, wws_bytes, nullptr);
         if (rc != VG_OK) { printf("  wgrad failed (%d): %s\n", rc, vg_last_error()); ok = false; }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
@@ -188,7 +191,7 @@ static bool run_case(const Case& c, bool verbose_fail) {
         }
         ok = ok && o1 && o2 && o3;
         cudaFree(d_big); cudaFree(d_small); cudaFree(d_out_small); cudaFree(d_out_big); cudaFree(d_w);
-        cudaFree(d_bias); cudaFree(d_dw); cudaFree(d_ws);
+        cudaFree(d_bias); cudaFree(d_dw); cudaFree(d_ws); cudaFree(d_wws);
         if (d_wd) cudaFree(d_wd);
         if (d_wu) cudaFree(d_wu);
     }
@@ -213,6 +216,9 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
     CK(cudaMemset(d_w, 0, n_w * 4));
     CK(cudaMemset(d_dw, 0, n_w * 4));
     vg_pack_weights_bf16(&g, d_w, d_wd, d_wu, nullptr);
+    void* d_wws = nullptr;
+    const size_t wws_bytes = vg_conv_wgrad_workspace_bytes(&g, VG_BF16);
+    CK(cudaMalloc(&d_wws, wws_bytes + 16));
     const double flops = 2.0 * g.batch * g.small_h * g.small_w * (double)g.small_c * g.big_c * kk;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -221,7 +227,7 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
         auto run = [&]() {
             if (op == 0) return vg_conv_down(&g, VG_BF16, d_big, d_wd, nullptr, d_small, 0, nullptr, 0, nullptr);
             if (op == 1) return vg_conv_up(&g, VG_BF16, d_small, d_wu, d_big, nullptr);
-            return vg_conv_wgrad(&g, VG_BF16, d_small, d_big, d_dw, nullptr);
+            return vg_conv_wgrad(&g, VG_BF16, d_small, d_big, d_dw, d_wws, wws_bytes, nullptr);
         };
         for (int i = 0; i < 3; ++i)
             if (run() != VG_OK) { printf("perf %s failed: %s\n", name, vg_last_error()); return; }
@@ -236,7 +242,7 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
         printf("  perf %-28s %-5s %8.1f us  %7.1f TFLOP/s\n", name, op == 0 ? "down" : (op == 1 ? "up" : "wgrad"),
                ms * 1e3, flops / (ms * 1e-3) / 1e12);
     }
-    cudaFree(d_big); cudaFree(d_small); cudaFree(d_wd); cudaFree(d_wu); cudaFree(d_w); cudaFree(d_dw);
+    cudaFree(d_big); cudaFree(d_small); cudaFree(d_wd); cudaFree(d_wu); cudaFree(d_w); cudaFree(d_dw); cudaFree(d_wws);
 }
 
 int main(int argc, char** argv) {

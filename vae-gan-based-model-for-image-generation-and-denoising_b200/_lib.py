@@ -36,7 +36,8 @@ PROTOTYPES = {
     "vg_conv_down_workspace_bytes": (c_size_t, [_G]),
     "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),
-    "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P]),
+    "vg_conv_wgrad_workspace_bytes": (c_size_t, [_G, c_int]),
+    "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "vg_reduce_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "vg_bn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "vg_bn_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,

@@ -260,8 +260,10 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
 }
 
 // ---------------------------------------------------------------------------------------------- wgrad
-static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, float* dw, cudaStream_t stream) {
-    if (!aligned16(big) || !aligned16(small)) return fail(VG_ERR_ALIGN, "wgrad: 16-byte alignment");
+static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, float* dw, void* ws, size_t ws_bytes,
+                      cudaStream_t stream, size_t* ws_needed = nullptr) {
+    if (ws_needed == nullptr && (!aligned16(big) || !aligned16(small)))
+        return fail(VG_ERR_ALIGN, "wgrad: 16-byte alignment");
     WgradParams p;
     std::memset(&p, 0, sizeof(p));
     const int k = g->kernel, s = g->stride, pad = g->pad;
@@ -279,13 +281,13 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.taps_per_cta = std::min(p.num_taps, 512 / p.n_tile);
     if (p.num_taps % 4 == 0) p.taps_per_cta = std::max(4, p.taps_per_cta / 4 * 4);
     p.taps_per_cta = std::min(p.taps_per_cta, 16);
-    {
+    if (ws_needed == nullptr) {
         const int rc = make_view(&p.pmap, small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.p_atom_c, p.tw,
                                  p.th, p.tb, p.p_atom_c * 2);
         if (rc != 0) return fail(VG_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(P) failed (%d)", rc);
     }
     const int nviews = s * s;
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < 4 && ws_needed == nullptr; ++v) {
         const int vv = v < nviews ? v : 0;
         const int rc = make_view(&p.qmap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, p.q_atom_c,
                                  p.tw, p.th, p.tb, p.q_atom_c * 2);
@@ -304,7 +306,9 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int tap_groups = ceil_div(p.num_taps, p.taps_per_cta);
     const int base_ctas = p.m_tiles * p.n_tiles * tap_groups;
-    p.splits = std::max(1, std::min(total_tiles, ceil_div(296, base_ctas)));
+    // one CTA per SM (the accumulators fill TMEM): aim at a single full wave; split the pixel range only when the
+    // (channel tile, tap group) grid alone leaves most SMs idle
+    p.splits = base_ctas >= 100 ? 1 : std::max(1, std::min(total_tiles, 148 / base_ctas));
     const int kpix = 64;
     const int a_stage = kpix * 256, b_stage = p.n_tile * kpix * 2;
     p.stages_a = 3;
@@ -317,10 +321,20 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.m_valid = g->small_c;
     p.n_valid = bcv;
     // dw[m][n][tap..tap+3] contiguous and 16-byte aligned when k*k is a multiple of 4
-    p.vec4_taps = (k * k) % 4 == 0 && p.taps_per_cta % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0;
+    p.vec4_taps = (k * k) % 4 == 0 && p.taps_per_cta % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0 &&
+                  (p.s_m % 4) == 0;
+    if (p.splits > 1) {
+        const size_t need = wgrad_partial_bytes(p);
+        if (ws_needed != nullptr) { *ws_needed = need; return VG_OK; }
+        if (ws != nullptr && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) p.partial = static_cast<float*>(ws);
+        else p.splits = 1;   // no scratch: correct but with idle SMs
+    } else if (ws_needed != nullptr) {
+        *ws_needed = 0;
+        return VG_OK;
+    }
     const int rc = launch_wgrad(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_wgrad_kernel");
-    note_launch();
+    note_launch(p.splits > 1 ? 2 : 1);
     return VG_OK;
 }
 
@@ -390,14 +404,22 @@ extern "C" int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small,
     return simt_conv_up(g, dtype, small, w, big, as_stream(stream));
 }
 
+extern "C" size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dtype) {
+    if (g == nullptr || check_geom(g) != VG_OK || dtype != VG_BF16 || is_gemv(g) || !umma_wgrad_ok(g)) return 0;
+    size_t need = 0;
+    float dummy = 0.f;
+    wgrad_umma(g, &dummy, &dummy, &dummy, nullptr, 0, nullptr, &need);
+    return need;
+}
+
 extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
-                             void* stream) {
+                             void* ws, size_t ws_bytes, void* stream) {
     int rc = check_geom(g);
     if (rc != VG_OK) return rc;
     if (big == nullptr || dw == nullptr || small == nullptr) return fail(VG_ERR_ARG, "wgrad: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
     if (is_gemv(g)) return gemv_wgrad(g, dtype, small, big, dw, as_stream(stream));
-    if (dtype == VG_BF16 && umma_wgrad_ok(g)) return wgrad_umma(g, small, big, dw, as_stream(stream));
+    if (dtype == VG_BF16 && umma_wgrad_ok(g)) return wgrad_umma(g, small, big, dw, ws, ws_bytes, as_stream(stream));
     return simt_conv_wgrad(g, dtype, small, big, dw, as_stream(stream));
 }

@@ -80,7 +80,10 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxChannels = 4096;
 constexpr int kSlots = 64;
-__device__ double g_acc[kSlots][2 * kMaxChannels];   // zero at module load; every launch leaves its slot zero again
+constexpr int kAccDoubles = 2 * kMaxChannels;
+// zero at module load; every launch leaves its slot zero again.  A slot holds `reps` replicas of the [2][C] totals
+// (reps = min(16, kAccDoubles / 2C)); block b adds into replica b % reps, which spreads the same-address atomics.
+__device__ double g_acc[kSlots][kAccDoubles];
 __device__ unsigned int g_ticket[kSlots];
 
 struct ReduceArgs {
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     const long long r1 = min(a.rows, r0 + a.rows_per_block);
     const T* x = static_cast<const T*>(a.x);
     const T* dy = static_cast<const T*>(a.dy);
-    double* acc = g_acc[a.slot];
+    const int reps = max(1, min(16, kAccDoubles / (2 * a.C)));
+    double* acc = g_acc[a.slot] + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
 
     for (int cg = 0; cg < tpr / lanes; ++cg) {
         const int c0 = (cg * lanes + lane) * V;
@@ -197,11 +201,18 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     if (!is_last) return;
     __threadfence();
     const double n = static_cast<double>(a.rows);
+    double* all = g_acc[a.slot];
     for (int c = threadIdx.x; c < a.C; c += kThreads) {
-        const double s = __ldcg(acc + c);
-        const double ss = MODE != 2 ? __ldcg(acc + a.C + c) : 0.0;
-        acc[c] = 0.0;
-        if (MODE != 2) acc[a.C + c] = 0.0;
+        double s = 0.0, ss = 0.0;
+        for (int r = 0; r < reps; ++r) {
+            double* base = all + static_cast<long long>(r) * 2 * a.C;
+            s += __ldcg(base + c);
+            base[c] = 0.0;
+            if (MODE != 2) {
+                ss += __ldcg(base + a.C + c);
+                base[a.C + c] = 0.0;
+            }
+        }
         if (MODE == 0) {
             const double dmean = s / n;
             const double mean = static_cast<double>(load1(x + c)) + dmean;

@@ -295,45 +295,71 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const bool valid = (row < p.m_atoms * p.p_atom_c) && (m < p.m_valid) && (pt_end > pt_begin);
+        const bool valid = (row < p.m_atoms * p.p_atom_c) && (m < p.m_valid);
+        const bool has_work = pt_end > pt_begin;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        if (p.vec4_taps) {
-            // dw[m][n][tap0 + 4g .. +3] is 16 contiguous bytes: one vector reduction per (n, group of 4 taps)
-            for (int g = 0; g < ntap; g += 4) {
-                float* dst = p.dw + static_cast<long long>(m) * p.s_m + (tap0 + g);
-                for (int c = 0; c < p.n_tile; c += 16) {
-                    uint32_t v0[16], v1[16], v2[16], v3[16];
-                    tmem_ld_32x16(taddr + (g + 0) * p.n_tile + c, v0);
-                    tmem_ld_32x16(taddr + (g + 1) * p.n_tile + c, v1);
-                    tmem_ld_32x16(taddr + (g + 2) * p.n_tile + c, v2);
-                    tmem_ld_32x16(taddr + (g + 3) * p.n_tile + c, v3);
-                    tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int n = n0 + c + j;
-                            if (n < p.n_valid)
-                                red_add_v4(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v0[j]),
-                                           __uint_as_float(v1[j]), __uint_as_float(v2[j]), __uint_as_float(v3[j]));
-                        }
-                    }
-                }
-            }
-        } else {
+        if (p.splits > 1) {
+            // partial tile -> workspace: [cta][tap_local][row][n_tile]; each thread writes its row contiguously
+            const long long cta = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            float* base = p.partial + cta * static_cast<long long>(p.taps_per_cta) * 128 * p.n_tile;
             for (int tl = 0; tl < ntap; ++tl) {
-                const int tap_id = p.taps[tap0 + tl].tap_id;
-                float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(tap_id) * p.s_tap;
+                float4* dst = reinterpret_cast<float4*>(base + (static_cast<long long>(tl) * 128 + row) * p.n_tile);
                 for (int c = 0; c < p.n_tile; c += 16) {
                     uint32_t v[16];
                     tmem_ld_32x16(taddr + tl * p.n_tile + c, v);
                     tmem_ld_wait();
-                    if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int n = n0 + c + j;
-                            if (n < p.n_valid) atomicAdd(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v[j]));
+                    for (int j = 0; j < 4; ++j)
+                        dst[c / 4 + j] = has_work ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+            // exclusive ownership: dw[m][n][tap] += acc, no atomics
+            if (p.vec4_taps) {
+                for (int g4 = 0; g4 < ntap; g4 += 4) {
+                    float* dst = p.dw + static_cast<long long>(m) * p.s_m + (tap0 + g4);
+                    for (int c = 0; c < p.n_tile; c += 16) {
+                        uint32_t v0[16], v1[16], v2[16], v3[16];
+                        tmem_ld_32x16(taddr + (g4 + 0) * p.n_tile + c, v0);
+                        tmem_ld_32x16(taddr + (g4 + 1) * p.n_tile + c, v1);
+                        tmem_ld_32x16(taddr + (g4 + 2) * p.n_tile + c, v2);
+                        tmem_ld_32x16(taddr + (g4 + 3) * p.n_tile + c, v3);
+                        tmem_ld_wait();
+                        if (valid && has_work) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int n = n0 + c + j;
+                                if (n < p.n_valid) {
+                                    float4* q4 = reinterpret_cast<float4*>(dst + static_cast<long long>(n) * p.s_n);
+                                    float4 o = *q4;
+                                    o.x += __uint_as_float(v0[j]);
+                                    o.y += __uint_as_float(v1[j]);
+                                    o.z += __uint_as_float(v2[j]);
+                                    o.w += __uint_as_float(v3[j]);
+                                    *q4 = o;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int tl = 0; tl < ntap; ++tl) {
+                    const int tap_id = p.taps[tap0 + tl].tap_id;
+                    float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(tap_id) * p.s_tap;
+                    for (int c = 0; c < p.n_tile; c += 16) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr + tl * p.n_tile + c, v);
+                        tmem_ld_wait();
+                        if (valid && has_work) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int n = n0 + c + j;
+                                if (n < p.n_valid) dst[static_cast<long long>(n) * p.s_n] += __uint_as_float(v[j]);
+                            }
                         }
                     }
                 }
@@ -343,6 +369,47 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// dw[m][n][tap] += sum over splits of partial[cta(split, mn, group)][tap_local][row][col]
+// VEC = 4: one thread owns the 4 consecutive taps dw[m][n][4t..4t+3] (one float4 read-add-write); VEC = 1: one tap.
+template <int VEC>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) {
+    const int tap_units = p.num_taps / VEC;
+    const long long total = static_cast<long long>(p.m_valid) * p.n_valid * tap_units;
+    const int rows_per_tile = p.m_atoms * p.p_atom_c;
+    const long long plane = static_cast<long long>(128) * p.n_tile;
+    const long long cta_stride = static_cast<long long>(p.taps_per_cta) * plane;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // i enumerates (m, tap unit, n) with n fastest so that the partial reads are coalesced
+        const int n = static_cast<int>(i % p.n_valid);
+        const long long r = i / p.n_valid;
+        const int tap = static_cast<int>(r % tap_units) * VEC;
+        const int m = static_cast<int>(r / tap_units);
+        const int m_tile = m / rows_per_tile, row = m - m_tile * rows_per_tile;
+        const int n_tile_idx = n / p.n_tile, col = n - n_tile_idx * p.n_tile;
+        const int group = tap / p.taps_per_cta, tl = tap - group * p.taps_per_cta;
+        const long long y = static_cast<long long>(m_tile) * p.n_tiles + n_tile_idx;
+        const float* src = p.partial + ((static_cast<long long>(group) * (p.m_tiles * p.n_tiles) + y) * p.splits) * cta_stride +
+                           static_cast<long long>(tl) * plane + static_cast<long long>(row) * p.n_tile + col;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int s = 0; s < p.splits; ++s) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] += __ldcs(src + s * cta_stride + v * plane);
+        }
+        float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(n) * p.s_n +
+                     static_cast<long long>(tap) * p.s_tap;
+        if (VEC == 4) {
+            float4 o = *reinterpret_cast<float4*>(dst);
+            o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
+            *reinterpret_cast<float4*>(dst) = o;
+        } else {
+            dst[0] += acc[0];
+        }
+    }
 }
 
 __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, void* out,
@@ -402,7 +469,19 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
     dim3 grid(p.splits, p.m_tiles * p.n_tiles, tap_groups);
     igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || p.splits <= 1) return static_cast<int>(e);
+    const long long total = static_cast<long long>(p.m_valid) * p.n_valid * p.num_taps / (p.vec4_taps ? 4 : 1);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+    if (p.vec4_taps) wgrad_reduce_kernel<4><<<blocks, 256, 0, stream>>>(p);
+    else wgrad_reduce_kernel<1><<<blocks, 256, 0, stream>>>(p);
     return static_cast<int>(cudaGetLastError());
+}
+
+size_t wgrad_partial_bytes(const WgradParams& p) {
+    const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
+    return static_cast<size_t>(p.splits) * p.m_tiles * p.n_tiles * tap_groups * p.taps_per_cta * 128 * p.n_tile *
+           sizeof(float);
 }
 
 int igemm_smem_bytes(int stages, int stage_bytes) { return smem_bytes_for(stages, stage_bytes); }

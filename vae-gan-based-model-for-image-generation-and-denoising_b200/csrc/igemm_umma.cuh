@@ -65,15 +65,20 @@ struct alignas(64) WgradParams {
     int m_tiles, n_tiles;
     int splits;            // split of the pixel-tile range across CTAs
     int stages_a, stages_b;
-    float* dw;             // fp32, accumulated with red.global.add
+    float* dw;             // fp32 gradient, accumulated (+=)
     long long s_m, s_n, s_tap;  // element strides of dw for (P channel, Q channel, tap)
     int m_valid, n_valid;  // channel counts actually present (rows/cols beyond are dropped)
-    int vec4_taps;         // 1: taps of a CTA are 4-aligned and contiguous in dw -> 16-byte vector reductions
+    // Output policy.  splits == 1: every dw element is owned by exactly one CTA, which does a plain read-add-write.
+    // splits > 1: each CTA stores its fp32 partial tile to `partial` ([cta][tap_local][128 rows][n_tile], coalesced
+    // vector stores) and wgrad_reduce_kernel sums the splits into dw.  No atomics either way.
+    float* partial;
+    int vec4_taps;         // k*k and taps_per_cta multiples of 4, dw 16-byte aligned: dw[m][n][4 taps] moves as one float4
 };
 
 // Host-side launchers (return cudaError_t as int).
 int launch_igemm(const IgemmParams& p, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, cudaStream_t stream);
+size_t wgrad_partial_bytes(const WgradParams& p);
 
 // rank<=4 bf16 tensor map; dims/strides innermost first; strides in ELEMENTS for dims 1.. (dim 0 is contiguous).
 // swizzle_bytes in {128, 64, 32}.

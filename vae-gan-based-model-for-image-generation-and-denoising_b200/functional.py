@@ -110,7 +110,9 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
     if dw is None:
         dw = torch.zeros((g.small_c, g.big_c_valid or g.big_c, g.kernel, g.kernel), dtype=torch.float32,
                          device=small.device)
-    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _stream())
+    nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
+    ws = _ws(nbytes, small.device) if nbytes else None
+    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream())
     return dw
 
 
