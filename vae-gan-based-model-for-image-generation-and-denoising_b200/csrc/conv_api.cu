@@ -1,6 +1,7 @@
 // C-ABI for the three convolution contractions (down / up / wgrad): geometry -> tap tables + TMA tensor maps
 // -> tcgen05 implicit-GEMM launch (bf16), or the fp32 CUDA-core implicit GEMM (conv_simt.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_bf16.h>
@@ -267,7 +268,9 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     WgradParams p;
     std::memset(&p, 0, sizeof(p));
     const int k = g->kernel, s = g->stride, pad = g->pad;
-    pick_box(64, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
+    const char* kp = getenv("VG_WGRAD_KPIX");
+    const int kpix = kp ? atoi(kp) : 128;   // pixels reduced per pipeline stage
+    pick_box(kpix, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
     p.tiles_b = ceil_div(g->batch, p.tb);
@@ -309,11 +312,14 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     // one CTA per SM (the accumulators fill TMEM): aim at a single full wave; split the pixel range only when the
     // (channel tile, tap group) grid alone leaves most SMs idle
     p.splits = base_ctas >= 100 ? 1 : std::max(1, std::min(total_tiles, 148 / base_ctas));
-    const int kpix = 64;
     const int a_stage = kpix * 256, b_stage = p.n_tile * kpix * 2;
-    p.stages_a = 3;
-    p.stages_b = std::max(2, std::min(8, (200 * 1024 - p.stages_a * a_stage) / b_stage));
+    p.stages_a = kpix >= 128 ? 2 : 3;
+    p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;
+    {
+        const char* dbg = getenv("VG_DEBUG_WGRAD");
+        p.debug_flags = dbg ? atoi(dbg) : 0;
+    }
     const int bcv = bc_valid(g);
     p.s_m = static_cast<long long>(bcv) * k * k;
     p.s_n = k * k;

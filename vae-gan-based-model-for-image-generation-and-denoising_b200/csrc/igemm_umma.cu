@@ -14,7 +14,7 @@
 namespace vg {
 
 static constexpr int kIgemmThreads = 192;
-static constexpr int kMaxStages = 8;
+static constexpr int kMaxStages = 24;
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
     uint32_t c = 32;
@@ -78,16 +78,17 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
+            int tap_i = it_begin / p.c_chunks, c = it_begin % p.c_chunks;
+            int s = 0;
+            uint32_t par = 0;
+            IgemmTap tap = taps[tap_i];
             for (int it = 0; it < iters; ++it) {
-                const int g = it_begin + it;
-                const IgemmTap tap = taps[g / p.c_chunks];
-                const int c = g % p.c_chunks;
-                const int s = it % stages;
-                const uint32_t par = (it / stages) & 1;
                 mbar_wait(&empty[s], par ^ 1);
                 mbar_expect_tx(&full[s], a_stage + b_stage);
                 tma_load_4d(sA + s * a_stage, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx, i0 + tap.dy, b0);
                 tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+                if (++c == p.c_chunks) { c = 0; tap = taps[++tap_i]; }
+                if (++s == stages) { s = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -96,18 +97,30 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const uint32_t layout = p.kchunk == 64 ? 2u : (p.kchunk == 32 ? 4u : 6u);
             const uint32_t sbo = 8 * row_bytes;
             const int ksteps = p.kchunk / 16;
+            // descriptors of stage 0 / k-step 0; per instruction only the start-address field (lo word) moves
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 0, sbo, layout);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 0, sbo, layout);
+            const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+            const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
+            const uint32_t a_step = a_stage >> 4, b_step = b_stage >> 4;
+            int s = 0;
+            uint32_t par = 0, a_lo = a_lo0, b_lo = b_lo0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % stages;
-                const uint32_t par = (it / stages) & 1;
                 mbar_wait(&full[s], par);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * a_stage);
-                const uint32_t b_addr = smem_u32(sB + s * b_stage);
-                for (int k = 0; k < ksteps; ++k) {
-                    umma_bf16(tmem_base, make_smem_desc(a_addr + k * 32, 0, sbo, layout),
-                              make_smem_desc(b_addr + k * 32, 0, sbo, layout), idesc, (it | k) != 0);
+                if (ksteps == 4) {
+                    umma_bf16_lohi(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
+                    umma_bf16_lohi(tmem_base, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                    umma_bf16_lohi(tmem_base, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                    umma_bf16_lohi(tmem_base, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                } else {
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16_lohi(tmem_base, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (it | k) != 0);
                 }
                 umma_commit(&empty[s]);
+                a_lo += a_step;
+                b_lo += b_step;
+                if (++s == stages) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
             }
             umma_commit(tmem_full);   // (with zero iterations this arrives immediately: nothing is pending)
         }
@@ -216,7 +229,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     const int ntap = min(p.taps_per_cta, p.num_taps - tap0);
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pt_begin = static_cast<int>(static_cast<long long>(total_tiles) * split / p.splits);
-    const int pt_end = static_cast<int>(static_cast<long long>(total_tiles) * (split + 1) / p.splits);
+    int pt_end = static_cast<int>(static_cast<long long>(total_tiles) * (split + 1) / p.splits);
+    if (p.debug_flags & 2) pt_end = pt_begin;
     const uint32_t ncols = tmem_cols_for(p.taps_per_cta * p.n_tile);
 
     if (warp == 0 && lane == 0) {
@@ -238,28 +252,38 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            int ia = 0, ib = 0;
-            for (int pt = pt_begin; pt < pt_end; ++pt, ++ia) {
-                int t = pt;
-                const int j0 = (t % p.tiles_w) * p.tw;
-                t /= p.tiles_w;
-                const int i0 = (t % p.tiles_h) * p.th;
-                const int b0 = (t / p.tiles_h) * p.tb;
-                const int sa = ia % SA;
-                mbar_wait(&empty_a[sa], ((ia / SA) & 1) ^ 1);
-                mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
-                for (int a = 0; a < p.m_atoms; ++a)
-                    tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0, i0,
-                                b0);
-                for (int tl = 0; tl < ntap; ++tl, ++ib) {
-                    const IgemmTap tap = p.taps[tap0 + tl];
-                    const int sb = ib % SB;
-                    mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
-                    mbar_expect_tx(&full_b[sb], b_stage);
-                    for (int a = 0; a < n_atoms; ++a)
-                        tma_load_4d(sB + sb * b_stage + a * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
-                                    n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+            int sa = 0, sb = 0;
+            uint32_t par_a = 0, par_b = 0;
+            int t0 = pt_begin;
+            int tj = t0 % p.tiles_w;
+            t0 /= p.tiles_w;
+            int ti = t0 % p.tiles_h, tb_i = t0 / p.tiles_h;
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                const int j0 = tj * p.tw, i0 = ti * p.th, b0 = tb_i * p.tb;
+                mbar_wait(&empty_a[sa], par_a ^ 1);
+                if (p.debug_flags & 8) {
+                    mbar_arrive(&full_a[sa]);
+                } else {
+                    mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
+                    for (int a = 0; a < p.m_atoms; ++a)
+                        tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0,
+                                    i0, b0);
                 }
+                for (int tl = 0; tl < ntap; ++tl) {
+                    const IgemmTap tap = p.taps[tap0 + tl];
+                    mbar_wait(&empty_b[sb], par_b ^ 1);
+                    if (p.debug_flags & 8) {
+                        mbar_arrive(&full_b[sb]);
+                    } else {
+                        mbar_expect_tx(&full_b[sb], b_stage);
+                        for (int a = 0; a < n_atoms; ++a)
+                            tma_load_4d(sB + sb * b_stage + a * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
+                                        n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                    }
+                    if (++sb == SB) { sb = 0; par_b ^= 1; }
+                }
+                if (++sa == SA) { sa = 0; par_a ^= 1; }
+                if (++tj == p.tiles_w) { tj = 0; if (++ti == p.tiles_h) { ti = 0; ++tb_i; } }
             }
         }
     } else if (warp == 1) {
@@ -268,26 +292,50 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
             const uint32_t p_layout = p.p_atom_c == 64 ? 2u : 4u;
             const uint32_t q_layout = p.q_atom_c == 64 ? 2u : (p.q_atom_c == 32 ? 4u : 6u);
             const int ksteps = kpix / 16;
-            int ia = 0, ib = 0;
-            for (int pt = pt_begin; pt < pt_end; ++pt, ++ia) {
-                const int sa = ia % SA;
-                mbar_wait(&full_a[sa], (ia / SA) & 1);
-                const uint32_t a_addr = smem_u32(sA + sa * a_stage);
-                for (int tl = 0; tl < ntap; ++tl, ++ib) {
-                    const int sb = ib % SB;
-                    mbar_wait(&full_b[sb], (ib / SB) & 1);
+            // one UMMA consumes 16 pixel rows: two 8-row groups (SBO apart); MN atoms are LBO apart.  Descriptors of
+            // ring slot 0 / k-step 0 are built once; per instruction only the start-address field (lo word) moves.
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), p_atom_bytes, 8 * p_row, p_layout);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), q_atom_bytes, 8 * q_row, q_layout);
+            const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+            const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
+            const uint32_t a_step = a_stage >> 4, b_step = b_stage >> 4;
+            const uint32_t a_k = (16 * p_row) >> 4, b_k = (16 * q_row) >> 4;
+            int sa = 0, sb = 0;
+            uint32_t par_a = 0, par_b = 0, a_lo = a_lo0, b_lo = b_lo0;
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                mbar_wait(&full_a[sa], par_a);
+                const uint32_t acc = pt != pt_begin;
+                uint32_t d_tmem = tmem_base;
+                for (int tl = 0; tl < ntap; ++tl) {
+                    mbar_wait(&full_b[sb], par_b);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + sb * b_stage);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // one UMMA consumes 16 pixel rows: two 8-row groups (SBO apart); MN atoms are LBO apart
-                        umma_bf16(tmem_base + tl * p.n_tile,
-                                  make_smem_desc(a_addr + k * 16 * p_row, p_atom_bytes, 8 * p_row, p_layout),
-                                  make_smem_desc(b_addr + k * 16 * q_row, q_atom_bytes, 8 * q_row, q_layout), idesc,
-                                  (pt != pt_begin || k != 0) ? 1u : 0u);
+                    if (p.debug_flags & 4) {
+                        mbar_arrive(&empty_b[sb]);
+                    } else {
+                        if (ksteps == 8) {
+                            umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+#pragma unroll
+                            for (int k = 1; k < 8; ++k)
+                                umma_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, 1);
+                        } else if (ksteps == 4) {
+                            umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                            umma_bf16_lohi(d_tmem, a_lo + a_k, a_hi, b_lo + b_k, b_hi, idesc, 1);
+                            umma_bf16_lohi(d_tmem, a_lo + 2 * a_k, a_hi, b_lo + 2 * b_k, b_hi, idesc, 1);
+                            umma_bf16_lohi(d_tmem, a_lo + 3 * a_k, a_hi, b_lo + 3 * b_k, b_hi, idesc, 1);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
+                        }
+                        umma_commit(&empty_b[sb]);
                     }
-                    umma_commit(&empty_b[sb]);
+                    d_tmem += p.n_tile;
+                    b_lo += b_step;
+                    if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
                 }
-                umma_commit(&empty_a[sa]);
+                if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
+                else umma_commit(&empty_a[sa]);
+                a_lo += a_step;
+                if (++sa == SA) { sa = 0; par_a ^= 1; a_lo = a_lo0; }
             }
             umma_commit(tmem_full);
         }
@@ -296,7 +344,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const bool valid = (row < p.m_atoms * p.p_atom_c) && (m < p.m_valid);
-        const bool has_work = pt_end > pt_begin;
+        const bool has_work = (pt_end > pt_begin) && !(p.debug_flags & 1);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -330,17 +378,23 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                         tmem_ld_32x16(taddr + (g4 + 3) * p.n_tile + c, v3);
                         tmem_ld_wait();
                         if (valid && has_work) {
+                            // all 16 read-modify-writes of this chunk in flight together: loads first, stores after
+                            float4 old[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int n = min(n0 + c + j, p.n_valid - 1);
+                                old[j] = __ldcg(reinterpret_cast<const float4*>(dst + static_cast<long long>(n) * p.s_n));
+                            }
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int n = n0 + c + j;
                                 if (n < p.n_valid) {
-                                    float4* q4 = reinterpret_cast<float4*>(dst + static_cast<long long>(n) * p.s_n);
-                                    float4 o = *q4;
+                                    float4 o = old[j];
                                     o.x += __uint_as_float(v0[j]);
                                     o.y += __uint_as_float(v1[j]);
                                     o.z += __uint_as_float(v2[j]);
                                     o.w += __uint_as_float(v3[j]);
-                                    *q4 = o;
+                                    __stcg(reinterpret_cast<float4*>(dst + static_cast<long long>(n) * p.s_n), o);
                                 }
                             }
                         }

@@ -72,6 +72,7 @@ struct alignas(64) WgradParams {
     // splits > 1: each CTA stores its fp32 partial tile to `partial` ([cta][tap_local][128 rows][n_tile], coalesced
     // vector stores) and wgrad_reduce_kernel sums the splits into dw.  No atomics either way.
     float* partial;
+    int debug_flags;       // bit0: skip the epilogue stores, bit1: skip TMA+MMA main loop (profiling experiments only)
     int vec4_taps;         // k*k and taps_per_cta multiples of 4, dw 16-byte aligned: dw[m][n][4 taps] moves as one float4
 };
 
