@@ -38,3 +38,8 @@ for k, (us, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:28]:
 gaps = [(evs[i+1].time_range.start - evs[i].time_range.end) for i in range(len(evs)-1)]
 big = sorted(gaps, reverse=True)[:8]
 print("largest gaps (us):", [round(g,1) for g in big], " sum of gaps >2us:", round(sum(g for g in gaps if g > 2)/3,1), "us/step")
+# per-launch listing of the igemm kernels in the last profiled step (launch order)
+names = [e for e in evs if 'igemm' in e.name or 'wgrad_reduce' in e.name]
+per = len(names) // 3
+print("igemm launches of one step (order, us):")
+print(" ".join(f"{'W' if 'wgrad_k' in e.name else ('R' if 'reduce' in e.name else 'F')}{e.time_range.elapsed_us():.0f}" for e in names[-per:]))

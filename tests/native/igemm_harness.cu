@@ -268,6 +268,8 @@ int main(int argc, char** argv) {
         {"k4s2p1 16x16 c16->32 B4", geom(4, 16, 16, 16, 32, 4, 2, 1)},
         {"k4s1p0 4x4 c1024->128 B64 (splitK)", geom(64, 4, 4, 1024, 128, 4, 1, 0)},
         {"k4s2p1 64x64 c16->64 B2 (padded)", geom(2, 64, 64, 16, 64, 4, 2, 1)},
+        {"k3s1p1 32x32 c16<-64 B3 (padded)", geom(3, 32, 32, 16, 64, 3, 1, 1)},
+        {"k4s2p1 16x16 c32->64 B4", geom(4, 16, 16, 32, 64, 4, 2, 1)},
     };
     bool all = true;
     for (const Case& c : cases) {
@@ -281,6 +283,9 @@ int main(int argc, char** argv) {
         perf_case("G 512->256 8^2->16^2", geom(256, 16, 16, 256, 512, 4, 2, 1), 20);
         perf_case("G 256->128 16^2->32^2", geom(256, 32, 32, 128, 256, 4, 2, 1), 20);
         perf_case("G 128->64 32^2->64^2", geom(256, 64, 64, 64, 128, 4, 2, 1), 20);
+        perf_case("D 16pad->64 64^2->32^2 B512", geom(512, 64, 64, 16, 64, 4, 2, 1), 20);
+        perf_case("G 64->16pad k3 64^2", geom(256, 64, 64, 16, 64, 3, 1, 1), 20);
+        perf_case("D 256->512 8^2->4^2 B512", geom(512, 8, 8, 256, 512, 4, 2, 1), 20);
     }
     printf(all ? "ALL PASS\n" : "SOME FAILED\n");
     return all ? 0 : 1;

@@ -36,6 +36,15 @@ static int pick_n_tile(int n) {
     return 0;
 }
 
+// Narrow-channel layers (C == 16 or 32, one channel chunk): put several taps into one pipeline stage.
+static int pick_tps(int kchunk, int c_chunks, int taps) {
+    if (c_chunks != 1 || kchunk >= 64) return 1;
+    const int want = kchunk == 16 ? 4 : 2;
+    for (int t = want; t > 1; --t)
+        if (taps % t == 0) return t;
+    return 1;
+}
+
 static int pick_stages(int stage_bytes, int n_tile) {
     // two CTAs per SM when the accumulator is narrow (epilogue of one overlaps the main loop of the other)
     const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048;
@@ -148,7 +157,8 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
             t.tap_id = static_cast<int16_t>(ky * k + kx);
             t.brow = (ky * k + kx) * g->small_c;
         }
-    p.stages = pick_stages((128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile);
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -253,7 +263,8 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.out_C = g->big_c;
         p.osy = p.osx = s;
     }
-    p.stages = pick_stages((128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile);
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();
@@ -268,8 +279,12 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     WgradParams p;
     std::memset(&p, 0, sizeof(p));
     const int k = g->kernel, s = g->stride, pad = g->pad;
+    // taps per UMMA (side by side along N, N <= 256) and pixels reduced per pipeline stage (Q stage ~32 KB)
+    const int nt = wgrad_n_tile(g->big_c);
+    const int tpc = std::min(std::min(k * k, 512 / nt), 16);
+    const int merge = nt <= 64 ? std::max(1, std::min(tpc, 256 / nt)) : 1;   // wide tiles keep one tap per UMMA
     const char* kp = getenv("VG_WGRAD_KPIX");
-    const int kpix = kp ? atoi(kp) : 128;   // pixels reduced per pipeline stage
+    const int kpix = kp ? atoi(kp) : 128;
     pick_box(kpix, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
@@ -284,6 +299,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.taps_per_cta = std::min(p.num_taps, 512 / p.n_tile);
     if (p.num_taps % 4 == 0) p.taps_per_cta = std::max(4, p.taps_per_cta / 4 * 4);
     p.taps_per_cta = std::min(p.taps_per_cta, 16);
+    p.merge = p.n_tile <= 64 ? std::max(1, std::min(p.taps_per_cta, 256 / p.n_tile)) : 1;
     if (ws_needed == nullptr) {
         const int rc = make_view(&p.pmap, small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.p_atom_c, p.tw,
                                  p.th, p.tb, p.p_atom_c * 2);
@@ -312,7 +328,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     // one CTA per SM (the accumulators fill TMEM): aim at a single full wave; split the pixel range only when the
     // (channel tile, tap group) grid alone leaves most SMs idle
     p.splits = base_ctas >= 100 ? 1 : std::max(1, std::min(total_tiles, 148 / base_ctas));
-    const int a_stage = kpix * 256, b_stage = p.n_tile * kpix * 2;
+    const int a_stage = kpix * 256, b_stage = p.merge * p.n_tile * kpix * 2;
     p.stages_a = kpix >= 128 ? 2 : 3;
     p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;

@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_bytes = p.kchunk * 2;
-    const int a_stage = 128 * row_bytes;
-    const int b_stage = p.n_tile * row_bytes;
+    const int tps = p.tps > 1 ? p.tps : 1;
+    const int a_sub = 128 * row_bytes, b_sub = p.n_tile * row_bytes;   // one tap's operand tiles
+    const int a_stage = tps * a_sub;
+    const int b_stage = tps * b_sub;
     const int stages = p.stages;
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * a_stage;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int phase = blockIdx.z / ksplit, kslice = blockIdx.z % ksplit;
     const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
-    const int total_iters = p.taps_per_phase * p.c_chunks;
+    const int total_iters = p.taps_per_phase / tps * p.c_chunks;
     const int it_begin = static_cast<int>(static_cast<long long>(total_iters) * kslice / ksplit);
     const int it_end = static_cast<int>(static_cast<long long>(total_iters) * (kslice + 1) / ksplit);
     const int iters = it_end - it_begin;
@@ -78,16 +80,19 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            int tap_i = it_begin / p.c_chunks, c = it_begin % p.c_chunks;
+            int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
             int s = 0;
             uint32_t par = 0;
-            IgemmTap tap = taps[tap_i];
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(&empty[s], par ^ 1);
                 mbar_expect_tx(&full[s], a_stage + b_stage);
-                tma_load_4d(sA + s * a_stage, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx, i0 + tap.dy, b0);
-                tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
-                if (++c == p.c_chunks) { c = 0; tap = taps[++tap_i]; }
+                for (int t = 0; t < tps; ++t) {
+                    const IgemmTap tap = taps[tap_i + t];
+                    tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx,
+                                i0 + tap.dy, b0);
+                    tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+                }
+                if (++c == p.c_chunks) { c = 0; tap_i += tps; }
                 if (++s == stages) { s = 0; par ^= 1; }
             }
         }
@@ -114,8 +119,11 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     umma_bf16_lohi(tmem_base, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
                     umma_bf16_lohi(tmem_base, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
                 } else {
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16_lohi(tmem_base, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (it | k) != 0);
+                    const uint32_t a_t = a_sub >> 4, b_t = b_sub >> 4;
+                    for (int t = 0; t < tps; ++t)
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16_lohi(tmem_base, a_lo + t * a_t + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi, idesc,
+                                           (it | t | k) != 0);
                 }
                 umma_commit(&empty[s]);
                 a_lo += a_step;
@@ -210,8 +218,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     const int p_row = p.p_atom_c * 2, q_row = p.q_atom_c * 2;       // bytes per pixel row inside one atom
     const int p_atom_bytes = kpix * p_row, q_atom_bytes = kpix * q_row;
     const int n_atoms = p.n_tile / p.q_atom_c;
+    const int merge = p.merge > 1 ? p.merge : 1;
     const int a_stage = kpix * 256;                                  // room for all 128 M rows (128 ch x 2 B) per pixel
-    const int b_stage = n_atoms * q_atom_bytes;
+    const int tap_bytes = n_atoms * q_atom_bytes;                    // one tap's Q tile
+    const int b_stage = merge * tap_bytes;
     const int SA = p.stages_a, SB = p.stages_b;
     uint8_t* sA = smem;
     uint8_t* sB = smem + SA * a_stage;
@@ -269,16 +279,19 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                         tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0,
                                     i0, b0);
                 }
-                for (int tl = 0; tl < ntap; ++tl) {
-                    const IgemmTap tap = p.taps[tap0 + tl];
+                for (int tl = 0; tl < ntap; tl += merge) {
+                    const int cnt = min(merge, ntap - tl);
                     mbar_wait(&empty_b[sb], par_b ^ 1);
                     if (p.debug_flags & 8) {
                         mbar_arrive(&full_b[sb]);
                     } else {
-                        mbar_expect_tx(&full_b[sb], b_stage);
-                        for (int a = 0; a < n_atoms; ++a)
-                            tma_load_4d(sB + sb * b_stage + a * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
-                                        n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                        mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                        for (int j = 0; j < cnt; ++j) {
+                            const IgemmTap tap = p.taps[tap0 + tl + j];
+                            for (int a = 0; a < n_atoms; ++a)
+                                tma_load_4d(sB + sb * b_stage + j * tap_bytes + a * q_atom_bytes, &p.qmap[tap.view],
+                                            &full_b[sb], n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                        }
                     }
                     if (++sb == SB) { sb = 0; par_b ^= 1; }
                 }
@@ -288,7 +301,9 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 1, 1);
+            const uint32_t idesc_full = make_idesc_bf16(128, merge * p.n_tile, 1, 1);
+            const int tail = ntap % merge;
+            const uint32_t idesc_tail = make_idesc_bf16(128, (tail ? tail : merge) * p.n_tile, 1, 1);
             const uint32_t p_layout = p.p_atom_c == 64 ? 2u : 4u;
             const uint32_t q_layout = p.q_atom_c == 64 ? 2u : (p.q_atom_c == 32 ? 4u : 6u);
             const int ksteps = kpix / 16;
@@ -306,7 +321,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                 mbar_wait(&full_a[sa], par_a);
                 const uint32_t acc = pt != pt_begin;
                 uint32_t d_tmem = tmem_base;
-                for (int tl = 0; tl < ntap; ++tl) {
+                for (int tl = 0; tl < ntap; tl += merge) {
+                    const uint32_t idesc = (tl + merge <= ntap) ? idesc_full : idesc_tail;
                     mbar_wait(&full_b[sb], par_b);
                     tc_fence_after();
                     if (p.debug_flags & 4) {
@@ -328,7 +344,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                         }
                         umma_commit(&empty_b[sb]);
                     }
-                    d_tmem += p.n_tile;
+                    d_tmem += merge * p.n_tile;
                     b_lo += b_step;
                     if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
                 }
@@ -427,15 +443,19 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
 
 // dw[m][n][tap] += sum over splits of partial[cta(split, mn, group)][tap_local][row][col]
 // VEC = 4: one thread owns the 4 consecutive taps dw[m][n][4t..4t+3] (one float4 read-add-write); VEC = 1: one tap.
-template <int VEC>
+// WARP = true: one warp per output unit, lanes stride over the splits (few outputs, many splits);
+// WARP = false: one thread per output unit (many outputs, few splits).
+template <int VEC, bool WARP>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) {
     const int tap_units = p.num_taps / VEC;
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * tap_units;
     const int rows_per_tile = p.m_atoms * p.p_atom_c;
     const long long plane = static_cast<long long>(128) * p.n_tile;
     const long long cta_stride = static_cast<long long>(p.taps_per_cta) * plane;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = WARP ? tid / 32 : tid; i < total; i += WARP ? nthr / 32 : nthr) {
         // i enumerates (m, tap unit, n) with n fastest so that the partial reads are coalesced
         const int n = static_cast<int>(i % p.n_valid);
         const long long r = i / p.n_valid;
@@ -450,9 +470,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) 
         float acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        for (int s = 0; s < p.splits; ++s) {
+        for (int s = WARP ? lane : 0; s < p.splits; s += WARP ? 32 : 1) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] += __ldcs(src + s * cta_stride + v * plane);
+        }
+        if (WARP) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
+            if (lane != 0) continue;
         }
         float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(n) * p.s_n +
                      static_cast<long long>(tap) * p.s_tap;
@@ -491,7 +518,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
         attr_err = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
-    const int stage_bytes = (128 + p.n_tile) * p.kchunk * 2;
+    const int stage_bytes = (p.tps > 1 ? p.tps : 1) * (128 + p.n_tile) * p.kchunk * 2;
     const int smem = smem_bytes_for(p.stages, stage_bytes);
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.n_tiles, p.num_phases * ksplit);
@@ -519,16 +546,24 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int kpix = p.tw * p.th * p.tb;
-    const int smem = p.stages_a * kpix * 256 + p.stages_b * p.n_tile * kpix * 2 + 1024 + kBarrierBytes;
+    const int smem = p.stages_a * kpix * 256 + p.stages_b * (p.merge > 1 ? p.merge : 1) * p.n_tile * kpix * 2 + 1024 +
+                     kBarrierBytes;
     const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
     dim3 grid(p.splits, p.m_tiles * p.n_tiles, tap_groups);
     igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.splits <= 1) return static_cast<int>(e);
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * p.num_taps / (p.vec4_taps ? 4 : 1);
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
-    if (p.vec4_taps) wgrad_reduce_kernel<4><<<blocks, 256, 0, stream>>>(p);
-    else wgrad_reduce_kernel<1><<<blocks, 256, 0, stream>>>(p);
+    const bool warp = p.splits >= 16 && total <= 32768;   // few outputs, many splits: lanes stride over the splits
+    const long long threads = warp ? total * 32 : total;
+    const int blocks = static_cast<int>(std::min<long long>((threads + 255) / 256, 148 * 16));
+    if (p.vec4_taps) {
+        if (warp) wgrad_reduce_kernel<4, true><<<blocks, 256, 0, stream>>>(p);
+        else wgrad_reduce_kernel<4, false><<<blocks, 256, 0, stream>>>(p);
+    } else {
+        if (warp) wgrad_reduce_kernel<1, true><<<blocks, 256, 0, stream>>>(p);
+        else wgrad_reduce_kernel<1, false><<<blocks, 256, 0, stream>>>(p);
+    }
     return static_cast<int>(cudaGetLastError());
 }
 

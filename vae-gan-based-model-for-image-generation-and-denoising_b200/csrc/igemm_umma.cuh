@@ -37,6 +37,8 @@ struct alignas(64) IgemmParams {
     int n_tile;    // UMMA N (multiple of 16, <= 256)
     int n_tiles;   // grid.y: N_total / n_tile
     int stages;
+    int tps;       // taps per pipeline stage (> 1 only when c_chunks == 1: narrow-channel layers, amortises the
+                   // per-stage barrier / issue overhead over several K=16..32 slabs)
     // output: NHWC tensor, element (b, y, x, n) with y = i*osy + ay[phase], x = j*osx + ax[phase]
     void* out;
     int out_fp32;
@@ -56,6 +58,8 @@ struct alignas(64) WgradParams {
     IgemmTap taps[16];
     int num_taps;
     int taps_per_cta;      // accumulators resident in TMEM per CTA (taps_per_cta * n_tile <= 512)
+    int merge;             // taps whose Q tiles sit side by side in one stage and are multiplied by ONE UMMA of
+                           // N = merge * n_tile (<= 256): the P tile is read from smem once per `merge` taps
     int tw, th, tb;        // pixel box; tw*th*tb = kpix (multiple of 16, <= 128)
     int tiles_w, tiles_h, tiles_b;
     int p_atom_c;          // channels per MN-major atom of P: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
