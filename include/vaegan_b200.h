@@ -112,6 +112,16 @@ int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int channels, con
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     float* mean_out, float* rstd_out, float* scale_out, float* shift_out, float* ws, size_t ws_bytes,
                     void* stream);
+/* Fused forms used by the training step: ONE cooperative launch each (grid barrier between the statistics pass and
+ * the apply pass, whose re-read of the activation is served from L2).  stats = [4][channels] = mean, rstd, scale,
+ * shift: written by the forward, consumed by the backward.  Shapes the fused kernel does not take fall back to the
+ * two-kernel forms above internally. */
+int vg_bn_act_train_fwd(const void* x, VgDType dt, long long rows, int channels, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                        float eps, VgAct act, float slope, float* stats, void* y, void* stream);
+int vg_bn_act_train_bwd(const void* dy, const void* x, VgDType dt, long long rows, int channels, const float* stats,
+                        VgAct act, float slope, float* dgamma, float* dbeta, void* dx, float* ws, size_t ws_bytes,
+                        void* stream);
 /* eval-mode BatchNorm folded to scale/shift from the running statistics (main_vae.py:360, decoder.eval()). */
 int vg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int channels, float* scale_out, float* shift_out, void* stream);

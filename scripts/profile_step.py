@@ -43,3 +43,9 @@ names = [e for e in evs if 'igemm' in e.name or 'wgrad_reduce' in e.name]
 per = len(names) // 3
 print("igemm launches of one step (order, us):")
 print(" ".join(f"{'W' if 'wgrad_k' in e.name else ('R' if 'reduce' in e.name else 'F')}{e.time_range.elapsed_us():.0f}" for e in names[-per:]))
+
+for pat, tag in (("channel_reduce_kernel<__nv_bfloat16, 1>", "BN-bwd reduce"), ("bn_act_bwd_apply", "BN-bwd apply"),
+                 ("channel_reduce_kernel<__nv_bfloat16, 0>", "BN stats"), ("scale_shift_act_vec", "BN apply")):
+    sel = [e for e in evs if pat in e.name]
+    per = len(sel) // 3
+    print(tag, "per-launch us:", " ".join(f"{e.time_range.elapsed_us():.0f}" for e in sel[-per:]))

@@ -129,6 +129,17 @@ def test_batchnorm_act_fwd_bwd(rows, C, act, slope, prec):
     dx = fn.bn_act_bwd(dy.cuda().to(dt).view(1, 1, rows, C), xd, stats, act, slope, dg, db)
     torch.cuda.synchronize()
     out_tol = 1e-5 if prec == "fp32" else 6e-3
+    # the fused (single cooperative launch) forms must agree with the two-kernel forms
+    rm2, rv2, nbt2 = rm.cuda(), rv.cuda(), torch.zeros((), dtype=torch.int64, device="cuda")
+    y2, stats2 = fn.bn_act_train_fwd(xd, gamma.cuda(), beta.cuda(), rm2, rv2, nbt2, 0.1, 1e-5, act, slope)
+    dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx2 = fn.bn_act_train_bwd(dy.cuda().to(dt).view(1, 1, rows, C), xd, stats2, act, slope, dg2, db2)
+    torch.cuda.synchronize()
+    assert int(nbt2) == 1 and rel_err(rm2, rm_ref) < 1e-5 and rel_err(rv2, rv_ref) < 1e-5
+    assert rel_err(stats2, stats) < 1e-5
+    assert rel_err(y2.float().view(rows, C), y_ref) < out_tol
+    assert rel_err(dx2.float().view(rows, C), xr.grad) < (2e-4 if prec == "fp32" else 1e-2) * (10 if rows < 16 else 1)
+    assert rel_err(dg2, gr.grad) < 1e-4 and rel_err(db2, br.grad) < 1e-4
     assert int(nbt) == 1
     assert rel_err(rmd, rm_ref) < 1e-5 and rel_err(rvd, rv_ref) < 1e-5
     assert rel_err(y.float().view(rows, C), y_ref) < out_tol

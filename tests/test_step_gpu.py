@@ -126,7 +126,10 @@ def test_graph_replay_equals_eager_and_device_noise_runs():
         # The two runs differ only in the summation order of wgrad's fp32 atomics, but Adam's first updates are
         # ~lr*sign(g), so near-zero gradients flip individual weights by 2*lr and the GAN trajectories drift apart:
         # tight on the first step, loose afterwards.
-        tol = 2e-3 if it == 0 else 5e-2
+        # (repeated runs of the SAME configuration from the same state already differ by up to ~4e-3 in the losses:
+        # the fp64-atomic BatchNorm totals round to fp32 means that can differ by one ulp, and a 1-ulp change
+        # avalanches through bf16 rounding - scripts/debug_determinism.py)
+        tol = 1e-2 if it == 0 else 5e-2
         for k in la:
             assert abs(float(la[k]) - float(lb[k])) <= tol * abs(float(la[k])) + 1e-5, (it, k)
     # noise drawn on the device (Philox) instead of injected: runs, finite, and differs from step to step

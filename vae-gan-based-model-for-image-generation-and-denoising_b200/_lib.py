@@ -42,6 +42,9 @@ PROTOTYPES = {
     "vg_bn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "vg_bn_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,
                                 c_size_t, _P]),
+    "vg_bn_act_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_float, _P,
+                                    _P, _P]),
+    "vg_bn_act_train_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, _P, c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "vg_bn_eval_coeffs": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P]),
     "vg_scale_shift_act": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_int, c_float, _P, c_int, _P]),
     "vg_bn_act_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -244,6 +245,227 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused BatchNorm passes (cooperative launch: all blocks co-resident, one grid barrier).
+//   FWD : pass 1 = pivoted sums -> barrier -> every thread derives scale/shift of ITS channels from the totals ->
+//         pass 2 = y = act(x*scale+shift).  Block 0 also writes mean/rstd/scale/shift and updates the running stats.
+//   BWD : pass 1 = sum dz, sum dz*xhat -> barrier -> pass 2 = dx = scale*(dz - c1 - xhat*c2); block 0 adds dgamma/dbeta.
+// The second pass re-reads the block's own rows, which are L2-resident for all but the largest tensors, so HBM sees
+// the activation once per direction instead of twice, and two launches (reduce + apply) become one.
+// Threads keep a FIXED channel group for the whole kernel, so per-channel parameters live in registers.
+// ------------------------------------------------------------------------------------------------
+__device__ unsigned int g_barrier[kSlots];
+__device__ unsigned int g_ticket2[kSlots];
+
+struct FusedArgs {
+    const void* x;      // raw conv output
+    const void* dy;     // BWD: gradient of the activated output
+    void* out;          // FWD: activated output; BWD: gradient of the raw conv output
+    long long rows;
+    int C;
+    long long rows_per_block;
+    int act;
+    float slope;
+    int slot;
+    const float *gamma, *beta;
+    float *running_mean, *running_var;
+    long long* num_batches_tracked;
+    float momentum, eps;
+    float* stats;       // [4][C]: mean, rstd, scale, shift (FWD: written, BWD: read)
+    float *dgamma, *dbeta;
+};
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kThreads) bn_fused_kernel(const FusedArgs a) {
+    constexpr int V = Vec<T>::N;
+    constexpr int U = 4;                            // rows in flight per thread
+    __shared__ float red[kThreads][2 * V + 1];
+    const int lanes = a.C / V;                      // <= kThreads (checked by the launcher), power of two
+    const int rows_per_iter = kThreads / lanes;
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    const long long r0 = blockIdx.x * a.rows_per_block;
+    const long long r1 = min(a.rows, r0 + a.rows_per_block);
+    const T* x = static_cast<const T*>(a.x);
+    const T* dy = static_cast<const T*>(a.dy);
+    T* out = static_cast<T*>(a.out);
+    const int reps = max(1, min(16, kAccDoubles / (2 * a.C)));
+    double* acc_all = g_acc[a.slot];
+    double* acc = acc_all + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
+    const int c0 = lane * V;
+    const double n = static_cast<double>(a.rows);
+
+    float sc[V], sh[V], mu[V], rs[V], piv[V];
+    if (BWD) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            mu[i] = a.stats[c0 + i];
+            rs[i] = a.stats[a.C + c0 + i];
+            sc[i] = a.stats[2 * a.C + c0 + i];
+            sh[i] = a.stats[3 * a.C + c0 + i];
+        }
+    } else {
+        Vec<T>::load(x + c0, piv);
+    }
+
+    // ---- pass 1
+    float s0[V], s1[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0.f;
+    for (long long r = r0 + rsub; r < r1; r += static_cast<long long>(rows_per_iter) * U) {
+        float xv[U][V], dv[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+            if (rr < r1) {
+                Vec<T>::load(x + rr * a.C + c0, xv[u]);
+                if (BWD) Vec<T>::load(dy + rr * a.C + c0, dv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+            if (rr < r1) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    if (BWD) {
+                        const float z = fmaf(xv[u][i], sc[i], sh[i]);
+                        const float dz = dv[u][i] * act_grad(z, a.act, a.slope);
+                        s0[i] += dz;
+                        s1[i] = fmaf(dz, (xv[u][i] - mu[i]) * rs[i], s1[i]);
+                    } else {
+                        const float d = xv[u][i] - piv[i];
+                        s0[i] += d;
+                        s1[i] = fmaf(d, d, s1[i]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) { red[threadIdx.x][i] = s0[i]; red[threadIdx.x][V + i] = s1[i]; }
+    __syncthreads();
+    if (rsub == 0) {
+        for (int j = 1; j < rows_per_iter; ++j)
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                s0[i] += red[j * lanes + lane][i];
+                s1[i] += red[j * lanes + lane][V + i];
+            }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            atomicAdd(acc + c0 + i, static_cast<double>(s0[i]));
+            atomicAdd(acc + a.C + c0 + i, static_cast<double>(s1[i]));
+        }
+    }
+
+    // ---- grid barrier (co-residency is guaranteed by the cooperative launch)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&g_barrier[a.slot], 1u);
+        const long long t_start = clock64();
+        while (*reinterpret_cast<volatile unsigned int*>(&g_barrier[a.slot]) < gridDim.x) {
+            if (clock64() - t_start > 4000000000LL) {   // ~2 s: turn a would-be hang into a CUDA error
+                printf("vg: bn_fused_kernel grid barrier timed out (block %d of %d)\n", blockIdx.x, gridDim.x);
+                __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+
+    // ---- totals of this thread's channels
+    float c1[V], c2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int r = 0; r < reps; ++r) {
+            t0 += __ldcg(acc_all + static_cast<long long>(r) * 2 * a.C + c0 + i);
+            t1 += __ldcg(acc_all + static_cast<long long>(r) * 2 * a.C + a.C + c0 + i);
+        }
+        if (BWD) {
+            c1[i] = static_cast<float>(t0 / n);
+            c2[i] = static_cast<float>(t1 / n);
+            if (blockIdx.x == 0 && rsub == 0) {
+                if (a.dbeta != nullptr) a.dbeta[c0 + i] += static_cast<float>(t0);
+                if (a.dgamma != nullptr) a.dgamma[c0 + i] += static_cast<float>(t1);
+            }
+        } else {
+            const double dmean = t0 / n;
+            const double mean = static_cast<double>(piv[i]) + dmean;
+            double var = t1 / n - dmean * dmean;
+            if (var < 0.0) var = 0.0;
+            const double rstd = 1.0 / sqrt(var + static_cast<double>(a.eps));
+            const float g = a.gamma ? a.gamma[c0 + i] : 1.f, bt = a.beta ? a.beta[c0 + i] : 0.f;
+            sc[i] = static_cast<float>(g * rstd);
+            sh[i] = static_cast<float>(bt - mean * g * rstd);
+            if (blockIdx.x == 0 && rsub == 0) {
+                const int c = c0 + i;
+                a.stats[c] = static_cast<float>(mean);
+                a.stats[a.C + c] = static_cast<float>(rstd);
+                a.stats[2 * a.C + c] = sc[i];
+                a.stats[3 * a.C + c] = sh[i];
+                if (a.running_mean != nullptr) {
+                    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                    a.running_mean[c] = static_cast<float>((1.0 - a.momentum) * a.running_mean[c] + a.momentum * mean);
+                    a.running_var[c] = static_cast<float>((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+                }
+            }
+        }
+    }
+    if (!BWD && blockIdx.x == 0 && threadIdx.x == 0 && a.num_batches_tracked != nullptr) *a.num_batches_tracked += 1;
+
+    // ---- everyone has read the totals once the second ticket is full: the last block re-arms the slot
+    __shared__ bool last2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last2 = atomicAdd(&g_ticket2[a.slot], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last2) {
+        for (int i = threadIdx.x; i < reps * 2 * a.C; i += kThreads) acc_all[i] = 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            g_barrier[a.slot] = 0;
+            g_ticket2[a.slot] = 0;
+            __threadfence();
+        }
+    }
+
+    // ---- pass 2
+    for (long long r = r0 + rsub; r < r1; r += static_cast<long long>(rows_per_iter) * U) {
+        float xv[U][V], dv[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+            if (rr < r1) {
+                Vec<T>::load(x + rr * a.C + c0, xv[u]);
+                if (BWD) Vec<T>::load(dy + rr * a.C + c0, dv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+            if (rr < r1) {
+                float o[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float z = fmaf(xv[u][i], sc[i], sh[i]);
+                    if (BWD) {
+                        const float dz = dv[u][i] * act_grad(z, a.act, a.slope);
+                        const float xhat = (xv[u][i] - mu[i]) * rs[i];
+                        o[i] = sc[i] * (dz - c1[i] - xhat * c2[i]);
+                    } else {
+                        o[i] = act_fwd(z, a.act, a.slope);
+                    }
+                }
+                Vec<T>::store(out + rr * a.C + c0, o);
+            }
+        }
+    }
+}
+
 struct ReducePlan {
     int blocks;
     long long rows_per_block;
@@ -277,6 +499,38 @@ int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
     if (dt == VG_BF16) channel_reduce_kernel<__nv_bfloat16, MODE><<<blocks, kThreads, 0, st>>>(a);
     else channel_reduce_kernel<float, MODE><<<blocks, kThreads, 0, st>>>(a);
     VG_LAUNCHED();
+    return VG_OK;
+}
+
+// Cooperative launch of the fused BatchNorm kernel; returns VG_ERR_SHAPE when the shape does not fit (caller falls
+// back to the two-kernel path).
+template <bool BWD>
+int launch_fused(VgDType dt, FusedArgs a, cudaStream_t st) {
+    const int V = dt == VG_BF16 ? 8 : 4;
+    if (a.C % V != 0 || !is_pow2(a.C / V) || a.C / V > kThreads || a.C > kMaxChannels) return VG_ERR_SHAPE;
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    int& o = occ[dt == VG_BF16][BWD];
+    if (o == 0) {
+        int v = 0;
+        cudaError_t e = dt == VG_BF16
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, bn_fused_kernel<__nv_bfloat16, BWD>, kThreads, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, bn_fused_kernel<float, BWD>, kThreads, 0);
+        if (e != cudaSuccess || v <= 0) return VG_ERR_SHAPE;
+        o = v;
+    }
+    int sms = 148;
+    const int lanes = a.C / V, rows_per_iter = kThreads / lanes;
+    long long want = (a.rows + static_cast<long long>(rows_per_iter) * 4 - 1) / (static_cast<long long>(rows_per_iter) * 4);
+    int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sms) * std::min(o, 4))));
+    a.rows_per_block = (a.rows + blocks - 1) / blocks;
+    blocks = static_cast<int>((a.rows + a.rows_per_block - 1) / a.rows_per_block);
+    a.slot = next_slot();
+    void* args[] = {&a};
+    cudaError_t e = dt == VG_BF16
+        ? cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bn_fused_kernel<__nv_bfloat16, BWD>), dim3(blocks), dim3(kThreads), args, 0, st)
+        : cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bn_fused_kernel<float, BWD>), dim3(blocks), dim3(kThreads), args, 0, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(bn_fused_kernel)");
+    note_launch();
     return VG_OK;
 }
 
@@ -664,4 +918,45 @@ extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, int Cs, float* dst, 
                                                                           HW, act, slope);
     VG_LAUNCHED();
     return VG_OK;
+}
+
+
+/* Fused train-mode BatchNorm + activation forward: one cooperative launch (statistics, running-stat update, affine,
+ * activation).  stats = [4][C] (mean, rstd, scale, shift) is written for the backward pass. */
+extern "C" int vg_bn_act_train_fwd(const void* x, VgDType dt, long long rows, int C, const float* gamma,
+                                   const float* beta, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, float momentum, float eps, VgAct act, float slope,
+                                   float* stats, void* y, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (x == nullptr || stats == nullptr || y == nullptr) return fail(VG_ERR_ARG, "bn_act_train_fwd: null pointer");
+    if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
+    FusedArgs a{};
+    a.x = x; a.out = y; a.rows = rows; a.C = C; a.act = act; a.slope = slope;
+    a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
+    a.num_batches_tracked = num_batches_tracked; a.momentum = momentum; a.eps = eps; a.stats = stats;
+    rc = launch_fused<false>(dt, a, as_stream(stream));
+    if (rc != VG_ERR_SHAPE) return rc;
+    // shapes the fused kernel does not take: statistics kernel + apply kernel
+    rc = vg_bn_train_fwd(x, dt, rows, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, stats,
+                         stats + C, stats + 2 * C, stats + 3 * C, nullptr, 0, stream);
+    if (rc != VG_OK) return rc;
+    return vg_scale_shift_act(x, dt, rows, C, stats + 2 * C, stats + 3 * C, act, slope, y, dt, stream);
+}
+
+/* Fused backward of act(BN(x)): one cooperative launch; stats as written by the forward. */
+extern "C" int vg_bn_act_train_bwd(const void* dy, const void* x, VgDType dt, long long rows, int C, const float* stats,
+                                   VgAct act, float slope, float* dgamma, float* dbeta, void* dx, float* ws,
+                                   size_t ws_bytes, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dy == nullptr || x == nullptr || dx == nullptr || stats == nullptr)
+        return fail(VG_ERR_ARG, "bn_act_train_bwd: null pointer");
+    FusedArgs a{};
+    a.x = x; a.dy = dy; a.out = dx; a.rows = rows; a.C = C; a.act = act; a.slope = slope;
+    a.stats = const_cast<float*>(stats); a.dgamma = dgamma; a.dbeta = dbeta;
+    rc = launch_fused<true>(dt, a, as_stream(stream));
+    if (rc != VG_ERR_SHAPE) return rc;
+    return vg_bn_act_bwd(dy, x, dt, rows, C, stats + 2 * C, stats + 3 * C, stats, stats + C, act, slope, dgamma, dbeta, dx,
+                         ws, ws_bytes, stream);
 }

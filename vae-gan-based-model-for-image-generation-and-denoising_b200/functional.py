@@ -113,6 +113,8 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
     nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
     ws = _ws(nbytes, small.device) if nbytes else None
     call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream())
+    if ws is not None and WgradOverlap.stream is not None:
+        WgradOverlap.keepalive.append(ws)
     return dw
 
 
@@ -131,6 +133,30 @@ def bn_train_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, num_ba
          _p(num_batches_tracked), float(momentum), float(eps), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
          _p(ws), nbytes, _stream())
     return stats
+
+
+def bn_act_train_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float,
+                     eps: float, act: int, slope: float, out=None):
+    """Fused training BatchNorm + activation (one cooperative launch).  Returns (y, stats[4, C])."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    stats = torch.empty((4, C), dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty_like(x)
+    call("vg_bn_act_train_fwd", _p(x), _DT[x.dtype], rows, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         _p(num_batches_tracked), float(momentum), float(eps), act, float(slope), _p(stats), _p(y), _stream())
+    return y, stats
+
+
+def bn_act_train_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act: int, slope: float, dgamma, dbeta,
+                     out=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = out if out is not None else torch.empty_like(x)
+    nbytes = _lib.load().vg_bn_bwd_workspace_bytes(rows, C)
+    ws = _ws(nbytes, x.device)
+    call("vg_bn_act_train_bwd", _p(dy), _p(x), _DT[x.dtype], rows, C, _p(stats), act, float(slope), _p(dgamma),
+         _p(dbeta), _p(dx), _p(ws), nbytes, _stream())
+    return dx
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps: float):
@@ -195,6 +221,31 @@ def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0, cha
     dst = torch.empty((B, C, H, W), dtype=torch.float32, device=src.device)
     call("vg_nhwc_to_nchw", _p(src), _DT[src.dtype], Cs, _p(dst), B, C, H, W, act, float(slope), _stream())
     return dst
+
+
+# --------------------------------------------------------------------------------------------- side stream for wgrad
+class WgradOverlap:
+    """Weight gradients are off the backward critical path (BN-backward -> dgrad -> BN-backward ...), and they are
+    tensor/L2-bound while the BatchNorm passes are HBM-bound.  The fused step therefore issues every wgrad on a
+    second stream (a parallel branch of the captured CUDA graph) and joins it before the optimizer.  Tensors the
+    side stream reads are kept alive until the join, so the caching allocator cannot hand their memory out early."""
+    stream: Optional["torch.cuda.Stream"] = None
+    keepalive: list = []
+
+    @classmethod
+    def enable(cls, stream):
+        cls.stream, cls.keepalive = stream, []
+
+    @classmethod
+    def join(cls):
+        if cls.stream is not None:
+            torch.cuda.current_stream().wait_stream(cls.stream)
+        cls.keepalive = []
+
+    @classmethod
+    def disable(cls):
+        cls.join()
+        cls.stream = None
 
 
 # --------------------------------------------------------------------------------------------- weight cache
@@ -268,17 +319,15 @@ class ConvLayerFn(torch.autograd.Function):
                     else (None, None, None)
                 # F.batch_norm semantics: momentum=None means cumulative average - the reference never uses it
                 if groups == 1:
-                    stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
-                    y = scale_shift_act(raw, stats[2], stats[3], act, slope)
+                    y, stats = bn_act_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps,
+                                                act, slope)
                 else:
                     if B % groups:
                         raise RuntimeError(f"batch {B} is not divisible into {groups} sub-batches")
                     rg, y = raw.view(groups, -1, raw.shape[-1]), torch.empty_like(raw)
                     yg = y.view(groups, -1, raw.shape[-1])
-                    per = [bn_train_fwd(rg[i], gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
-                           for i in range(groups)]
-                    for i in range(groups):
-                        scale_shift_act(rg[i], per[i][2], per[i][3], act, slope, out=yg[i])
+                    per = [bn_act_train_fwd(rg[i], gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps, act,
+                                            slope, out=yg[i])[1] for i in range(groups)]
                     stats = torch.stack(per)
             else:
                 stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
@@ -314,13 +363,13 @@ class ConvLayerFn(torch.autograd.Function):
                         dgamma = torch.zeros_like(gamma, dtype=torch.float32)
                         dbeta = torch.zeros_like(beta, dtype=torch.float32)
                 if ctx.groups == 1:
-                    d_raw = bn_act_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
+                    d_raw = bn_act_train_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
                 else:
                     C = raw.shape[-1]
                     d_raw = torch.empty_like(raw)
                     dyg, rg, dg = dy.view(ctx.groups, -1, C), raw.view(ctx.groups, -1, C), d_raw.view(ctx.groups, -1, C)
                     for i in range(ctx.groups):
-                        bn_act_bwd(dyg[i], rg[i], stats[i], act, slope, dgamma, dbeta, out=dg[i])
+                        bn_act_train_bwd(dyg[i], rg[i], stats[i], act, slope, dgamma, dbeta, out=dg[i])
             else:
                 raise _lib.VaeganB200Error("backward through eval-mode BatchNorm is not part of the VAE-GAN step")
         elif act != ACT_NONE:
@@ -336,7 +385,15 @@ class ConvLayerFn(torch.autograd.Function):
             colsum(d_raw, dbias)
         small, big = (d_raw, x) if spec.kind == "down" else (x, d_raw)
         if need_w:
-            dw = conv_wgrad(small, big, g, getattr(weight, "main_grad", None))
+            main_grad = getattr(weight, "main_grad", None)
+            side = WgradOverlap.stream
+            if side is not None and main_grad is not None:
+                side.wait_stream(torch.cuda.current_stream())          # d_raw (and x) are complete
+                with torch.cuda.stream(side):
+                    dw = conv_wgrad(small, big, g, main_grad)
+                WgradOverlap.keepalive.append((small, big))
+            else:
+                dw = conv_wgrad(small, big, g, main_grad)
             dw = dw.view(weight.shape)
         if need_x:
             if x.dtype == torch.bfloat16:

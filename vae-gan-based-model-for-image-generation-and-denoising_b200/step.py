@@ -106,7 +106,7 @@ class VAEGANStep:
     def __init__(self, encoder, decoder, discriminator, *, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  alpha_kl: float = 0.1, alpha_adv: float = 0.1, kl_warmup_epochs: int = 50, sigma_inst: float = 0.05,
                  denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
-                 process_group=None, use_cuda_graph: bool = True, seed: int = 0):
+                 process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True):
         self.E, self.G, self.D = encoder, decoder, discriminator
         self.dtype = encoder._dtype()
         self.dev = next(encoder.parameters()).device
@@ -124,6 +124,7 @@ class VAEGANStep:
         self.opt_D = _FlatAdam(discriminator, lr, betas, eps)
         self.use_graph = use_cuda_graph
         self.seed = seed
+        self.wgrad_stream = torch.cuda.Stream(device=self.dev) if overlap_wgrad else None
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -155,6 +156,14 @@ class VAEGANStep:
 
     # ------------------------------------------------------------------------------------------ the schedule
     def _run(self, gen_noise: bool):
+        if self.wgrad_stream is not None:
+            F_.WgradOverlap.enable(self.wgrad_stream)
+        try:
+            self._run_body(gen_noise)
+        finally:
+            F_.WgradOverlap.disable()
+
+    def _run_body(self, gen_noise: bool):
         s = self._static
         E, G, D = self.E, self.G, self.D
         real, loss = s["real"], s["losses"]
@@ -194,6 +203,7 @@ class VAEGANStep:
             call("vg_bce", _p(p_pair[:B]), B, self.real_label, 1.0, _p(slot), 0, _p(dp[:B]), _stream())
             call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
             torch.autograd.backward([p_pair], [dp])
+            F_.WgradOverlap.join()
             self._allreduce(self.opt_D)
             self.opt_D.step(1.0 / self.world)
             D.invalidate_packed_weights()
@@ -213,6 +223,7 @@ class VAEGANStep:
                 p.requires_grad_(True)
         call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
              _p(loss[5:6]), _stream())
+        F_.WgradOverlap.join()
         self._allreduce(self.opt_E)
         self._allreduce(self.opt_G)
         self.opt_E.step(1.0 / self.world)
