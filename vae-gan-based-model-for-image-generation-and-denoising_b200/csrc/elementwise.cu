@@ -115,7 +115,7 @@ __device__ __forceinline__ float load1(const T* p) {
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const ReduceArgs a) {
     constexpr int V = Vec<T>::N;
     __shared__ float red[kThreads][2 * V + 1];
     __shared__ bool is_last;
@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     const T* x = static_cast<const T*>(a.x);
     const T* dy = static_cast<const T*>(a.dy);
     const int reps = max(1, min(16, kAccDoubles / (2 * a.C)));
-    double* acc = g_acc[a.slot] + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
+    // cross-block totals: fp32 atomics on a float view of the slot (per-block partials are fp32 sums of <= a few
+    // thousand pivoted values; fp64 atomics measured ~10 us slower per launch)
+    float* accf_all = reinterpret_cast<float*>(g_acc[a.slot]);
+    float* acc = accf_all + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
 
     for (int cg = 0; cg < tpr / lanes; ++cg) {
         const int c0 = (cg * lanes + lane) * V;
@@ -151,36 +154,61 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
                 rs[i] = a.rstd[c0 + i];
             }
         }
-        for (long long r = r0 + rsub; r < r1; r += rows_per_iter) {
-            float xv[V];
-            Vec<T>::load(x + r * a.C + c0, xv);
-            if (MODE == 0) {
+        constexpr int U = 1;   // rows in flight per thread: more costs registers -> occupancy -> waves (measured)
+        for (long long r = r0 + rsub; r < r1; r += static_cast<long long>(rows_per_iter) * U) {
+            float xv[U][V], dv[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+                if (rr < r1) {
+                    Vec<T>::load(x + rr * a.C + c0, xv[u]);
+                    if (MODE == 1) Vec<T>::load(dy + rr * a.C + c0, dv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rows_per_iter;
+                if (rr >= r1) continue;
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
-                    const float d = xv[i] - piv[i];
-                    s0[i] += d;
-                    s1[i] = fmaf(d, d, s1[i]);
+                    if (MODE == 0) {
+                        const float d = xv[u][i] - piv[i];
+                        s0[i] += d;
+                        s1[i] = fmaf(d, d, s1[i]);
+                    } else if (MODE == 1) {
+                        const float z = fmaf(xv[u][i], sc[i], sh[i]);
+                        const float dz = dv[u][i] * act_grad(z, a.act, a.slope);
+                        s0[i] += dz;
+                        s1[i] = fmaf(dz, (xv[u][i] - mu[i]) * rs[i], s1[i]);
+                    } else {
+                        s0[i] += xv[u][i];
+                    }
                 }
-            } else if (MODE == 1) {
-                float dv[V];
-                Vec<T>::load(dy + r * a.C + c0, dv);
-#pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const float z = fmaf(xv[i], sc[i], sh[i]);
-                    const float dz = dv[i] * act_grad(z, a.act, a.slope);
-                    s0[i] += dz;
-                    s1[i] = fmaf(dz, (xv[i] - mu[i]) * rs[i], s1[i]);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < V; ++i) s0[i] += xv[i];
             }
         }
+        // combine the row sub-groups: inside a warp by shuffles (when a row is narrower than a warp), then across the
+        // (at most 8) warps / row groups through shared memory
+        if (lanes < 32) {
+            for (int o = lanes; o < 32; o <<= 1) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) { red[threadIdx.x][i] = s0[i]; red[threadIdx.x][V + i] = s1[i]; }
+                for (int i = 0; i < V; ++i) {
+                    s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
+                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+                }
+            }
+        }
+        const int groups = lanes < 32 ? kThreads / 32 : rows_per_iter;     // partial sums left per channel vector
+        const int gidx = lanes < 32 ? (threadIdx.x >> 5) : rsub;
+        const bool writer = lanes < 32 ? ((threadIdx.x & 31) < lanes) : true;
+        if (writer) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { red[gidx * lanes + lane][i] = s0[i]; red[gidx * lanes + lane][V + i] = s1[i]; }
+        }
         __syncthreads();
-        if (rsub == 0) {
-            for (int j = 1; j < rows_per_iter; ++j)
+        if (threadIdx.x < lanes) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { s0[i] = red[lane][i]; s1[i] = red[lane][V + i]; }
+            for (int j = 1; j < groups; ++j)
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     s0[i] += red[j * lanes + lane][i];
@@ -188,8 +216,8 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
                 }
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                atomicAdd(acc + c0 + i, static_cast<double>(s0[i]));
-                if (MODE != 2) atomicAdd(acc + a.C + c0 + i, static_cast<double>(s1[i]));
+                atomicAdd(acc + c0 + i, s0[i]);
+                if (MODE != 2) atomicAdd(acc + a.C + c0 + i, s1[i]);
             }
         }
         __syncthreads();
@@ -202,16 +230,29 @@ __global__ void __launch_bounds__(kThreads) channel_reduce_kernel(const ReduceAr
     if (!is_last) return;
     __threadfence();
     const double n = static_cast<double>(a.rows);
-    double* all = g_acc[a.slot];
+    float* all = accf_all;
     for (int c = threadIdx.x; c < a.C; c += kThreads) {
+        // all replica loads are issued before the first store: interleaving them with the re-zeroing stores would
+        // serialise 2*reps dependent L2 round trips (~20 us), which used to be the floor of every reduction launch
+        float v0[16], v1[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            v0[r] = v1[r] = 0.f;
+            if (r < reps) {
+                const float* base = all + static_cast<long long>(r) * 2 * a.C;
+                v0[r] = __ldcg(base + c);
+                if (MODE != 2) v1[r] = __ldcg(base + a.C + c);
+            }
+        }
         double s = 0.0, ss = 0.0;
-        for (int r = 0; r < reps; ++r) {
-            double* base = all + static_cast<long long>(r) * 2 * a.C;
-            s += __ldcg(base + c);
-            base[c] = 0.0;
-            if (MODE != 2) {
-                ss += __ldcg(base + a.C + c);
-                base[a.C + c] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { s += static_cast<double>(v0[r]); ss += static_cast<double>(v1[r]); }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (r < reps) {
+                float* base = all + static_cast<long long>(r) * 2 * a.C;
+                base[c] = 0.f;
+                if (MODE != 2) base[a.C + c] = 0.f;
             }
         }
         if (MODE == 0) {
@@ -470,9 +511,12 @@ struct ReducePlan {
     int blocks;
     long long rows_per_block;
 };
-ReducePlan plan_reduce(long long rows) {
+// `rows_per_iter` = rows one block covers per loop iteration (256 threads / vectors per row): small tensors get many
+// short blocks (2 rows per thread) so that the pass is not bound by a few threads' dependent load chains.
+ReducePlan plan_reduce(long long rows, int rows_per_iter = 16) {
     ReducePlan p;
-    p.blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(kMaxBlocks, (rows + 31) / 32)));
+    const long long per_block = static_cast<long long>(std::max(1, rows_per_iter)) * 2;
+    p.blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(kMaxBlocks, (rows + per_block - 1) / per_block)));
     p.rows_per_block = (rows + p.blocks - 1) / p.blocks;
     p.blocks = static_cast<int>((rows + p.rows_per_block - 1) / p.rows_per_block);
     return p;
@@ -572,6 +616,9 @@ __global__ void __launch_bounds__(kThreads) scale_shift_act_kernel(const TI* __r
     }
 }
 
+// The two apply passes are launched with a thread count that is a multiple of the vectors per row, so every
+// thread keeps ONE channel group for its whole grid-stride loop: per-channel parameters are loaded once into
+// registers, and 4 independent 16-byte loads are in flight per tensor.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) scale_shift_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                       long long nvec, int C,
@@ -579,17 +626,28 @@ __global__ void __launch_bounds__(kThreads) scale_shift_act_vec_kernel(const T* 
                                                                       const float* __restrict__ shift, int act,
                                                                       float slope) {
     constexpr int V = Vec<T>::N;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>((i * V) % C);
-        float v[V];
-        Vec<T>::load(x + i * V, v);
+    constexpr int U = 4;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c0 = static_cast<int>((tid * V) % C);
+    float sc[V], sh[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const float z = fmaf(v[j], scale ? __ldg(scale + c0 + j) : 1.f, shift ? __ldg(shift + c0 + j) : 0.f);
-            v[j] = act_fwd(z, act, slope);
+    for (int j = 0; j < V; ++j) {
+        sc[j] = scale ? __ldg(scale + c0 + j) : 1.f;
+        sh[j] = shift ? __ldg(shift + c0 + j) : 0.f;
+    }
+    for (long long i = tid; i < nvec; i += stride * U) {
+        float v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) Vec<T>::load(x + (i + u * stride) * V, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) continue;
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+            Vec<T>::store(y + (i + u * stride) * V, v[u]);
         }
-        Vec<T>::store(y + i * V, v);
     }
 }
 
@@ -603,22 +661,40 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_apply_kernel(const T* __r
                                                                    const float* __restrict__ c1,
                                                                    const float* __restrict__ c2, int act, float slope) {
     constexpr int V = Vec<T>::N;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>((i * V) % C);
-        float xv[V], dv[V];
-        Vec<T>::load(x + i * V, xv);
-        Vec<T>::load(dy + i * V, dv);
+    constexpr int U = 4;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c0 = static_cast<int>((tid * V) % C);
+    // dx = scale*(dz - c1 - xhat*c2) = scale*dz + kx*x + k0   with xhat = (x - mean)*rstd
+    float sc[V], sh[V], kx[V], k0[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const int c = c0 + j;
-            const float sc = __ldg(scale + c);
-            const float z = fmaf(xv[j], sc, __ldg(shift + c));
-            const float dz = dv[j] * act_grad(z, act, slope);
-            const float xhat = (xv[j] - __ldg(mean + c)) * __ldg(rstd + c);
-            dv[j] = sc * (dz - __ldg(c1 + c) - xhat * __ldg(c2 + c));
+    for (int j = 0; j < V; ++j) {
+        const int c = c0 + j;
+        sc[j] = __ldg(scale + c);
+        sh[j] = __ldg(shift + c);
+        const float t = sc[j] * __ldg(c2 + c) * __ldg(rstd + c);
+        kx[j] = -t;
+        k0[j] = t * __ldg(mean + c) - sc[j] * __ldg(c1 + c);
+    }
+    for (long long i = tid; i < nvec; i += stride * U) {
+        float xv[U][V], dv[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) {
+                Vec<T>::load(x + (i + u * stride) * V, xv[u]);
+                Vec<T>::load(dy + (i + u * stride) * V, dv[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) continue;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float z = fmaf(xv[u][j], sc[j], sh[j]);
+                const float dz = dv[u][j] * act_grad(z, act, slope);
+                dv[u][j] = fmaf(sc[j], dz, fmaf(kx[j], xv[u][j], k0[j]));
+            }
+            Vec<T>::store(dx + (i + u * stride) * V, dv[u]);
         }
-        Vec<T>::store(dx + i * V, dv);
     }
 }
 
@@ -712,6 +788,14 @@ int grid_for(long long n) {
     return static_cast<int>(std::max<long long>(1, std::min<long long>(148 * 8, (n + kThreads - 1) / kThreads)));
 }
 
+// Grid for the channel-affine apply kernels: ~nvec/4 threads, total thread count a multiple of `vec_per_row`.
+int grid_affine(long long nvec, int vec_per_row) {
+    long long blocks = std::max<long long>(1, std::min<long long>(148 * 8, (nvec / 4 + kThreads - 1) / kThreads));
+    const int mult = std::max(1, vec_per_row / kThreads);          // vec_per_row is a power of two
+    blocks = (blocks + mult - 1) / mult * mult;
+    return static_cast<int>(blocks);
+}
+
 }  // namespace
 }  // namespace vg
 
@@ -736,7 +820,7 @@ extern "C" int vg_bn_train_fwd(const void* x, VgDType dt, long long rows, int C,
     rc = check_channels(dt, C);
     if (rc != VG_OK) return rc;
     if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
-    const ReducePlan p = plan_reduce(rows);
+    const ReducePlan p = plan_reduce(rows, std::max(1, kThreads / (C / (dt == VG_BF16 ? 8 : 4))));
     ReduceArgs a{};
     a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block;
     a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
@@ -764,13 +848,13 @@ extern "C" int vg_scale_shift_act(const void* x, VgDType in_dt, long long rows, 
     const long long n = rows * C;
     cudaStream_t st = as_stream(stream);
     const int V = in_dt == VG_BF16 ? 8 : 4;
-    if (in_dt == out_dt && C % V == 0) {
+    if (in_dt == out_dt && C % V == 0 && is_pow2(C / V)) {
         const long long nvec = n / V;
         if (in_dt == VG_BF16)
-            scale_shift_act_vec_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, st>>>(
+            scale_shift_act_vec_kernel<__nv_bfloat16><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
                 static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, scale, shift, act, slope);
         else
-            scale_shift_act_vec_kernel<float><<<grid_for(nvec), kThreads, 0, st>>>(
+            scale_shift_act_vec_kernel<float><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
                 static_cast<const float*>(x), static_cast<float*>(y), nvec, C, scale, shift, act, slope);
     } else if (in_dt == VG_BF16 && out_dt == VG_BF16) {
         scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n), kThreads, 0, st>>>(
@@ -799,7 +883,7 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
         return fail(VG_ERR_ARG, "bn_act_bwd: null pointer");
     rc = check_channels(dt, C);
     if (rc != VG_OK) return rc;
-    const ReducePlan p = plan_reduce(rows);
+    const ReducePlan p = plan_reduce(rows, std::max(1, kThreads / (C / (dt == VG_BF16 ? 8 : 4))));
     const size_t need = 2 * static_cast<size_t>(C) * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return fail(VG_ERR_WORKSPACE, "bn_act_bwd: workspace too small");
     float* c1 = ws;
@@ -814,11 +898,11 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     const int V = dt == VG_BF16 ? 8 : 4;
     const long long nvec = rows * C / V;
     if (dt == VG_BF16)
-        bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_for(nvec), kThreads, 0, st>>>(
+        bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
             static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
             static_cast<__nv_bfloat16*>(dx), nvec, C, scale, shift, mean, rstd, c1, c2, act, slope);
     else
-        bn_act_bwd_apply_kernel<float><<<grid_for(nvec), kThreads, 0, st>>>(
+        bn_act_bwd_apply_kernel<float><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
             static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
             mean, rstd, c1, c2, act, slope);
     VG_LAUNCHED();
@@ -877,7 +961,7 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
     (void)ws;
     (void)ws_bytes;
     if (C > kMaxChannels) return fail(VG_ERR_SHAPE, "colsum: more than %d channels", kMaxChannels);
-    const ReducePlan p = plan_reduce(rows);
+    const ReducePlan p = plan_reduce(rows, std::max(1, kThreads / (C / (dt == VG_BF16 ? 8 : 4))));
     ReduceArgs a{};
     a.x = x; a.rows = rows; a.C = C; a.rows_per_block = p.rows_per_block; a.colsum_out = out;
     return launch_reduce<2>(dt, a, p.blocks, as_stream(stream));

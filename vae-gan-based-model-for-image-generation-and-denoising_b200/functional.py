@@ -137,7 +137,9 @@ def bn_train_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, num_ba
 
 def bn_act_train_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, num_batches_tracked, momentum: float,
                      eps: float, act: int, slope: float, out=None):
-    """Fused training BatchNorm + activation (one cooperative launch).  Returns (y, stats[4, C])."""
+    """Fused training BatchNorm + activation (one cooperative launch).  Returns (y, stats[4, C]).
+    Measured slower than the two-kernel path at the VAE-GAN's sizes (round 1: 63 vs 32 us average forward, 113 vs 65
+    backward - few co-resident blocks, long per-thread chains), so ConvLayerFn does not use it yet."""
     C = x.shape[-1]
     rows = x.numel() // C
     stats = torch.empty((4, C), dtype=torch.float32, device=x.device)
@@ -319,15 +321,17 @@ class ConvLayerFn(torch.autograd.Function):
                     else (None, None, None)
                 # F.batch_norm semantics: momentum=None means cumulative average - the reference never uses it
                 if groups == 1:
-                    y, stats = bn_act_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps,
-                                                act, slope)
+                    stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+                    y = scale_shift_act(raw, stats[2], stats[3], act, slope)
                 else:
                     if B % groups:
                         raise RuntimeError(f"batch {B} is not divisible into {groups} sub-batches")
                     rg, y = raw.view(groups, -1, raw.shape[-1]), torch.empty_like(raw)
                     yg = y.view(groups, -1, raw.shape[-1])
-                    per = [bn_act_train_fwd(rg[i], gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps, act,
-                                            slope, out=yg[i])[1] for i in range(groups)]
+                    per = [bn_train_fwd(rg[i], gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
+                           for i in range(groups)]
+                    for i in range(groups):
+                        scale_shift_act(rg[i], per[i][2], per[i][3], act, slope, out=yg[i])
                     stats = torch.stack(per)
             else:
                 stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
@@ -363,13 +367,13 @@ class ConvLayerFn(torch.autograd.Function):
                         dgamma = torch.zeros_like(gamma, dtype=torch.float32)
                         dbeta = torch.zeros_like(beta, dtype=torch.float32)
                 if ctx.groups == 1:
-                    d_raw = bn_act_train_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
+                    d_raw = bn_act_bwd(dy, raw, stats, act, slope, dgamma, dbeta)
                 else:
                     C = raw.shape[-1]
                     d_raw = torch.empty_like(raw)
                     dyg, rg, dg = dy.view(ctx.groups, -1, C), raw.view(ctx.groups, -1, C), d_raw.view(ctx.groups, -1, C)
                     for i in range(ctx.groups):
-                        bn_act_train_bwd(dyg[i], rg[i], stats[i], act, slope, dgamma, dbeta, out=dg[i])
+                        bn_act_bwd(dyg[i], rg[i], stats[i], act, slope, dgamma, dbeta, out=dg[i])
             else:
                 raise _lib.VaeganB200Error("backward through eval-mode BatchNorm is not part of the VAE-GAN step")
         elif act != ACT_NONE:
