@@ -75,6 +75,14 @@ long long vg_launch_count(void);
  * Either output may be NULL.  Replaces the implicit weight reads of nn.Conv2d / nn.ConvTranspose2d
  * (main_vae.py:23, gan_code.py:21-49, 61-84). */
 int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* wd, void* wu, void* stream);
+/* The same for many layers in ONE launch (items is a host array; used after every optimizer step). */
+typedef struct VgPackItem {
+    const float* w;
+    void* wd;
+    void* wu;
+    int32_t small_c, big_c, big_c_valid, kk; /* kk = kernel * kernel */
+} VgPackItem;
+int vg_pack_weights_multi(const VgPackItem* items, int n_items, void* stream);
 
 /* ---- convolution contractions -------------------------------------------------------------------------------
  * dtype selects the arithmetic path: VG_BF16 = TMA-fed tcgen05/TMEM implicit GEMM (bf16 operands, fp32

@@ -24,6 +24,11 @@ class VgConvGeom(Structure):
                 ("kernel", c_int32), ("stride", c_int32), ("pad", c_int32), ("big_c_valid", c_int32)]
 
 
+class VgPackItem(Structure):
+    _fields_ = [("w", c_void_p), ("wd", c_void_p), ("wu", c_void_p), ("small_c", c_int32), ("big_c", c_int32),
+                ("big_c_valid", c_int32), ("kk", c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
 _G = POINTER(VgConvGeom)
 _P = c_void_p
@@ -33,6 +38,7 @@ PROTOTYPES = {
     "vg_device_check": (c_int, []),
     "vg_launch_count": (c_longlong, []),
     "vg_pack_weights_bf16": (c_int, [_G, _P, _P, _P, _P]),
+    "vg_pack_weights_multi": (c_int, [POINTER(VgPackItem), c_int, _P]),
     "vg_conv_down_workspace_bytes": (c_size_t, [_G]),
     "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),

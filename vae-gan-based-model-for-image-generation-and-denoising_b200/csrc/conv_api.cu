@@ -377,9 +377,53 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     }
 }
 
+struct PackBatch {
+    VgPackItem item[16];
+    int n;
+};
+
+// blockIdx.y = layer; same mapping as pack_weights_kernel
+__global__ void pack_weights_multi_kernel(const PackBatch b) {
+    const VgPackItem it = b.item[blockIdx.y];
+    const int sc = it.small_c, bc = it.big_c, bcv = it.big_c_valid > 0 ? it.big_c_valid : it.big_c, kk = it.kk;
+    const long long n = static_cast<long long>(sc) * bc * kk;
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(it.wd);
+    __nv_bfloat16* wu = static_cast<__nv_bfloat16*>(it.wu);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int bi = static_cast<int>(i % bc);
+        const int s = static_cast<int>((i / bc) % sc);
+        const int tap = static_cast<int>(i / (static_cast<long long>(bc) * sc));
+        const float v = bi < bcv ? it.w[(static_cast<long long>(s) * bcv + bi) * kk + tap] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        if (wd != nullptr) wd[i] = h;
+        if (wu != nullptr) wu[(static_cast<long long>(tap) * bc + bi) * sc + s] = h;
+    }
+}
+
 }  // namespace vg
 
 using namespace vg;
+
+extern "C" int vg_pack_weights_multi(const VgPackItem* items, int n_items, void* stream) {
+    if (items == nullptr || n_items <= 0) return fail(VG_ERR_ARG, "pack_multi: no items");
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    for (int base = 0; base < n_items; base += 16) {
+        PackBatch b;
+        b.n = std::min(16, n_items - base);
+        long long biggest = 0;
+        for (int i = 0; i < b.n; ++i) {
+            b.item[i] = items[base + i];
+            if (b.item[i].w == nullptr) return fail(VG_ERR_ARG, "pack_multi: null master weight");
+            biggest = std::max(biggest, static_cast<long long>(b.item[i].small_c) * b.item[i].big_c * b.item[i].kk);
+        }
+        const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((biggest + 255) / 256, 148 * 4)));
+        pack_weights_multi_kernel<<<dim3(blocks, b.n), 256, 0, as_stream(stream)>>>(b);
+        VG_LAUNCHED();
+    }
+    return VG_OK;
+}
 
 extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* wd, void* wu, void* stream) {
     if (g == nullptr || w == nullptr) return fail(VG_ERR_ARG, "pack: null argument");

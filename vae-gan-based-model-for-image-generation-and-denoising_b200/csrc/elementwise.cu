@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -128,10 +129,11 @@ __global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const Reduc
     const T* x = static_cast<const T*>(a.x);
     const T* dy = static_cast<const T*>(a.dy);
     const int reps = max(1, min(16, kAccDoubles / (2 * a.C)));
-    // cross-block totals: fp32 atomics on a float view of the slot (per-block partials are fp32 sums of <= a few
-    // thousand pivoted values; fp64 atomics measured ~10 us slower per launch)
-    float* accf_all = reinterpret_cast<float*>(g_acc[a.slot]);
-    float* acc = accf_all + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
+    // cross-block totals: the bf16 mode adds fp32 partials with fp32 atomics on a float view of the slot; the fp32
+    // (reference-accurate) mode keeps fp64 atomics
+    using AccT = typename std::conditional<sizeof(T) == 4, double, float>::type;
+    AccT* accf_all = reinterpret_cast<AccT*>(g_acc[a.slot]);
+    AccT* acc = accf_all + static_cast<long long>(blockIdx.x % reps) * 2 * a.C;
 
     for (int cg = 0; cg < tpr / lanes; ++cg) {
         const int c0 = (cg * lanes + lane) * V;
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const Reduc
                 }
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                atomicAdd(acc + c0 + i, s0[i]);
-                if (MODE != 2) atomicAdd(acc + a.C + c0 + i, s1[i]);
+                atomicAdd(acc + c0 + i, static_cast<AccT>(s0[i]));
+                if (MODE != 2) atomicAdd(acc + a.C + c0 + i, static_cast<AccT>(s1[i]));
             }
         }
         __syncthreads();
@@ -230,16 +232,16 @@ __global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const Reduc
     if (!is_last) return;
     __threadfence();
     const double n = static_cast<double>(a.rows);
-    float* all = accf_all;
+    AccT* all = accf_all;
     for (int c = threadIdx.x; c < a.C; c += kThreads) {
         // all replica loads are issued before the first store: interleaving them with the re-zeroing stores would
         // serialise 2*reps dependent L2 round trips (~20 us), which used to be the floor of every reduction launch
-        float v0[16], v1[16];
+        AccT v0[16], v1[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            v0[r] = v1[r] = 0.f;
+            v0[r] = v1[r] = 0;
             if (r < reps) {
-                const float* base = all + static_cast<long long>(r) * 2 * a.C;
+                const AccT* base = all + static_cast<long long>(r) * 2 * a.C;
                 v0[r] = __ldcg(base + c);
                 if (MODE != 2) v1[r] = __ldcg(base + a.C + c);
             }
@@ -250,9 +252,9 @@ __global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const Reduc
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             if (r < reps) {
-                float* base = all + static_cast<long long>(r) * 2 * a.C;
-                base[c] = 0.f;
-                if (MODE != 2) base[a.C + c] = 0.f;
+                AccT* base = all + static_cast<long long>(r) * 2 * a.C;
+                base[c] = 0;
+                if (MODE != 2) base[a.C + c] = 0;
             }
         }
         if (MODE == 0) {

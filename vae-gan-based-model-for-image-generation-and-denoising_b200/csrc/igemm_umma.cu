@@ -442,20 +442,20 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
 }
 
 // dw[m][n][tap] += sum over splits of partial[cta(split, mn, group)][tap_local][row][col]
-// VEC = 4: one thread owns the 4 consecutive taps dw[m][n][4t..4t+3] (one float4 read-add-write); VEC = 1: one tap.
-// WARP = true: one warp per output unit, lanes stride over the splits (few outputs, many splits);
-// WARP = false: one thread per output unit (many outputs, few splits).
-template <int VEC, bool WARP>
+// VEC = 4: one thread owns the 4 consecutive taps dw[m][n][4t..4t+3]; VEC = 1: one tap.
+// One thread per output unit, n fastest (coalesced partial reads).  When there are few outputs but many splits the
+// split range is cut into gridDim.y chunks whose sums are combined with fp32 atomics (CHUNKED = true).
+template <int VEC, bool CHUNKED>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) {
     const int tap_units = p.num_taps / VEC;
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * tap_units;
     const int rows_per_tile = p.m_atoms * p.p_atom_c;
     const long long plane = static_cast<long long>(128) * p.n_tile;
     const long long cta_stride = static_cast<long long>(p.taps_per_cta) * plane;
-    const int lane = threadIdx.x & 31;
-    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = WARP ? tid / 32 : tid; i < total; i += WARP ? nthr / 32 : nthr) {
+    const int s_begin = CHUNKED ? static_cast<int>(static_cast<long long>(p.splits) * blockIdx.y / gridDim.y) : 0;
+    const int s_end = CHUNKED ? static_cast<int>(static_cast<long long>(p.splits) * (blockIdx.y + 1) / gridDim.y) : p.splits;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
         // i enumerates (m, tap unit, n) with n fastest so that the partial reads are coalesced
         const int n = static_cast<int>(i % p.n_valid);
         const long long r = i / p.n_valid;
@@ -470,20 +470,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) 
         float acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        for (int s = WARP ? lane : 0; s < p.splits; s += WARP ? 32 : 1) {
+        for (int s = s_begin; s < s_end; ++s) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] += __ldcs(src + s * cta_stride + v * plane);
         }
-        if (WARP) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
-            if (lane != 0) continue;
-        }
         float* dst = p.dw + static_cast<long long>(m) * p.s_m + static_cast<long long>(n) * p.s_n +
                      static_cast<long long>(tap) * p.s_tap;
-        if (VEC == 4) {
+        if (CHUNKED) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) atomicAdd(dst + v, acc[v]);
+        } else if (VEC == 4) {
             float4 o = *reinterpret_cast<float4*>(dst);
             o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
             *reinterpret_cast<float4*>(dst) = o;
@@ -554,15 +550,15 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.splits <= 1) return static_cast<int>(e);
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * p.num_taps / (p.vec4_taps ? 4 : 1);
-    const bool warp = p.splits >= 16 && total <= 32768;   // few outputs, many splits: lanes stride over the splits
-    const long long threads = warp ? total * 32 : total;
-    const int blocks = static_cast<int>(std::min<long long>((threads + 255) / 256, 148 * 16));
+    const bool chunked = p.splits >= 16 && total <= 32768;   // few outputs, many splits
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+    const dim3 rgrid(blocks, chunked ? std::min(p.splits / 4, 32) : 1);
     if (p.vec4_taps) {
-        if (warp) wgrad_reduce_kernel<4, true><<<blocks, 256, 0, stream>>>(p);
-        else wgrad_reduce_kernel<4, false><<<blocks, 256, 0, stream>>>(p);
+        if (chunked) wgrad_reduce_kernel<4, true><<<rgrid, 256, 0, stream>>>(p);
+        else wgrad_reduce_kernel<4, false><<<rgrid, 256, 0, stream>>>(p);
     } else {
-        if (warp) wgrad_reduce_kernel<1, true><<<blocks, 256, 0, stream>>>(p);
-        else wgrad_reduce_kernel<1, false><<<blocks, 256, 0, stream>>>(p);
+        if (chunked) wgrad_reduce_kernel<1, true><<<rgrid, 256, 0, stream>>>(p);
+        else wgrad_reduce_kernel<1, false><<<rgrid, 256, 0, stream>>>(p);
     }
     return static_cast<int>(cudaGetLastError());
 }

@@ -265,12 +265,35 @@ class PackedWeights:
     def invalidate(self):
         self.version = None
 
+    def stage(self, w: torch.Tensor, small_c: int, big_c: int, kernel: int):
+        """Make sure persistent wd / wu buffers of the right shape exist and mark them current for `w` (the caller
+        is about to fill them through vg_pack_weights_multi)."""
+        kk = kernel * kernel
+        if self.wd is None or self.wd.shape != (kk, small_c, big_c) or self.wd.device != w.device:
+            self.wd = torch.empty((kk, small_c, big_c), dtype=torch.bfloat16, device=w.device)
+            self.wu = torch.empty((kk, big_c, small_c), dtype=torch.bfloat16, device=w.device)
+        self.version, self.key = w._version, (w.data_ptr(), small_c, big_c, kernel)
+
     def get(self, w: torch.Tensor, g: VgConvGeom):
         key = (w.data_ptr(), g.small_c, g.big_c, g.kernel)
         if self.version != w._version or self.key != key:
             self.wd, self.wu = pack_weights(w.detach(), g)
             self.version, self.key = w._version, key
         return self.wd, self.wu
+
+
+def pack_layers(layers, dtype) -> None:
+    """Refresh the bf16 copies of every layer in `layers` (objects with .spec, .conv, .cache) with ONE launch."""
+    if dtype != torch.bfloat16 or not layers:
+        return
+    items = (_lib.VgPackItem * len(layers))()
+    for i, layer in enumerate(layers):
+        sp, w = layer.spec, layer.conv.weight
+        bc = padded_channels(sp.big_c, dtype)
+        layer.cache.stage(w, sp.small_c, bc, sp.kernel)
+        items[i] = _lib.VgPackItem(w.data_ptr(), layer.cache.wd.data_ptr(), layer.cache.wu.data_ptr(), sp.small_c, bc,
+                                   sp.big_c if bc != sp.big_c else 0, sp.kernel * sp.kernel)
+    call("vg_pack_weights_multi", items, len(layers), _stream())
 
 
 # --------------------------------------------------------------------------------------------- autograd glue

@@ -101,6 +101,11 @@ class _KernelModule(nn.Module):
     def _dtype(self):
         return F_.PRECISION_DTYPE[self.precision]
 
+    def repack_weights(self) -> None:
+        """Refresh every layer's packed bf16 weights from the fp32 masters in one launch (fused step: after its
+        own Adam kernel, which updates the masters without touching autograd's version counters)."""
+        F_.pack_layers(self._layers(), self._dtype())
+
     def invalidate_packed_weights(self) -> None:
         """Force a re-pack of the bf16 weight copies (needed after the masters were changed behind autograd's back)."""
         for layer in self._layers():

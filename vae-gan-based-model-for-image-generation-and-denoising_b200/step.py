@@ -168,8 +168,8 @@ class VAEGANStep:
         E, G, D = self.E, self.G, self.D
         real, loss = s["real"], s["losses"]
         B = real.shape[0]
-        for net in (E, G, D):          # every replay starts from freshly packed bf16 weights
-            net.invalidate_packed_weights()
+        for net in (E, G, D):          # every replay starts from freshly packed bf16 weights (one launch per net)
+            net.repack_weights()
         if gen_noise:                  # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
             self._randn_into(s["eps"], 1)
             self._randn_into(s["n_real"], 2)
@@ -206,7 +206,7 @@ class VAEGANStep:
             F_.WgradOverlap.join()
             self._allreduce(self.opt_D)
             self.opt_D.step(1.0 / self.world)
-            D.invalidate_packed_weights()
+            D.repack_weights()
 
         # ---- generator / encoder update                                               (:110-135)
         self.opt_E.zero_grad()
