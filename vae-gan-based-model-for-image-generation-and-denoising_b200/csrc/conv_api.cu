@@ -45,8 +45,10 @@ static int pick_tps(int kchunk, int c_chunks, int taps) {
     return 1;
 }
 
-static int pick_stages(int stage_bytes, int n_tile) {
-    // two CTAs per SM when the accumulator is narrow (epilogue of one overlaps the main loop of the other)
+static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30) {
+    // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question:
+    // narrow accumulators leave room for two CTAs per SM (110 KB each), wide ones take the whole SM.
+    (void)iters;
     const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048;
     return std::max(2, std::min(8, budget / stage_bytes));
 }
@@ -140,10 +142,13 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
                                  p.tw, p.th, p.tb, swz);
         if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(A view %d) failed (%d)", v, rc);
     }
+    p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
+    // taps are enumerated in packed order, so with a single N tile the tps slabs of a stage are adjacent rows
+    p.b_merged = p.tps > 1 && p.n_tiles == 1 && p.tps * p.n_tile <= 256;
     {
         const uint64_t dims[2] = {(uint64_t)g->big_c, (uint64_t)k * k * g->small_c};
         const uint64_t strides[2] = {1, (uint64_t)g->big_c};
-        const uint32_t box[2] = {(uint32_t)p.kchunk, (uint32_t)p.n_tile};
+        const uint32_t box[2] = {(uint32_t)p.kchunk, (uint32_t)(p.b_merged ? p.tps * p.n_tile : p.n_tile)};
         const int rc = make_tmap_bf16(&p.bmap, wd, 2, dims, strides, box, swz);
         if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(B) failed (%d)", rc);
     }
@@ -158,7 +163,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
             t.brow = (ky * k + kx) * g->small_c;
         }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks);
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -264,7 +269,7 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.osy = p.osx = s;
     }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks);
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();

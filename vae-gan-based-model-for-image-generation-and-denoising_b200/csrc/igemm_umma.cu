@@ -26,6 +26,9 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 // fprop-type kernel: A = activation views (K-major), B = packed weights (K-major), D -> NHWC output
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
+    // Persistent: each CTA walks work items (M tile, N tile, phase, K slice) with stride gridDim.x.  The smem ring
+    // runs continuously across items and the accumulator is double-buffered in TMEM, so the epilogue of item i
+    // overlaps the loads and MMAs of item i+1 and the per-CTA prologue (TMEM alloc, barrier init) is paid once.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -40,24 +43,15 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     uint8_t* sB = smem + stages * a_stage;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
     uint64_t* empty = full + kMaxStages;
-    uint64_t* tmem_full = empty + kMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + kMaxStages;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    int tile = blockIdx.x;
-    const int tile_w = tile % p.tiles_w;
-    tile /= p.tiles_w;
-    const int tile_h = tile % p.tiles_h;
-    const int tile_b = tile / p.tiles_h;
-    const int i0 = tile_h * p.th, j0 = tile_w * p.tw, b0 = tile_b * p.tb;
-    const int n0 = blockIdx.y * p.n_tile;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
-    const int phase = blockIdx.z / ksplit, kslice = blockIdx.z % ksplit;
-    const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int total_items = m_tiles * p.n_tiles * p.num_phases * ksplit;
     const int total_iters = p.taps_per_phase / tps * p.c_chunks;
-    const int it_begin = static_cast<int>(static_cast<long long>(total_iters) * kslice / ksplit);
-    const int it_end = static_cast<int>(static_cast<long long>(total_iters) * (kslice + 1) / ksplit);
-    const int iters = it_end - it_begin;
-    const uint32_t ncols = tmem_cols_for(p.n_tile);
+    const uint32_t ncols = tmem_cols_for(2 * p.n_tile);
 
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.amap[v]);
@@ -66,7 +60,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -78,22 +75,47 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // item -> coordinates (m fastest: consecutive CTAs share the same weight tile)
+    auto decode = [&](int item, int& i0, int& j0, int& b0, int& n0, int& phase, int& it_begin, int& iters) {
+        int t = item % m_tiles;
+        int r = item / m_tiles;
+        const int n_idx = r % p.n_tiles;
+        const int z = r / p.n_tiles;
+        j0 = (t % p.tiles_w) * p.tw;
+        t /= p.tiles_w;
+        i0 = (t % p.tiles_h) * p.th;
+        b0 = (t / p.tiles_h) * p.tb;
+        n0 = n_idx * p.n_tile;
+        phase = z / ksplit;
+        const int kslice = z % ksplit;
+        it_begin = static_cast<int>(static_cast<long long>(total_iters) * kslice / ksplit);
+        iters = static_cast<int>(static_cast<long long>(total_iters) * (kslice + 1) / ksplit) - it_begin;
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
             int s = 0;
             uint32_t par = 0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(&empty[s], par ^ 1);
-                mbar_expect_tx(&full[s], a_stage + b_stage);
-                for (int t = 0; t < tps; ++t) {
-                    const IgemmTap tap = taps[tap_i + t];
-                    tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk, j0 + tap.dx,
-                                i0 + tap.dy, b0);
-                    tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                int i0, j0, b0, n0, phase, it_begin, iters;
+                decode(item, i0, j0, b0, n0, phase, it_begin, iters);
+                const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
+                int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&empty[s], par ^ 1);
+                    mbar_expect_tx(&full[s], a_stage + b_stage);
+                    for (int t = 0; t < tps; ++t) {
+                        const IgemmTap tap = taps[tap_i + t];
+                        tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
+                                    j0 + tap.dx, i0 + tap.dy, b0);
+                        if (!p.b_merged)
+                            tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+                    }
+                    if (p.b_merged)
+                        tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, taps[tap_i].brow + n0);
+                    if (++c == p.c_chunks) { c = 0; tap_i += tps; }
+                    if (++s == stages) { s = 0; par ^= 1; }
                 }
-                if (++c == p.c_chunks) { c = 0; tap_i += tps; }
-                if (++s == stages) { s = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -108,29 +130,38 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
             const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
             const uint32_t a_step = a_stage >> 4, b_step = b_stage >> 4;
+            const uint32_t a_t = a_sub >> 4, b_t = b_sub >> 4;
             int s = 0;
             uint32_t par = 0, a_lo = a_lo0, b_lo = b_lo0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(&full[s], par);
+            int li = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+                int i0, j0, b0, n0, phase, it_begin, iters;
+                decode(item, i0, j0, b0, n0, phase, it_begin, iters);
+                const int acc = li & 1;
+                mbar_wait(&tmem_empty[acc], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
-                if (ksteps == 4) {
-                    umma_bf16_lohi(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
-                    umma_bf16_lohi(tmem_base, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                    umma_bf16_lohi(tmem_base, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                    umma_bf16_lohi(tmem_base, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
-                } else {
-                    const uint32_t a_t = a_sub >> 4, b_t = b_sub >> 4;
-                    for (int t = 0; t < tps; ++t)
-                        for (int k = 0; k < ksteps; ++k)
-                            umma_bf16_lohi(tmem_base, a_lo + t * a_t + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi, idesc,
-                                           (it | t | k) != 0);
+                const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&full[s], par);
+                    tc_fence_after();
+                    if (ksteps == 4) {
+                        umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
+                        umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                        umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                        umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                    } else {
+                        for (int t = 0; t < tps; ++t)
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_bf16_lohi(d_tmem, a_lo + t * a_t + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi, idesc,
+                                               (it | t | k) != 0);
+                    }
+                    umma_commit(&empty[s]);
+                    a_lo += a_step;
+                    b_lo += b_step;
+                    if (++s == stages) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
                 }
-                umma_commit(&empty[s]);
-                a_lo += a_step;
-                b_lo += b_step;
-                if (++s == stages) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+                umma_commit(&tmem_full[acc]);   // (with zero iterations this arrives immediately)
             }
-            umma_commit(tmem_full);   // (with zero iterations this arrives immediately: nothing is pending)
         }
     } else {
         const int q = warp & 3;
@@ -138,60 +169,70 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         const int w_l = row % p.tw;
         const int h_l = (row / p.tw) % p.th;
         const int b_l = row / (p.tw * p.th);
-        const int b = b0 + b_l;
-        const int y = (i0 + h_l) * p.osy + p.ph_ay[phase];
-        const int x = (j0 + w_l) * p.osx + p.ph_ax[phase];
-        const bool valid = (b < p.out_B) && (y < p.out_H) && (x < p.out_W);
-        const size_t off = ((static_cast<size_t>(b) * p.out_H + y) * p.out_W + x) * p.out_C + n0;
+        int li = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+            int i0, j0, b0, n0, phase, it_begin, iters;
+            decode(item, i0, j0, b0, n0, phase, it_begin, iters);
+            const int acc = li & 1;
+            const int b = b0 + b_l;
+            const int y = (i0 + h_l) * p.osy + p.ph_ay[phase];
+            const int x = (j0 + w_l) * p.osx + p.ph_ax[phase];
+            const bool valid = (b < p.out_B) && (y < p.out_H) && (x < p.out_W);
+            const size_t off = ((static_cast<size_t>(b) * p.out_H + y) * p.out_W + x) * p.out_C + n0;
 
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c = 0; c < p.n_tile; c += 32) {
-            uint32_t v[32];
-            const int cols = (p.n_tile - c) >= 32 ? 32 : 16;
-            if (cols == 32) {
-                tmem_ld_32x32(taddr + c, v);
-            } else {
-                uint32_t h[16];
-                tmem_ld_32x16(taddr + c, h);
+            mbar_wait(&tmem_full[acc], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile;
+            for (int c = 0; c < p.n_tile; c += 32) {
+                uint32_t v[32];
+                const int cols = (p.n_tile - c) >= 32 ? 32 : 16;
+                if (cols == 32) {
+                    tmem_ld_32x32(taddr + c, v);
+                } else {
+                    uint32_t h[16];
+                    tmem_ld_32x16(taddr + c, h);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
-            }
-            tmem_ld_wait();
-            float f[32];
+                    for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
+                }
+                tmem_ld_wait();
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (ksplit > 1) {
-                if (valid && iters > 0) {
-                    float* dst = p.splitk_acc + off + c;
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (ksplit > 1) {
+                    if (valid && iters > 0) {
+                        float* dst = p.splitk_acc + off + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < cols) atomicAdd(dst + j, f[j]);
+                    }
+                    continue;
+                }
+                if (p.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < cols) atomicAdd(dst + j, f[j]);
+                        if (j < cols) f[j] += __ldg(p.bias + n0 + c + j);
                 }
-                continue;
-            }
-            if (p.bias != nullptr) {
+                if (valid) {
+                    if (p.out_fp32) {
+                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + c);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < cols) f[j] += __ldg(p.bias + n0 + c + j);
-            }
-            if (valid) {
-                if (p.out_fp32) {
-                    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + c);
+                        for (int j = 0; j < 8; ++j)
+                            if (j * 4 < cols) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j * 4 < cols) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j * 8 < cols)
-                            dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
-                                                pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 8 < cols)
+                                dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                                                    pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    }
                 }
             }
+            // this warp is done reading the accumulator: hand it back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
     }
     tc_fence_before();
@@ -503,7 +544,7 @@ __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float*
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static constexpr int kBarrierBytes = (4 * kMaxStages + 1) * 8 + 16;
+static constexpr int kBarrierBytes = (4 * kMaxStages + 4) * 8 + 16;
 
 static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_bytes + 1024 + kBarrierBytes; }
 
@@ -517,7 +558,9 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     const int stage_bytes = (p.tps > 1 ? p.tps : 1) * (128 + p.n_tile) * p.kchunk * 2;
     const int smem = smem_bytes_for(p.stages, stage_bytes);
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
-    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.n_tiles, p.num_phases * ksplit);
+    const long long items = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * p.n_tiles * p.num_phases * ksplit;
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    dim3 grid(static_cast<unsigned>(std::min<long long>(items, 148LL * per_sm)));
     const size_t out_elems = static_cast<size_t>(p.out_B) * p.out_H * p.out_W * p.out_C;
     if (ksplit > 1) {
         cudaError_t e = cudaMemsetAsync(p.splitk_acc, 0, out_elems * sizeof(float), stream);

@@ -37,6 +37,7 @@ struct alignas(64) IgemmParams {
     int n_tile;    // UMMA N (multiple of 16, <= 256)
     int n_tiles;   // grid.y: N_total / n_tile
     int stages;
+    int b_merged;  // the tps weight slabs of a stage are adjacent rows of the packed tensor: ONE TMA box loads them
     int tps;       // taps per pipeline stage (> 1 only when c_chunks == 1: narrow-channel layers, amortises the
                    // per-stage barrier / issue overhead over several K=16..32 slabs)
     // output: NHWC tensor, element (b, y, x, n) with y = i*osy + ay[phase], x = j*osx + ax[phase]
