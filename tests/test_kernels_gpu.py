@@ -103,6 +103,37 @@ def test_conv_fwd_dgrad_wgrad(case, prec):
     assert rel_err(dw.cpu(), wr.grad) < 2e-5           # fp32 accumulate + fp32 output in both modes
 
 
+@pytest.mark.parametrize("sc,bc,bcv,k", [(64, 128, 128, 4), (48, 80, 80, 3), (64, 16, 3, 4), (64, 16, 3, 3),
+                                         (1, 512, 512, 4), (130, 34, 34, 5), (128, 512, 512, 4)])
+def test_pack_weights_bit_exact(sc, bc, bcv, k):
+    """wd[tap][small][big] / wu[tap][big][small] are the bf16 roundings of the master, zero in the padded channels -
+    both through the single-layer entry point and through the one-launch multi-layer path."""
+    fn = _fn()
+    from vaegan_b200 import _lib
+    gen = torch.Generator().manual_seed(sc * 7 + bc)
+    w = torch.randn(sc, bcv, k, k, generator=gen)
+    ref = torch.zeros(sc, bc, k * k)
+    ref[:, :bcv] = w.view(sc, bcv, k * k)
+    ref = ref.bfloat16()
+    wd_ref, wu_ref = ref.permute(2, 0, 1).contiguous(), ref.permute(2, 1, 0).contiguous()
+    g = _lib.VgConvGeom(1, 8, 8, bc, 4, 4, sc, k, 1, 0, bcv if bcv != bc else 0)
+    wdev = w.cuda()
+    wd, wu = fn.pack_weights(wdev, g)
+    assert torch.equal(wd.cpu(), wd_ref) and torch.equal(wu.cpu(), wu_ref)
+    wd2, wu2 = torch.empty_like(wd).fill_(7.0), torch.empty_like(wu).fill_(7.0)
+    w_other = torch.randn(32, 32, 2, 2, generator=gen).cuda()
+    od, ou = torch.empty(4, 32, 32, dtype=torch.bfloat16, device="cuda"), torch.empty(4, 32, 32, dtype=torch.bfloat16, device="cuda")
+    items = (_lib.VgPackItem * 2)(
+        _lib.VgPackItem(w_other.data_ptr(), od.data_ptr(), ou.data_ptr(), 32, 32, 0, 4),
+        _lib.VgPackItem(wdev.data_ptr(), wd2.data_ptr(), wu2.data_ptr(), sc, bc, bcv if bcv != bc else 0, k * k))
+    _lib.call("vg_pack_weights_multi", items, 2, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(wd2.cpu(), wd_ref) and torch.equal(wu2.cpu(), wu_ref)
+    o_ref = w_other.cpu().view(32, 32, 4).bfloat16()
+    assert torch.equal(od.cpu(), o_ref.permute(2, 0, 1).contiguous())
+    assert torch.equal(ou.cpu(), o_ref.permute(2, 1, 0).contiguous())
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2), (2, 0.01)])
 @pytest.mark.parametrize("rows,C", [(4 * 31 * 31, 32), (7 * 4 * 4, 512), (2 * 64 * 64, 64), (3, 2048)])
