@@ -99,6 +99,36 @@ size_t vg_conv_down_workspace_bytes(const VgConvGeom* g);
 int vg_conv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias, void* small,
                  int out_f32, void* ws, size_t ws_bytes, void* stream);
 int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big, void* stream);
+/* ---- fused epilogues of the tensor-core contractions (bf16 path) ----------------------------------------------
+ * The BatchNorm that follows a convolution in every (Conv|ConvT, BatchNorm2d, ReLU|LeakyReLU) triple of the
+ * reference (main_vae.py:27-31, gan_code.py:19-51, 59-86) needs per-channel sums of the convolution output, and its
+ * backward needs per-channel sums over the gradient the NEXT layer's dgrad produces.  Both ride the epilogue of the
+ * producing contraction, so the activation is not re-read from HBM for the reduction:
+ *   VG_EPI_BN_STATS  out = conv;  sums[g][0][c] += out, sums[g][1][c] += out^2            (forward)
+ *   VG_EPI_BN_BWD    acc = dy;    out = dz = dy*act'(x*scale+shift);  sums[g][0][c] += dz,
+ *                                 sums[g][1][c] += dz*(x-mean)*rstd                        (dgrad of the next layer)
+ *   VG_EPI_ACT_BWD   out = dy*act'(x)                                                      (layer without BatchNorm)
+ * `groups` = independent sub-batches along the batch axis with separate statistics; `sums` = fp32
+ * [groups][2][channels], zero-initialised by the caller, accumulated with atomics; `x` = the saved raw convolution
+ * output (same NHWC shape as this call's output); `stats` = [groups][4][channels] (mean, rstd, scale, shift).
+ * vg_conv_epilogue_supported() tells whether a geometry takes the fused form (1) or the caller has to use the
+ * stand-alone reduction kernels below (0). */
+typedef enum VgEpilogueMode { VG_EPI_NONE = 0, VG_EPI_BN_STATS = 1, VG_EPI_BN_BWD = 2, VG_EPI_ACT_BWD = 3 } VgEpilogueMode;
+typedef struct VgEpilogue {
+    int32_t mode;      /* VgEpilogueMode */
+    int32_t groups;
+    int32_t channels;
+    int32_t act;       /* VgAct of the layer whose backward is fused (modes 2, 3) */
+    float slope;
+    float* sums;
+    const void* x;
+    const float* stats;
+} VgEpilogue;
+int vg_conv_epilogue_supported(const VgConvGeom* g, VgDType dtype, int up, const VgEpilogue* ep);
+int vg_conv_down_ex(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias, void* small,
+                    const VgEpilogue* ep, void* stream);
+int vg_conv_up_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big,
+                  const VgEpilogue* ep, void* stream);
 /* dw (fp32, reference layout [small_c][big_c_valid][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient.
  * Optional scratch (ws may be NULL): with vg_conv_wgrad_workspace_bytes() the tensor-core path splits the pixel
  * reduction across SMs and combines the partial tiles in a second kernel (no atomics are used either way). */
@@ -130,6 +160,18 @@ int vg_bn_act_train_fwd(const void* x, VgDType dt, long long rows, int channels,
 int vg_bn_act_train_bwd(const void* dy, const void* x, VgDType dt, long long rows, int channels, const float* stats,
                         VgAct act, float slope, float* dgamma, float* dbeta, void* dx, float* ws, size_t ws_bytes,
                         void* stream);
+/* BatchNorm passes fed by the raw sums of a fused convolution epilogue (VgEpilogue above); `rows` is per group and
+ * the `groups` sub-batches are consecutive in memory.  vg_bn_apply_from_sums finalises the statistics
+ * (stats[groups][4][channels] written, running statistics advanced once per group, in order) and writes
+ * y = act(BN(x)); vg_bn_bwd_apply_from_sums turns dz (activation derivative already applied) into the gradient of the
+ * convolution output and adds dgamma / dbeta.  `rows` here are rows per group. */
+int vg_bn_apply_from_sums(const void* x, VgDType dt, long long rows, int channels, int groups, const float* sums,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, float momentum, float eps, VgAct act, float slope,
+                          float* stats, void* y, void* stream);
+int vg_bn_bwd_apply_from_sums(const void* dz, const void* x, VgDType dt, long long rows, int channels, int groups,
+                              const float* stats, const float* sums, float* dgamma, float* dbeta, void* dx,
+                              void* stream);
 /* eval-mode BatchNorm folded to scale/shift from the running statistics (main_vae.py:360, decoder.eval()). */
 int vg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int channels, float* scale_out, float* shift_out, void* stream);

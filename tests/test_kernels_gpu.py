@@ -134,6 +134,109 @@ def test_pack_weights_bit_exact(sc, bc, bcv, k):
     assert torch.equal(ou.cpu(), o_ref.permute(2, 1, 0).contiguous())
 
 
+FUSE_CASES = [
+    # kind, B, H, W, Cin, Cout, k, s, p, groups, bias
+    ("down", 8, 16, 16, 64, 128, 4, 2, 1, 2, False),     # discriminator stage, real/fake pair
+    ("down", 6, 31, 31, 32, 64, 4, 2, 0, 1, True),       # encoder stage (bias + BatchNorm), odd extents
+    ("up", 8, 8, 8, 128, 64, 4, 2, 1, 1, False),         # generator stage, 4 output phases
+    ("up", 256, 1, 1, 128, 256, 4, 1, 0, 2, False),      # first generator layer: dense GEMM, channel = column % C
+    ("down", 260, 8, 8, 64, 256, 4, 2, 1, 1, False),     # several tiles per CTA, two N tiles... and a ragged last tile
+]
+
+
+@pytest.mark.parametrize("case", FUSE_CASES, ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-g{c[9]}")
+def test_fused_bn_stats_epilogue(case):
+    """VG_EPI_BN_STATS + vg_bn_apply_from_sums against the stand-alone statistics / apply kernels on the same raw
+    convolution output (which must be bit-identical with and without the fused epilogue)."""
+    fn = _fn()
+    kind, B, H, W, cin, cout, k, s, p, groups, with_bias = case
+    gen = torch.Generator().manual_seed(B * 131 + cin)
+    dt = torch.bfloat16
+    x = torch.randn(B, H, W, cin, generator=gen).cuda().to(dt)
+    if kind == "down":
+        spec, w = fn.ConvSpec("down", cout, cin, k, s, p), torch.randn(cout, cin, k, k, generator=gen).cuda() * 0.1
+    else:
+        spec, w = fn.ConvSpec("up", cin, cout, k, s, p), torch.randn(cin, cout, k, k, generator=gen).cuda() * 0.1
+    g = spec.geom(B, H, W)
+    wd, wu = fn.pack_weights(w, g)
+    bias = (torch.randn(cout, generator=gen).cuda() if with_bias else None)
+    C = cout
+    sums = torch.zeros(groups * 2 * C, device="cuda")
+    ep = fn.make_epilogue(fn.EPI_BN_STATS, groups, C, sums=sums)
+    assert fn.epilogue_supported(g, kind == "up", ep)
+    if kind == "down":
+        raw0, raw1 = fn.conv_down(x, wd, g, bias), fn.conv_down(x, wd, g, bias, ep=ep)
+    else:
+        raw0, raw1 = fn.conv_up(x, wu, g), fn.conv_up(x, wu, g, ep=ep)
+    assert torch.equal(raw0, raw1)
+    gamma, beta = torch.rand(C, generator=gen).cuda() + 0.5, torch.randn(C, generator=gen).cuda()
+    rm0, rv0 = torch.randn(C, generator=gen).cuda(), torch.rand(C, generator=gen).cuda() + 0.5
+    rm1, rv1 = rm0.clone(), rv0.clone()
+    nbt0, nbt1 = (torch.zeros((), dtype=torch.int64, device="cuda") for _ in range(2))
+    y1, st1 = fn.bn_apply_from_sums(raw1, sums, groups, gamma, beta, rm1, rv1, nbt1, 0.1, 1e-5, 2, 0.2)
+    rg = raw0.view(groups, -1, C)
+    for i in range(groups):
+        st0 = fn.bn_train_fwd(rg[i], gamma, beta, rm0, rv0, nbt0, 0.1, 1e-5)
+        y0 = fn.scale_shift_act(rg[i], st0[2], st0[3], 2, 0.2)
+        torch.cuda.synchronize()
+        for j, name in enumerate(("mean", "rstd", "scale", "shift")):
+            assert rel_err(st1[i, j].cpu(), st0[j].cpu()) < 2e-5, (i, name)
+        assert rel_err(y1.view(groups, -1, C)[i].float().cpu(), y0.float().cpu()) < 8e-3     # one bf16 ulp
+    assert rel_err(rm1.cpu(), rm0.cpu()) < 1e-5 and rel_err(rv1.cpu(), rv0.cpu()) < 2e-5
+    assert int(nbt1) == int(nbt0) == groups
+
+
+@pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2)])
+@pytest.mark.parametrize("case", FUSE_CASES[:3] + [FUSE_CASES[4]],
+                         ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-g{c[9]}")
+def test_fused_bn_bwd_epilogue(case, act, slope):
+    """The dgrad of layer L+1 with VG_EPI_BN_BWD (and VG_EPI_ACT_BWD) against dgrad -> vg_bn_act_bwd / vg_act_bwd:
+    layer L here is a BatchNorm'd tensor of the dgrad's output shape."""
+    fn = _fn()
+    kind, B, H, W, cin, cout, k, s, p, groups, _ = case
+    gen = torch.Generator().manual_seed(B * 17 + cout)
+    dt = torch.bfloat16
+    if kind == "down":      # layer L+1 is a Conv2d: its dgrad is `up` and lands on the [B, H, W, cin] input
+        spec, w = fn.ConvSpec("down", cout, cin, k, s, p), torch.randn(cout, cin, k, k, generator=gen).cuda() * 0.1
+    else:
+        spec, w = fn.ConvSpec("up", cin, cout, k, s, p), torch.randn(cin, cout, k, k, generator=gen).cuda() * 0.1
+    g = spec.geom(B, H, W)
+    oh, ow = spec.out_hw(H, W)
+    wd, wu = fn.pack_weights(w, g)
+    d_next = torch.randn(B, oh, ow, cout, generator=gen).cuda().to(dt)           # gradient of layer L+1's raw output
+    raw_l = (torch.randn(B, H, W, cin, generator=gen) * 1.5 + 0.3).cuda().to(dt)   # layer L's raw conv output
+    C = cin
+    gamma, beta = torch.rand(C, generator=gen).cuda() + 0.5, torch.randn(C, generator=gen).cuda() * 0.3
+    stats = torch.stack([fn.bn_train_fwd(r, gamma, beta, None, None, None, 0.1, 1e-5)
+                         for r in raw_l.view(groups, -1, C)])
+    dgrad = (lambda ep=None: fn.conv_up(d_next, wu, g, ep=ep)) if kind == "down" else \
+            (lambda ep=None: fn.conv_down(d_next, wd, g, ep=ep))
+    # reference: plain dgrad, then the stand-alone BatchNorm backward per group
+    dy = dgrad()
+    dg0, db0 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx0 = torch.empty_like(raw_l)
+    for i in range(groups):
+        fn.bn_act_bwd(dy.view(groups, -1, C)[i], raw_l.view(groups, -1, C)[i], stats[i], act, slope, dg0, db0,
+                      out=dx0.view(groups, -1, C)[i])
+    # fused
+    sums = torch.zeros(groups * 2 * C, device="cuda")
+    ep = fn.make_epilogue(fn.EPI_BN_BWD, groups, C, act, slope, sums, raw_l, stats)
+    assert fn.epilogue_supported(g, kind == "down", ep)
+    dz = dgrad(ep)
+    dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx1 = fn.bn_bwd_apply_from_sums(dz, raw_l, stats, sums, groups, dg1, db1)
+    torch.cuda.synchronize()
+    assert rel_err(dx1.float().cpu(), dx0.float().cpu()) < 1.5e-2          # dz is rounded to bf16 once more
+    assert rel_err(dg1.cpu(), dg0.cpu()) < 3e-3 and rel_err(db1.cpu(), db0.cpu()) < 3e-3
+    # activation-only form
+    ep3 = fn.make_epilogue(fn.EPI_ACT_BWD, 1, C, act, slope, None, raw_l, None)
+    assert fn.epilogue_supported(g, kind == "down", ep3)
+    dz3 = dgrad(ep3)
+    ref3 = fn.act_bwd(dy, raw_l, act, slope)
+    torch.cuda.synchronize()
+    assert rel_err(dz3.float().cpu(), ref3.float().cpu()) < 8e-3
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2), (2, 0.01)])
 @pytest.mark.parametrize("rows,C", [(4 * 31 * 31, 32), (7 * 4 * 4, 512), (2 * 64 * 64, 64), (3, 2048)])

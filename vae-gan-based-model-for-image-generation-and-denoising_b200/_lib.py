@@ -29,8 +29,16 @@ class VgPackItem(Structure):
                 ("big_c_valid", c_int32), ("kk", c_int32)]
 
 
+class VgEpilogue(Structure):
+    _fields_ = [("mode", c_int32), ("groups", c_int32), ("channels", c_int32), ("act", c_int32), ("slope", c_float),
+                ("sums", c_void_p), ("x", c_void_p), ("stats", c_void_p)]
+
+
+EPI_NONE, EPI_BN_STATS, EPI_BN_BWD, EPI_ACT_BWD = 0, 1, 2, 3
+
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
 _G = POINTER(VgConvGeom)
+_E = POINTER(VgEpilogue)
 _P = c_void_p
 PROTOTYPES = {
     "vg_last_error": (c_char_p, []),
@@ -42,6 +50,9 @@ PROTOTYPES = {
     "vg_conv_down_workspace_bytes": (c_size_t, [_G]),
     "vg_conv_down": (c_int, [_G, c_int, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "vg_conv_up": (c_int, [_G, c_int, _P, _P, _P, _P]),
+    "vg_conv_epilogue_supported": (c_int, [_G, c_int, c_int, _E]),
+    "vg_conv_down_ex": (c_int, [_G, c_int, _P, _P, _P, _P, _E, _P]),
+    "vg_conv_up_ex": (c_int, [_G, c_int, _P, _P, _P, _E, _P]),
     "vg_conv_wgrad_workspace_bytes": (c_size_t, [_G, c_int]),
     "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "vg_reduce_workspace_bytes": (c_size_t, [c_longlong, c_int]),
@@ -51,6 +62,9 @@ PROTOTYPES = {
     "vg_bn_act_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_float, _P,
                                     _P, _P]),
     "vg_bn_act_train_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, _P, c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "vg_bn_apply_from_sums": (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int,
+                                      c_float, _P, _P, _P]),
+    "vg_bn_bwd_apply_from_sums": (c_int, [_P, _P, c_int, c_longlong, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "vg_bn_eval_coeffs": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P]),
     "vg_scale_shift_act": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_int, c_float, _P, c_int, _P]),
     "vg_bn_act_bwd": (c_int, [_P, _P, c_int, c_longlong, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P, _P,

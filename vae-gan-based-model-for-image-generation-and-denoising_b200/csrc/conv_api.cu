@@ -45,11 +45,11 @@ static int pick_tps(int kchunk, int c_chunks, int taps) {
     return 1;
 }
 
-static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30) {
+static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30, int extra_smem = 0) {
     // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question:
     // narrow accumulators leave room for two CTAs per SM (110 KB each), wide ones take the whole SM.
     (void)iters;
-    const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048;
+    const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048 - extra_smem;
     return std::max(2, std::min(8, budget / stage_bytes));
 }
 
@@ -111,6 +111,60 @@ bool umma_wgrad_ok(const VgConvGeom* g) {
            wgrad_n_tile(g->big_c) != 0;
 }
 
+// ---------------------------------------------------------------------------------------------- fused epilogues
+// Tiling decisions shared by the launchers and by vg_conv_epilogue_supported.
+static void down_tiling(const VgConvGeom* g, int* tw, int* th, int* tb, int* n_tile) {
+    pick_box(128, g->small_w, g->small_h, tw, th, tb);
+    *n_tile = pick_n_tile(g->small_c);
+}
+static void up_tiling(const VgConvGeom* g, int* tw, int* th, int* tb, int* n_tile, int* n_total) {
+    const bool dense = g->small_h == 1 && g->small_w == 1 && g->stride == 1 && g->pad == 0;
+    *n_total = dense ? g->kernel * g->kernel * g->big_c : g->big_c;
+    *n_tile = pick_n_tile(*n_total);
+    const int grid_h = dense ? 1 : ceil_div(g->big_h, g->stride), grid_w = dense ? 1 : ceil_div(g->big_w, g->stride);
+    pick_box(128, grid_w, grid_h, tw, th, tb);
+}
+
+// 0 when `ep` can ride the tensor-core launch of this contraction, else a negative VG_ERR_* (message set).
+static int fuse_check(const VgConvGeom* g, bool up, const VgEpilogue* ep) {
+    if (ep == nullptr || ep->mode == VG_EPI_NONE) return VG_OK;
+    if (is_gemv(g) || !(up ? umma_up_ok(g) : umma_down_ok(g)))
+        return fail(VG_ERR_SHAPE, "fused epilogue: this geometry does not run on the tensor-core path");
+    int tw, th, tb, n_tile, n_total = g->small_c;
+    if (up) up_tiling(g, &tw, &th, &tb, &n_tile, &n_total); else down_tiling(g, &tw, &th, &tb, &n_tile);
+    if (ep->mode < VG_EPI_BN_STATS || ep->mode > VG_EPI_ACT_BWD) return fail(VG_ERR_ARG, "fused epilogue: bad mode %d", ep->mode);
+    if (ep->mode != VG_EPI_BN_STATS) {
+        if (ep->x == nullptr) return fail(VG_ERR_ARG, "fused epilogue: saved conv output missing");
+        if (ep->act != VG_ACT_NONE && ep->act != VG_ACT_RELU && ep->act != VG_ACT_LEAKY)
+            return fail(VG_ERR_SHAPE, "fused epilogue: only ReLU / LeakyReLU / identity derivatives");
+        if (!aligned16(ep->x)) return fail(VG_ERR_ALIGN, "fused epilogue: 16-byte alignment");
+    }
+    if (ep->mode == VG_EPI_ACT_BWD) return VG_OK;
+    const int C = ep->channels, G = ep->groups;
+    if (ep->sums == nullptr || (ep->mode == VG_EPI_BN_BWD && ep->stats == nullptr))
+        return fail(VG_ERR_ARG, "fused epilogue: null statistics buffer");
+    if (C <= 0 || C % 32 != 0 || n_tile % 32 != 0 || n_total % C != 0)
+        return fail(VG_ERR_SHAPE, "fused epilogue: %d channels / N tile %d not multiples of 32", C, n_tile);
+    if (G < 1 || g->batch % G != 0 || (G > 1 && (g->batch / G) % tb != 0))
+        return fail(VG_ERR_SHAPE, "fused epilogue: %d statistics groups do not align with %d-image tiles", G, tb);
+    if (static_cast<long long>(G) * C * 24 > 48 * 1024)
+        return fail(VG_ERR_SHAPE, "fused epilogue: %d x %d channel table exceeds the shared-memory budget", G, C);
+    return VG_OK;
+}
+
+static void fuse_fill(IgemmParams& p, const VgConvGeom* g, const VgEpilogue* ep) {
+    if (ep == nullptr || ep->mode == VG_EPI_NONE) return;
+    p.fuse_mode = ep->mode;
+    p.fuse_groups = ep->groups > 0 ? ep->groups : 1;
+    p.fuse_group_batch = g->batch / p.fuse_groups;
+    p.fuse_c = ep->channels;
+    p.fuse_sums = ep->sums;
+    p.fuse_x = ep->x;
+    p.fuse_stats = ep->stats;
+    p.fuse_act = ep->act;
+    p.fuse_slope = ep->slope;
+}
+
 // ---------------------------------------------------------------------------------------------- down
 static int pick_ksplit(int tiles, int iters) {
     // few output tiles and a long (tap, channel-chunk) loop: spread the reduction over ~one wave of CTAs
@@ -119,10 +173,11 @@ static int pick_ksplit(int tiles, int iters) {
 }
 
 static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const float* bias, void* small,
-                     int out_f32, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                     int out_f32, void* ws, size_t ws_bytes, cudaStream_t stream, const VgEpilogue* ep = nullptr) {
     if (!aligned16(big) || !aligned16(wd) || !aligned16(small)) return fail(VG_ERR_ALIGN, "down: 16-byte alignment");
     IgemmParams p;
     std::memset(&p, 0, sizeof(p));
+    fuse_fill(p, g, ep);
     const int k = g->kernel, s = g->stride, pad = g->pad;
     p.kchunk = pick_kchunk(g->big_c);
     p.c_chunks = g->big_c / p.kchunk;
@@ -163,7 +218,8 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
             t.brow = (ky * k + kx) * g->small_c;
         }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
+                           igemm_fuse_smem_bytes(p));
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -174,7 +230,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     p.bias = bias;
     const size_t acc_bytes = static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
     const int ks = pick_ksplit(p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles, p.taps_per_phase * p.c_chunks);
-    if (ks > 1 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    if (ks > 1 && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
         p.ksplit = ks;
         p.splitk_acc = static_cast<float*>(ws);
     }
@@ -185,10 +241,12 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
 }
 
 // ---------------------------------------------------------------------------------------------- up
-static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void* big, cudaStream_t stream) {
+static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void* big, cudaStream_t stream,
+                   const VgEpilogue* ep = nullptr) {
     if (!aligned16(big) || !aligned16(wu) || !aligned16(small)) return fail(VG_ERR_ALIGN, "up: 16-byte alignment");
     IgemmParams p;
     std::memset(&p, 0, sizeof(p));
+    fuse_fill(p, g, ep);
     const int k = g->kernel, s = g->stride, pad = g->pad;
     const bool dense = g->small_h == 1 && g->small_w == 1 && s == 1 && pad == 0;
     p.kchunk = pick_kchunk(g->small_c);
@@ -269,7 +327,8 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.osy = p.osx = s;
     }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks);
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
+                           igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();
@@ -519,6 +578,37 @@ extern "C" int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small,
     if (is_gemv(g)) return gemv_up(g, dtype, small, w, big, as_stream(stream));
     if (dtype == VG_BF16 && umma_up_ok(g)) return up_umma(g, small, w, big, as_stream(stream));
     return simt_conv_up(g, dtype, small, w, big, as_stream(stream));
+}
+
+extern "C" int vg_conv_epilogue_supported(const VgConvGeom* g, VgDType dtype, int up, const VgEpilogue* ep) {
+    if (check_geom(g) != VG_OK || dtype != VG_BF16 || ep == nullptr) return 0;
+    return fuse_check(g, up != 0, ep) == VG_OK ? 1 : 0;
+}
+
+extern "C" int vg_conv_down_ex(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias,
+                               void* small, const VgEpilogue* ep, void* stream) {
+    int rc = check_geom(g);
+    if (rc != VG_OK) return rc;
+    if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "down: null pointer");
+    rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dtype != VG_BF16) return fail(VG_ERR_SHAPE, "fused epilogues exist on the bf16 tensor-core path only");
+    rc = fuse_check(g, false, ep);
+    if (rc != VG_OK) return rc;
+    return down_umma(g, big, w, bias, small, 0, nullptr, 0, as_stream(stream), ep);
+}
+
+extern "C" int vg_conv_up_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big,
+                             const VgEpilogue* ep, void* stream) {
+    int rc = check_geom(g);
+    if (rc != VG_OK) return rc;
+    if (big == nullptr || w == nullptr || small == nullptr) return fail(VG_ERR_ARG, "up: null pointer");
+    rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dtype != VG_BF16) return fail(VG_ERR_SHAPE, "fused epilogues exist on the bf16 tensor-core path only");
+    rc = fuse_check(g, true, ep);
+    if (rc != VG_OK) return rc;
+    return up_umma(g, small, w, big, as_stream(stream), ep);
 }
 
 extern "C" size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dtype) {

@@ -700,6 +700,128 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_apply_kernel(const T* __r
     }
 }
 
+// ---- BatchNorm passes fed by the raw per-channel sums a convolution epilogue accumulated (VgEpilogue modes 1 / 2).
+// The finalisation (sums -> mean, rstd, scale, shift, or -> the two projection coefficients) is a few flops per
+// channel, so every thread redoes it for ITS channel group in the prologue instead of paying for a finalize launch;
+// block (0, group) publishes the per-channel results, block (0, 0) walks the running statistics through all groups
+// in order (momentum updates do not commute).  blockIdx.y = statistics group (sub-batch of `rows` rows).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
+    const T* __restrict__ x, T* __restrict__ y, long long nvec, int C, long long rows, const float* __restrict__ sums,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+    long long* num_batches_tracked, float momentum, float eps, float* __restrict__ stats, int act, float slope) {
+    constexpr int V = Vec<T>::N;
+    constexpr int U = 4;
+    const int grp = blockIdx.y, groups = gridDim.y;
+    x += static_cast<long long>(grp) * nvec * V;
+    y += static_cast<long long>(grp) * nvec * V;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c0 = static_cast<int>((tid * V) % C);
+    const double inv_n = 1.0 / static_cast<double>(rows);
+    const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = c0 + j;
+        const float* sg = sums + static_cast<long long>(grp) * 2 * C;
+        const double m = static_cast<double>(sg[c]) * inv_n;
+        double var = static_cast<double>(sg[C + c]) * inv_n - m * m;
+        if (var < 0.0) var = 0.0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const float g = gamma ? __ldg(gamma + c) : 1.f, bt = beta ? __ldg(beta + c) : 0.f;
+        sc[j] = g * rstd;
+        sh[j] = bt - static_cast<float>(m) * sc[j];
+        if (publisher) {
+            float* st = stats + static_cast<long long>(grp) * 4 * C;
+            st[c] = static_cast<float>(m);
+            st[C + c] = rstd;
+            st[2 * C + c] = sc[j];
+            st[3 * C + c] = sh[j];
+            if (grp == 0 && running_mean != nullptr) {
+                const double n = static_cast<double>(rows);
+                float rm = running_mean[c], rv = running_var[c];
+                for (int q = 0; q < groups; ++q) {
+                    const float* sq = sums + static_cast<long long>(q) * 2 * C;
+                    const double mq = static_cast<double>(sq[c]) * inv_n;
+                    double vq = static_cast<double>(sq[C + c]) * inv_n - mq * mq;
+                    if (vq < 0.0) vq = 0.0;
+                    const double unbiased = n > 1.0 ? vq * n / (n - 1.0) : vq;
+                    rm = static_cast<float>((1.0 - momentum) * rm + momentum * mq);
+                    rv = static_cast<float>((1.0 - momentum) * rv + momentum * unbiased);
+                }
+                running_mean[c] = rm;
+                running_var[c] = rv;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && grp == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += groups;
+    for (long long i = tid; i < nvec; i += stride * U) {
+        float v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) Vec<T>::load(x + (i + u * stride) * V, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) continue;
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+            Vec<T>::store(y + (i + u * stride) * V, v[u]);
+        }
+    }
+}
+
+// dx = scale*(dz - c1 - xhat*c2) with c1 = sum(dz)/n, c2 = sum(dz*xhat)/n taken from `sums`; dz already carries the
+// activation derivative (VG_EPI_BN_BWD).  dgamma += sum(dz*xhat), dbeta += sum(dz) (atomics: groups share them).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
+    const T* __restrict__ dz, const T* __restrict__ x, T* __restrict__ dx, long long nvec, int C, long long rows,
+    const float* __restrict__ stats, const float* __restrict__ sums, float* dgamma, float* dbeta) {
+    constexpr int V = Vec<T>::N;
+    constexpr int U = 4;
+    const int grp = blockIdx.y;
+    dz += static_cast<long long>(grp) * nvec * V;
+    x += static_cast<long long>(grp) * nvec * V;
+    dx += static_cast<long long>(grp) * nvec * V;
+    stats += static_cast<long long>(grp) * 4 * C;
+    sums += static_cast<long long>(grp) * 2 * C;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c0 = static_cast<int>((tid * V) % C);
+    const float inv_n = 1.f / static_cast<float>(rows);
+    const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
+    float sc[V], kx[V], k0[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = c0 + j;
+        const float s0 = sums[c], s1 = sums[C + c];
+        sc[j] = __ldg(stats + 2 * C + c);
+        const float t = sc[j] * (s1 * inv_n) * __ldg(stats + C + c);
+        kx[j] = -t;
+        k0[j] = t * __ldg(stats + c) - sc[j] * (s0 * inv_n);
+        if (publisher) {
+            if (dbeta != nullptr) atomicAdd(dbeta + c, s0);
+            if (dgamma != nullptr) atomicAdd(dgamma + c, s1);
+        }
+    }
+    for (long long i = tid; i < nvec; i += stride * U) {
+        float xv[U][V], dv[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < nvec) {
+                Vec<T>::load(x + (i + u * stride) * V, xv[u]);
+                Vec<T>::load(dz + (i + u * stride) * V, dv[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u * stride >= nvec) continue;
+#pragma unroll
+            for (int j = 0; j < V; ++j) dv[u][j] = fmaf(sc[j], dv[u][j], fmaf(kx[j], xv[u][j], k0[j]));
+            Vec<T>::store(dx + (i + u * stride) * V, dv[u]);
+        }
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const TI* __restrict__ dy, const TI* __restrict__ x,
                                                           TO* __restrict__ dx, long long n, int act, float slope) {
@@ -907,6 +1029,62 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
         bn_act_bwd_apply_kernel<float><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
             static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
             mean, rstd, c1, c2, act, slope);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_bn_apply_from_sums(const void* x, VgDType dt, long long rows, int C, int groups, const float* sums,
+                                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, float momentum, float eps, VgAct act, float slope,
+                                     float* stats, void* y, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (x == nullptr || y == nullptr || sums == nullptr || stats == nullptr)
+        return fail(VG_ERR_ARG, "bn_apply_from_sums: null pointer");
+    rc = check_channels(dt, C);
+    if (rc != VG_OK) return rc;
+    const int V = dt == VG_BF16 ? 8 : 4;
+    if (C / V > kThreads) return fail(VG_ERR_SHAPE, "bn_apply_from_sums: at most %d channels", kThreads * V);
+    if (groups < 1 || groups > 64) return fail(VG_ERR_SHAPE, "bn_apply_from_sums: bad group count %d", groups);
+    if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
+    const long long nvec = rows * C / V;
+    const dim3 grid(grid_affine(nvec, C / V), groups);
+    cudaStream_t st = as_stream(stream);
+    if (dt == VG_BF16)
+        bn_apply_from_sums_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, rows, sums, gamma, beta,
+            running_mean, running_var, num_batches_tracked, momentum, eps, stats, act, slope);
+    else
+        bn_apply_from_sums_kernel<float><<<grid, kThreads, 0, st>>>(
+            static_cast<const float*>(x), static_cast<float*>(y), nvec, C, rows, sums, gamma, beta, running_mean,
+            running_var, num_batches_tracked, momentum, eps, stats, act, slope);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_bn_bwd_apply_from_sums(const void* dz, const void* x, VgDType dt, long long rows, int C, int groups,
+                                         const float* stats, const float* sums, float* dgamma, float* dbeta, void* dx,
+                                         void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dz == nullptr || x == nullptr || dx == nullptr || stats == nullptr || sums == nullptr)
+        return fail(VG_ERR_ARG, "bn_bwd_apply_from_sums: null pointer");
+    rc = check_channels(dt, C);
+    if (rc != VG_OK) return rc;
+    const int V = dt == VG_BF16 ? 8 : 4;
+    if (C / V > kThreads) return fail(VG_ERR_SHAPE, "bn_bwd_apply_from_sums: at most %d channels", kThreads * V);
+    if (groups < 1 || groups > 64) return fail(VG_ERR_SHAPE, "bn_bwd_apply_from_sums: bad group count %d", groups);
+    const long long nvec = rows * C / V;
+    const dim3 grid(grid_affine(nvec, C / V), groups);
+    cudaStream_t st = as_stream(stream);
+    if (dt == VG_BF16)
+        bn_bwd_apply_from_sums_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
+            nvec, C, rows, stats, sums, dgamma, dbeta);
+    else
+        bn_bwd_apply_from_sums_kernel<float><<<grid, kThreads, 0, st>>>(
+            static_cast<const float*>(dz), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, rows, stats,
+            sums, dgamma, dbeta);
     VG_LAUNCHED();
     return VG_OK;
 }

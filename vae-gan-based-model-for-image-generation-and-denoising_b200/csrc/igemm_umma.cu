@@ -15,6 +15,29 @@ namespace vg {
 
 static constexpr int kIgemmThreads = 192;
 static constexpr int kMaxStages = 24;
+static constexpr int kBarrierBytes = (4 * kMaxStages + 4) * 8 + 16;
+
+// Column totals over the 32 lanes of a warp: v[j] is this lane's (= this output row's) value of column j.  A
+// transposing butterfly (16+8+4+2+1 = 31 shuffles instead of 32 x 5) leaves the total of column `lane` in the
+// returned value.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const float send = upper ? v[j] : v[j + o];
+            const float keep = upper ? v[j + o] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ float fuse_act_grad(float z, int act, float slope) {
+    // VgAct: 1 = ReLU, 2 = LeakyReLU; anything else is the identity (the launcher admits only these)
+    return (act == 1) ? (z > 0.f ? 1.f : 0.f) : ((act == 2) ? (z > 0.f ? 1.f : slope) : 1.f);
+}
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
     uint32_t c = 32;
@@ -46,6 +69,21 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     uint64_t* tmem_full = empty + kMaxStages;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    // fused-epilogue scratch: per-CTA channel sums [groups][2][C], then (mode 2) per-channel (mean, rstd, scale, shift)
+    const int fmode = p.fuse_mode;
+    const int fC = p.fuse_c;
+    float* s_sums = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarrierBytes);
+    float4* s_prm = reinterpret_cast<float4*>(s_sums + p.fuse_groups * 2 * fC);
+    if (fmode == 1 || fmode == 2) {
+        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += kIgemmThreads) s_sums[i] = 0.f;
+        if (fmode == 2) {
+            for (int i = threadIdx.x; i < p.fuse_groups * fC; i += kIgemmThreads) {
+                const int g = i / fC, c = i - g * fC;
+                const float* st = p.fuse_stats + static_cast<size_t>(g) * 4 * fC;
+                s_prm[i] = make_float4(__ldg(st + c), __ldg(st + fC + c), __ldg(st + 2 * fC + c), __ldg(st + 3 * fC + c));
+            }
+        }
+    }
 
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
@@ -169,6 +207,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         const int w_l = row % p.tw;
         const int h_l = (row / p.tw) % p.th;
         const int b_l = row / (p.tw * p.th);
+        const __nv_bfloat16* fx = static_cast<const __nv_bfloat16*>(p.fuse_x);
         int li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
             int i0, j0, b0, n0, phase, it_begin, iters;
@@ -179,6 +218,20 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const int x = (j0 + w_l) * p.osx + p.ph_ax[phase];
             const bool valid = (b < p.out_B) && (y < p.out_H) && (x < p.out_W);
             const size_t off = ((static_cast<size_t>(b) * p.out_H + y) * p.out_W + x) * p.out_C + n0;
+            const int grp = (fmode == 1 || fmode == 2) ? min(b0 / p.fuse_group_batch, p.fuse_groups - 1) : 0;   // tile-uniform
+            float* gs0 = s_sums + grp * 2 * fC;
+            float* gs1 = gs0 + fC;
+
+            // mode 2/3: this row's slice of the saved conv output, one 32-column chunk ahead of the accumulator
+            uint4 xq[4] = {};
+            auto load_x = [&](int c) {
+                if (!valid) return;
+                const uint4* src = reinterpret_cast<const uint4*>(fx + off + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j * 8 < p.n_tile) xq[j] = __ldg(src + j);
+            };
+            if (fmode >= 2) load_x(0);
 
             mbar_wait(&tmem_full[acc], (li >> 1) & 1);
             tc_fence_after();
@@ -212,20 +265,64 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     for (int j = 0; j < 32; ++j)
                         if (j < cols) f[j] += __ldg(p.bias + n0 + c + j);
                 }
-                if (valid) {
-                    if (p.out_fp32) {
+                if (p.out_fp32) {
+                    if (valid) {
                         float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + c);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j * 4 < cols) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
+                    }
+                    continue;
+                }
+                // fused statistics: fuse_c and n_tile are multiples of 32, so a chunk never wraps around the channel count
+                const int ch0 = (fmode == 1 || fmode == 2) ? (n0 + c) % fC : 0;
+                float xv[32];
+                if (fmode >= 2) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 8 < cols)
-                                dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
-                                                    pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w4[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            xv[8 * j + 2 * i] = __uint_as_float(w4[i] << 16);
+                            xv[8 * j + 2 * i + 1] = __uint_as_float(w4[i] & 0xFFFF0000u);
+                        }
+                    }
+                    if (c + 32 < p.n_tile) load_x(c + 32);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float z = xv[j];
+                        if (fmode == 2) {
+                            const float4 pr = s_prm[grp * fC + ch0 + j];
+                            z = fmaf(xv[j], pr.z, pr.w);
+                            xv[j] = (xv[j] - pr.x) * pr.y;          // xhat
+                        }
+                        f[j] *= fuse_act_grad(z, p.fuse_act, p.fuse_slope);
+                    }
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j * 8 < cols) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                if (fmode == 1 || fmode == 2) {
+                    // statistics of exactly what was stored (the bf16-rounded values), rows outside the tensor excluded
+                    float s1[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        f[2 * j] = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+                        f[2 * j + 1] = valid ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s1[j] = f[j] * (fmode == 1 ? f[j] : xv[j]);
+                    const float t0 = warp_colsum32(f, lane);
+                    const float t1 = warp_colsum32(s1, lane);
+                    if (lane < cols) {
+                        atomicAdd(gs0 + ch0 + lane, t0);
+                        atomicAdd(gs1 + ch0 + lane, t1);
                     }
                 }
             }
@@ -238,6 +335,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if (fmode == 1 || fmode == 2) {
+        // one flush per CTA; a persistent CTA touches one or two N tiles, the rest of its table is still zero
+        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += kIgemmThreads) {
+            const float t = s_sums[i];
+            if (t != 0.f) atomicAdd(p.fuse_sums + i, t);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,8 +648,6 @@ __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float*
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static constexpr int kBarrierBytes = (4 * kMaxStages + 4) * 8 + 16;
-
 static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_bytes + 1024 + kBarrierBytes; }
 
 int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
@@ -556,7 +658,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int stage_bytes = (p.tps > 1 ? p.tps : 1) * (128 + p.n_tile) * p.kchunk * 2;
-    const int smem = smem_bytes_for(p.stages, stage_bytes);
+    const int smem = smem_bytes_for(p.stages, stage_bytes) + igemm_fuse_smem_bytes(p);
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const long long items = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * p.n_tiles * p.num_phases * ksplit;
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;

@@ -51,7 +51,27 @@ struct alignas(64) IgemmParams {
     // their fp32 partial tiles into `splitk_acc` (zeroed by the launcher) and a finishing kernel converts / adds bias
     int ksplit;
     float* splitk_acc;
+    // Fused epilogue (bf16 output, ksplit == 1 only).  Statistics are per channel = (output column) % fuse_c and per
+    // statistics group = (image index) / fuse_group_batch; a tile never straddles two groups (launcher's contract).
+    //   mode 1  BatchNorm statistics of the stored (bf16-rounded) output:  sums[g][0][c] += v, sums[g][1][c] += v*v
+    //   mode 2  BatchNorm backward: the accumulator is dy; out = dz = dy * act'(x*scale+shift) with x = fuse_x (the
+    //           raw conv output the BatchNorm normalised), sums[g][0][c] += dz, sums[g][1][c] += dz*(x-mean)*rstd
+    //   mode 3  activation backward only: out = dy * act'(x)
+    // CTAs accumulate in shared memory and flush once with fp32 atomics into `fuse_sums` (caller zero-initialises).
+    int fuse_mode, fuse_groups, fuse_group_batch, fuse_c;
+    float* fuse_sums;          // [groups][2][fuse_c]
+    const void* fuse_x;        // bf16, same NHWC shape as `out`
+    const float* fuse_stats;   // [groups][4][fuse_c]: mean, rstd, scale, shift
+    int fuse_act;
+    float fuse_slope;
 };
+
+// shared memory the fused epilogue adds to a CTA
+inline int igemm_fuse_smem_bytes(const IgemmParams& p) {
+    if (p.fuse_mode == 1) return p.fuse_groups * 2 * p.fuse_c * 4;
+    if (p.fuse_mode == 2) return p.fuse_groups * p.fuse_c * (2 * 4 + 16);
+    return 0;
+}
 
 struct alignas(64) WgradParams {
     CUtensorMap pmap;      // "P" operand (plain view), channels -> UMMA M

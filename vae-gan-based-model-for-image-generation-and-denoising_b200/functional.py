@@ -13,7 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, VG_BF16, VG_F32, VgConvGeom, call)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_ACT_BWD, EPI_BN_BWD, EPI_BN_STATS, VG_BF16,
+                   VG_F32, VgConvGeom, VgEpilogue, call)
 
 _DT = {torch.float32: VG_F32, torch.bfloat16: VG_BF16}
 PRECISION_DTYPE = {"fp32": torch.float32, "bf16": torch.bfloat16}
@@ -85,24 +86,44 @@ def pack_weights(w: torch.Tensor, g: VgConvGeom) -> Tuple[torch.Tensor, torch.Te
     return wd, wu
 
 
+def make_epilogue(mode: int, groups: int = 1, channels: int = 0, act: int = ACT_NONE, slope: float = 0.0,
+                  sums: Optional[torch.Tensor] = None, x: Optional[torch.Tensor] = None,
+                  stats: Optional[torch.Tensor] = None) -> VgEpilogue:
+    """VgEpilogue for the fused forms of conv_down / conv_up (include/vaegan_b200.h).  The caller keeps the tensors
+    alive until the launch has been enqueued."""
+    ep = VgEpilogue(mode, groups, channels, act, float(slope), None if sums is None else sums.data_ptr(),
+                    None if x is None else x.data_ptr(), None if stats is None else stats.data_ptr())
+    return ep
+
+
+def epilogue_supported(g: VgConvGeom, up: bool, ep: VgEpilogue) -> bool:
+    return bool(_lib.load().vg_conv_epilogue_supported(ctypes.byref(g), VG_BF16, int(up), ctypes.byref(ep)))
+
+
 def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[torch.Tensor] = None,
-              out_f32: bool = False) -> torch.Tensor:
-    dt = big.dtype
-    out = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=torch.float32 if out_f32 else dt,
-                      device=big.device)
+              out_f32: bool = False, ep: Optional[VgEpilogue] = None) -> torch.Tensor:
+    out_dtype = torch.float32 if out_f32 else big.dtype
+    small = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=out_dtype, device=big.device)
+    if ep is not None:
+        call("vg_conv_down_ex", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), ctypes.byref(ep),
+             _stream())
+        return small
     ws, nbytes = None, 0
-    if dt == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
+    if big.dtype == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
         nbytes = _lib.load().vg_conv_down_workspace_bytes(ctypes.byref(g))
         ws = _ws(nbytes, big.device)
-    call("vg_conv_down", ctypes.byref(g), _DT[dt], _p(big), _p(w), _p(bias), _p(out), int(out_f32), _p(ws), nbytes,
-         _stream())
-    return out
+    call("vg_conv_down", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), int(out_f32), _p(ws),
+         nbytes, _stream())
+    return small
 
 
-def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom) -> torch.Tensor:
-    out = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
-    call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(out), _stream())
-    return out
+def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[VgEpilogue] = None) -> torch.Tensor:
+    big = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
+    if ep is not None:
+        call("vg_conv_up_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), ctypes.byref(ep), _stream())
+    else:
+        call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), _stream())
+    return big
 
 
 def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -158,6 +179,63 @@ def bn_act_train_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act
     ws = _ws(nbytes, x.device)
     call("vg_bn_act_train_bwd", _p(dy), _p(x), _DT[x.dtype], rows, C, _p(stats), act, float(slope), _p(dgamma),
          _p(dbeta), _p(dx), _p(ws), nbytes, _stream())
+    return dx
+
+
+class SumsArena:
+    """Zero-initialised fp32 scratch for the channel sums of the fused convolution epilogues.  Slices are handed
+    out sequentially from one buffer per device; `reset()` (called by the fused step at the start of every step, so
+    that a captured CUDA graph always sees the same addresses) re-zeroes it with one memset.  When the buffer runs out
+    a fresh zero buffer replaces it - the old one stays alive through the slices still referencing it."""
+    FLOATS = 1 << 20
+    _buf = {}
+    _off = {}
+
+    @classmethod
+    def take(cls, n: int, device) -> torch.Tensor:
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        n = (n + 31) // 32 * 32
+        buf = cls._buf.get(key)
+        if buf is None or cls._off[key] + n > buf.numel():
+            buf = torch.zeros(max(cls.FLOATS, n), dtype=torch.float32, device=device)
+            cls._buf[key], cls._off[key] = buf, 0
+        off = cls._off[key]
+        cls._off[key] = off + n
+        return buf[off:off + n]
+
+    @classmethod
+    def reset(cls, device) -> None:
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        buf = cls._buf.get(key)
+        if buf is None:
+            cls._buf[key] = torch.zeros(cls.FLOATS, dtype=torch.float32, device=device)
+        elif cls._off[key]:
+            buf.zero_()
+        cls._off[key] = 0
+
+
+def bn_apply_from_sums(x: torch.Tensor, sums: torch.Tensor, groups: int, gamma, beta, running_mean, running_var,
+                       num_batches_tracked, momentum: float, eps: float, act: int, slope: float):
+    """Finalise the BatchNorm statistics from the raw sums of a VG_EPI_BN_STATS epilogue and apply
+    y = act(BN(x)) in the same launch.  Returns (y, stats[groups, 4, C])."""
+    C = x.shape[-1]
+    rows = x.numel() // C // groups
+    stats = torch.empty((groups, 4, C), dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    call("vg_bn_apply_from_sums", _p(x), _DT[x.dtype], rows, C, groups, _p(sums), _p(gamma), _p(beta), _p(running_mean),
+         _p(running_var), _p(num_batches_tracked), float(momentum), float(eps), act, float(slope), _p(stats), _p(y),
+         _stream())
+    return y, stats
+
+
+def bn_bwd_apply_from_sums(dz: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, sums: torch.Tensor, groups: int,
+                           dgamma, dbeta) -> torch.Tensor:
+    """dx of BatchNorm from dz (activation derivative already applied) and the raw sums of a VG_EPI_BN_BWD epilogue."""
+    C = x.shape[-1]
+    rows = x.numel() // C // groups
+    dx = torch.empty_like(x)
+    call("vg_bn_bwd_apply_from_sums", _p(dz), _p(x), _DT[x.dtype], rows, C, groups, _p(stats), _p(sums), _p(dgamma),
+         _p(dbeta), _p(dx), _stream())
     return dx
 
 
@@ -303,6 +381,18 @@ def _accumulate_or_return(param: Optional[torch.Tensor], grad: Optional[torch.Te
     return None if (param is not None and getattr(param, "main_grad", None) is not None) else grad
 
 
+class LayerLink:
+    """Hand-shake between two CONSECUTIVE layers of a sequential chain (the output of the first feeds the second and
+    nothing else).  The producer records what its backward needs (raw conv output, BatchNorm statistics,
+    activation); the consumer's dgrad then applies the activation derivative and accumulates the BatchNorm-backward
+    sums in its own epilogue (VG_EPI_BN_BWD / VG_EPI_ACT_BWD), and the producer's backward starts from dz."""
+    __slots__ = ("raw", "stats", "act", "slope", "groups", "sums", "fused")
+
+    def __init__(self):
+        self.raw = self.stats = self.sums = None
+        self.act, self.slope, self.groups, self.fused = ACT_NONE, 0.0, 1, False
+
+
 class ConvLayerFn(torch.autograd.Function):
     """conv / convT (+bias) -> [BatchNorm2d, training or eval] -> activation, on NHWC tensors.
 
@@ -311,7 +401,8 @@ class ConvLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, spec: ConvSpec, act: int, slope: float, bn, training: bool,
-                cache: PackedWeights, out_f32: bool, groups: int = 1):
+                cache: PackedWeights, out_f32: bool, groups: int = 1, link_in: Optional[LayerLink] = None,
+                link_out: Optional[LayerLink] = None):
         """`groups` > 1: the batch holds that many independent sub-batches (e.g. the discriminator's real and fake
         batches of vaegan_code.py:96-97 run through ONE convolution launch); BatchNorm statistics, running-stat
         updates and the BN backward stay per sub-batch, in order, exactly as separate forward calls would."""
@@ -333,17 +424,32 @@ class ConvLayerFn(torch.autograd.Function):
             w_fwd = wd if spec.kind == "down" else wu
         else:
             w_fwd = _contig(weight.detach())
+        # training BatchNorm on the tensor-core path: the statistics ride the convolution's epilogue
+        ep = sums = None
+        if bn is not None and training and x.dtype == torch.bfloat16 and not out_f32:
+            if B % groups:
+                raise RuntimeError(f"batch {B} is not divisible into {groups} sub-batches")
+            C = spec.small_c if spec.kind == "down" else g.big_c
+            sums = SumsArena.take(groups * 2 * C, x.device)
+            ep = make_epilogue(EPI_BN_STATS, groups, C, sums=sums)
+            if not epilogue_supported(g, spec.kind == "up", ep):
+                ep = sums = None
         if spec.kind == "down":
-            raw = conv_down(x, w_fwd, g, bias.detach() if bias is not None else None, out_f32=out_f32)
+            raw = conv_down(x, w_fwd, g, bias.detach() if bias is not None else None, out_f32=out_f32, ep=ep)
         else:
-            raw = conv_up(x, w_fwd, g)
+            raw = conv_up(x, w_fwd, g, ep=ep)
         stats = None
         if bn is not None:
             if training:
                 rm, rv, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats \
                     else (None, None, None)
                 # F.batch_norm semantics: momentum=None means cumulative average - the reference never uses it
-                if groups == 1:
+                if ep is not None:
+                    y, stats = bn_apply_from_sums(raw, sums, groups, gamma.detach(), beta.detach(), rm, rv, nbt,
+                                                  bn.momentum, bn.eps, act, slope)
+                    if groups == 1:
+                        stats = stats[0]
+                elif groups == 1:
                     stats = bn_train_fwd(raw, gamma.detach(), beta.detach(), rm, rv, nbt, bn.momentum, bn.eps)
                     y = scale_shift_act(raw, stats[2], stats[3], act, slope)
                 else:
@@ -367,6 +473,11 @@ class ConvLayerFn(torch.autograd.Function):
         ctx.has_bn, ctx.bn_training, ctx.cache, ctx.out_f32 = bn is not None, training, cache, out_f32
         ctx.groups = groups
         ctx.params = (weight, bias, gamma, beta)
+        ctx.link_in, ctx.link_out = link_in, None
+        if (link_out is not None and x.dtype == torch.bfloat16 and not out_f32 and act in (ACT_NONE, ACT_RELU, ACT_LEAKY)
+                and (bn is None or training) and (bn is not None or act != ACT_NONE)):
+            link_out.raw, link_out.stats, link_out.act, link_out.slope, link_out.groups = raw, stats, act, slope, groups
+            ctx.link_out = link_out
         ctx.save_for_backward(x, raw, stats)
         return y
 
@@ -380,7 +491,20 @@ class ConvLayerFn(torch.autograd.Function):
         dgamma = dbeta = dbias = dw = dx = None
 
         # ---- through activation (+ BatchNorm) to the gradient of the raw conv output
-        if ctx.has_bn:
+        link_out = ctx.link_out
+        if link_out is not None and link_out.fused:
+            # the next layer's dgrad epilogue already produced dz = dy * act'(.) and the two channel sums
+            if ctx.has_bn:
+                if ctx.needs_input_grad[3]:
+                    dgamma = getattr(gamma, "main_grad", None)
+                    dbeta = getattr(beta, "main_grad", None)
+                    if dgamma is None:
+                        dgamma = torch.zeros_like(gamma, dtype=torch.float32)
+                        dbeta = torch.zeros_like(beta, dtype=torch.float32)
+                d_raw = bn_bwd_apply_from_sums(dy, raw, stats, link_out.sums, ctx.groups, dgamma, dbeta)
+            else:
+                d_raw = dy
+        elif ctx.has_bn:
             if ctx.bn_training:
                 want_affine = ctx.needs_input_grad[3]
                 if want_affine:
@@ -428,10 +552,24 @@ class ConvLayerFn(torch.autograd.Function):
                 w_bwd = wu if spec.kind == "down" else wd
             else:
                 w_bwd = _contig(weight.detach())
-            dx = conv_up(d_raw, w_bwd, g) if spec.kind == "down" else conv_down(d_raw, w_bwd, g)
+            # the producer of x left a link: fold ITS activation / BatchNorm backward reduction into this dgrad
+            link_in, ep, sums = ctx.link_in, None, None
+            if link_in is not None and link_in.raw is not None and x.dtype == torch.bfloat16:
+                C = link_in.raw.shape[-1]
+                if link_in.stats is not None:
+                    sums = SumsArena.take(link_in.groups * 2 * C, x.device)
+                    ep = make_epilogue(EPI_BN_BWD, link_in.groups, C, link_in.act, link_in.slope, sums, link_in.raw,
+                                       link_in.stats)
+                else:
+                    ep = make_epilogue(EPI_ACT_BWD, 1, C, link_in.act, link_in.slope, None, link_in.raw, None)
+                if not epilogue_supported(g, spec.kind == "down", ep):
+                    ep = None
+            dx = conv_up(d_raw, w_bwd, g, ep=ep) if spec.kind == "down" else conv_down(d_raw, w_bwd, g, ep=ep)
+            if ep is not None:
+                link_in.sums, link_in.fused = sums, True
         return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
                 _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 class ToNHWCFn(torch.autograd.Function):

@@ -67,12 +67,23 @@ class _Layer:
         self.spec = _spec_of(conv)
         self.cache = F_.PackedWeights()
 
-    def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1):
+    def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1,
+                 link_in=None, link_out=None):
         bn = self.bn
         act = self.act if fuse_act else ACT_NONE
         return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, bn.weight if bn is not None else None,
                                     bn.bias if bn is not None else None, self.spec, act, self.slope, bn, training,
-                                    self.cache, out_f32, groups)
+                                    self.cache, out_f32, groups, link_in, link_out)
+
+
+def _run_chain(layers, h, training: bool, groups: int = 1, link=None):
+    """Run consecutive layers whose outputs feed only the next layer, handing a LayerLink from each producer to its
+    consumer so that the backward reductions fuse into the consumer's dgrad.  Returns (output, link of the last layer)."""
+    for layer in layers:
+        nxt = F_.LayerLink() if torch.is_grad_enabled() else None
+        h = layer(h, training, groups=groups, link_in=link, link_out=nxt)
+        link = nxt
+    return h, link
 
 
 def _group_layers(seq: nn.Sequential) -> List[_Layer]:
@@ -180,8 +191,9 @@ class Encoder(_KernelModule):
 
     def forward_nhwc(self, h):
         """Same as forward for an input that is already an internal NHWC activation (used by the fused step)."""
-        for blk in self.cnn:
-            h = blk._layer()(h, self.training)
+        blocks = [blk._layer() for blk in self.cnn]
+        h, link = _run_chain(blocks[:-1], h, self.training)
+        h = blocks[-1](h, self.training, link_in=link)          # two heads read this output: no link beyond it
         if (h.shape[1], h.shape[2]) != self._feat_hw:
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({h.shape[0]}x"
                                f"{h.shape[1] * h.shape[2] * h.shape[3]} and {self.flatten_size}x{self.fc_mu.out_features})")
@@ -237,9 +249,8 @@ class Generator(_KernelModule):
     def forward_nhwc(self, h):
         """z as NHWC [B,1,1,nz] -> RAW last-conv output NHWC [B,H,W,nc]; the final Tanh rides the NCHW store."""
         layers = self._layers()
-        for layer in layers[:-1]:
-            h = layer(h, self.training)
-        return layers[-1](h, self.training, fuse_act=False)
+        h, link = _run_chain(layers[:-1], h, self.training)
+        return layers[-1](h, self.training, fuse_act=False, link_in=link)
 
 
 Decoder = Generator   # main_vae.py:10
@@ -276,10 +287,9 @@ class Discriminator(_KernelModule):
         """`groups` independent sub-batches stacked along the batch axis share every convolution launch while
         BatchNorm treats them separately (the fused step runs D(real) and D(fake) of vaegan_code.py:96-97 this way)."""
         layers = self._layers()
-        for layer in layers[:-1]:
-            h = layer(h, self.training, groups=groups)
+        h, link = _run_chain(layers[:-1], h, self.training, groups=groups)
         last = layers[-1]
-        logits = last(h, self.training, out_f32=True, fuse_act=False)     # [B, 1, 1, 1] fp32
+        logits = last(h, self.training, out_f32=True, fuse_act=False, link_in=link)     # [B, 1, 1, 1] fp32
         return F_.PointwiseActFn.apply(logits, last.act, last.slope).view(-1)
 
 

@@ -168,6 +168,7 @@ class VAEGANStep:
         E, G, D = self.E, self.G, self.D
         real, loss = s["real"], s["losses"]
         B = real.shape[0]
+        F_.SumsArena.reset(self.dev)   # channel-sum scratch of the fused conv epilogues: one memset per step
         for net in (E, G, D):          # every replay starts from freshly packed bf16 weights (one launch per net)
             net.repack_weights()
         if gen_noise:                  # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
