@@ -48,7 +48,9 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 // ------------------------------------------------------------------------------------------------
 // fprop-type kernel: A = activation views (K-major), B = packed weights (K-major), D -> NHWC output
 // ------------------------------------------------------------------------------------------------
+template <int FMODE>
 __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
+    // FMODE = IgemmParams::fuse_mode (compile-time: the plain kernel carries none of the fused-epilogue code).
     // Persistent: each CTA walks work items (M tile, N tile, phase, K slice) with stride gridDim.x.  The smem ring
     // runs continuously across items and the accumulator is double-buffered in TMEM, so the epilogue of item i
     // overlaps the loads and MMAs of item i+1 and the per-CTA prologue (TMEM alloc, barrier init) is paid once.
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     // fused-epilogue scratch: per-CTA channel sums [groups][2][C], then (mode 2) per-channel (mean, rstd, scale, shift)
-    const int fmode = p.fuse_mode;
+    constexpr int fmode = FMODE;
     const int fC = p.fuse_c;
     float* s_sums = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarrierBytes);
     float4* s_prm = reinterpret_cast<float4*>(s_sums + p.fuse_groups * 2 * fC);
@@ -208,6 +210,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         const int h_l = (row / p.tw) % p.th;
         const int b_l = row / (p.tw * p.th);
         const __nv_bfloat16* fx = static_cast<const __nv_bfloat16*>(p.fuse_x);
+        // derivative of the fused layer's activation on the negative side (ReLU 0, LeakyReLU slope, identity 1)
+        const float neg_slope = p.fuse_act == 1 ? 0.f : (p.fuse_act == 2 ? p.fuse_slope : 1.f);
         int li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
             int i0, j0, b0, n0, phase, it_begin, iters;
@@ -218,18 +222,24 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const int x = (j0 + w_l) * p.osx + p.ph_ax[phase];
             const bool valid = (b < p.out_B) && (y < p.out_H) && (x < p.out_W);
             const size_t off = ((static_cast<size_t>(b) * p.out_H + y) * p.out_W + x) * p.out_C + n0;
-            const int grp = (fmode == 1 || fmode == 2) ? min(b0 / p.fuse_group_batch, p.fuse_groups - 1) : 0;   // tile-uniform
+            const bool all_valid = __all_sync(0xffffffffu, valid);
+            int grp = 0;
+            if (fmode == 1 || fmode == 2) grp = min(b0 / p.fuse_group_batch, p.fuse_groups - 1);   // tile-uniform
             float* gs0 = s_sums + grp * 2 * fC;
             float* gs1 = gs0 + fC;
 
             // mode 2/3: this row's slice of the saved conv output, one 32-column chunk ahead of the accumulator
             uint4 xq[4] = {};
             auto load_x = [&](int c) {
-                if (!valid) return;
-                const uint4* src = reinterpret_cast<const uint4*>(fx + off + c);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (c + j * 8 < p.n_tile) xq[j] = __ldg(src + j);
+                if (valid) {
+                    const uint4* src = reinterpret_cast<const uint4*>(fx + off + c);
+                    xq[0] = __ldg(src);
+                    xq[1] = __ldg(src + 1);
+                    if (c + 16 < p.n_tile) {
+                        xq[2] = __ldg(src + 2);
+                        xq[3] = __ldg(src + 3);
+                    }
+                }
             };
             if (fmode >= 2) load_x(0);
 
@@ -238,8 +248,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile;
             for (int c = 0; c < p.n_tile; c += 32) {
                 uint32_t v[32];
-                const int cols = (p.n_tile - c) >= 32 ? 32 : 16;
-                if (cols == 32) {
+                const bool full_chunk = (p.n_tile - c) >= 32;       // else a 16-column tail
+                if (full_chunk) {
                     tmem_ld_32x32(taddr + c, v);
                 } else {
                     uint32_t h[16];
@@ -251,31 +261,40 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (ksplit > 1) {
+                if (fmode == 0 && ksplit > 1) {
                     if (valid && iters > 0) {
                         float* dst = p.splitk_acc + off + c;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < cols) atomicAdd(dst + j, f[j]);
+                            if (j < 16 || full_chunk) atomicAdd(dst + j, f[j]);
                     }
                     continue;
                 }
                 if (p.bias != nullptr) {
+                    const float* bp = p.bias + n0 + c;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < cols) f[j] += __ldg(p.bias + n0 + c + j);
+                    for (int j = 0; j < 16; ++j) f[j] += __ldg(bp + j);
+                    if (full_chunk) {
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) f[j] += __ldg(bp + j);
+                    }
                 }
-                if (p.out_fp32) {
+                if (fmode == 0 && p.out_fp32) {
                     if (valid) {
                         float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + c);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j * 4 < cols) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        if (full_chunk) {
+#pragma unroll
+                            for (int j = 4; j < 8; ++j)
+                                dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
                     }
                     continue;
                 }
-                // fused statistics: fuse_c and n_tile are multiples of 32, so a chunk never wraps around the channel count
-                const int ch0 = (fmode == 1 || fmode == 2) ? (n0 + c) % fC : 0;
+                // fused statistics: fuse_c and n_tile are multiples of 32, so a chunk never wraps around the channels
+                int ch0 = 0;
+                if (fmode == 1 || fmode == 2) ch0 = (n0 + c) % fC;
                 float xv[32];
                 if (fmode >= 2) {
 #pragma unroll
@@ -288,15 +307,23 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                         }
                     }
                     if (c + 32 < p.n_tile) load_x(c + 32);
+                    if (fmode == 2) {
+                        const float4* pr_base = s_prm + grp * fC + ch0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float z = xv[j];
-                        if (fmode == 2) {
-                            const float4 pr = s_prm[grp * fC + ch0 + j];
-                            z = fmaf(xv[j], pr.z, pr.w);
-                            xv[j] = (xv[j] - pr.x) * pr.y;          // xhat
+                        for (int jb = 0; jb < 32; jb += 8) {
+                            float4 pr[8];                       // (mean, rstd, scale, shift) of 8 columns, loaded together
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pr[j] = pr_base[jb + j];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float z = fmaf(xv[jb + j], pr[j].z, pr[j].w);
+                                f[jb + j] *= z > 0.f ? 1.f : neg_slope;
+                                xv[jb + j] = (xv[jb + j] - pr[j].x) * pr[j].y;          // xhat
+                            }
                         }
-                        f[j] *= fuse_act_grad(z, p.fuse_act, p.fuse_slope);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] *= xv[j] > 0.f ? 1.f : neg_slope;
                     }
                 }
                 uint32_t pk[16];
@@ -304,23 +331,30 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                 if (valid) {
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j * 8 < cols) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (full_chunk) {
+                        dst[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+                        dst[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    }
                 }
                 if (fmode == 1 || fmode == 2) {
                     // statistics of exactly what was stored (the bf16-rounded values), rows outside the tensor excluded
                     float s1[32];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        f[2 * j] = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-                        f[2 * j + 1] = valid ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
+                        f[2 * j] = __uint_as_float(pk[j] << 16);
+                        f[2 * j + 1] = __uint_as_float(pk[j] & 0xFFFF0000u);
+                    }
+                    if (!all_valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) s1[j] = f[j] * (fmode == 1 ? f[j] : xv[j]);
                     const float t0 = warp_colsum32(f, lane);
                     const float t1 = warp_colsum32(s1, lane);
-                    if (lane < cols) {
+                    if (lane < 16 || full_chunk) {
                         atomicAdd(gs0 + ch0 + lane, t0);
                         atomicAdd(gs1 + ch0 + lane, t1);
                     }
@@ -654,7 +688,10 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        for (auto fn : {igemm_fprop_kernel<0>, igemm_fprop_kernel<1>, igemm_fprop_kernel<2>, igemm_fprop_kernel<3>}) {
+            const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) attr_err = e;
+        }
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int stage_bytes = (p.tps > 1 ? p.tps : 1) * (128 + p.n_tile) * p.kchunk * 2;
@@ -668,7 +705,12 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
         cudaError_t e = cudaMemsetAsync(p.splitk_acc, 0, out_elems * sizeof(float), stream);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
-    igemm_fprop_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+    switch (p.fuse_mode) {
+        case 1: igemm_fprop_kernel<1><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        case 2: igemm_fprop_kernel<2><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        case 3: igemm_fprop_kernel<3><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        default: igemm_fprop_kernel<0><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     if (ksplit > 1) {
