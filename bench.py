@@ -206,6 +206,11 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t)
 
+    # ---- dominant kernel (igemm_fprop_kernel: every forward / dgrad contraction of the step), timed live: one more
+    # step is run launch by launch (no graph) with a CUDA-event pair around each tensor-core launch on its stream.
+    # Every rank runs it (the step contains the gradient all-reduce).
+    dom = _dominant_kernel(torch, step, dev_pool[0], epoch, ms_per_step)
+
     if rank != 0:
         _finish(world)
         return 0
@@ -233,10 +238,22 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else None,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peaks["sustained"], "traffic": None,
-                     "what": "whole step: algorithmic conv+linear FLOPs (6.245 GFLOP/image) / step time, vs sustained "
-                             "bf16 peak, " + peaks["source"],
+        "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["sustained"], "unit": "TFLOP/s",
+                     "frac": dom["tflops"] / peaks["sustained"], "traffic": dom["traffic"],
+                     "kernel": "igemm_fprop_kernel", "launches_per_step": dom["launches"],
+                     "gflop_per_launch": dom["gflop_per_launch"], "us_per_launch": dom["us_per_launch"],
+                     "share_of_step": dom["share"], "share_basis": "sum of this kernel's event-bracketed launch times / "
+                     "sum over all %d C-ABI calls of the step (%.2f ms serialised; the graph overlaps the wgrad "
+                     "stream and replays in %.2f ms)" % (dom["timed_calls"], dom["timed_ms"], dom["graph_ms_per_step"]),
+                     "traffic_source": dom["traffic_source"],
+                     "what": "dominant kernel = the tcgen05 implicit-GEMM kernel behind every forward / dgrad "
+                             "contraction: algorithmic FLOPs (2 x MACs over the valid channels) of its launches in one "
+                             "step / their summed durations (CUDA events around each launch, eager replay of the same "
+                             "step, wgrad stream overlapping as in the graph); peak = sustained bf16, "
+                             + peaks["source"],
+                     "wgrad_kernel": dom["wgrad"],
+                     "whole_step": {"achieved": achieved_tflops, "frac": achieved_tflops / peaks["sustained"],
+                                    "what": "6.245 GFLOP/image x batch / step time"},
                      "kernels": kernels},
         "cpu_baseline": cpu,
         "final_total_loss": final_total,
@@ -253,6 +270,42 @@ def _finish(world: int):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):
+    """Every C-ABI call of one eagerly replayed step bracketed by CUDA events on its launching stream
+    (vaegan_b200._lib.LaunchTimer); the tcgen05 fprop-type kernel's launches are summed for the roofline."""
+    from importlib import import_module
+    lib = import_module("vaegan_b200._lib")
+    was_graph = step.use_graph
+    step.use_graph = False
+    try:
+        step.step(batch, epoch)                      # eager warm-up of this code path
+        torch.cuda.synchronize()
+        lib.LaunchTimer.start()
+        step.step(batch, epoch)
+        recs = lib.LaunchTimer.stop()
+    finally:
+        step.use_graph = was_graph
+    all_ms = sum(ms for _, _, _, ms in recs)
+    out = {}
+    for kind in ("fprop", "wgrad"):
+        sel = [(f, ms) for _, tag, f, ms in recs if tag == kind]
+        n, flops, ms = len(sel), sum(f for f, _ in sel), sum(m for _, m in sel)
+        out[kind] = {"launches": n, "gflop_per_launch": flops / n / 1e9, "us_per_launch": ms / n * 1e3,
+                     "tflops": flops / (ms * 1e-3) / 1e12, "ms_per_step": ms}
+    traffic, src = None, "no ncu capture committed"
+    path = os.path.join(ROOT, "profiles", "fprop_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            t = json.load(f)
+        traffic, src = t["dram_bytes_per_launch"], t["source"]
+    d = out["fprop"]
+    return {"tflops": d["tflops"], "launches": d["launches"], "gflop_per_launch": d["gflop_per_launch"],
+            "us_per_launch": d["us_per_launch"], "share": d["ms_per_step"] / all_ms,
+            "timed_calls": len(recs), "timed_ms": all_ms, "graph_ms_per_step": graph_ms_per_step,
+            "traffic": traffic, "traffic_source": src,
+            "wgrad": {k: out["wgrad"][k] for k in ("launches", "gflop_per_launch", "us_per_launch", "tflops")}}
 
 
 def _kernel_microbench(torch, vb, dev):

@@ -118,8 +118,38 @@ def check(rc: int, what: str) -> None:
         raise VaeganB200Error(f"{what} failed ({rc}): {last_error()}")
 
 
-def call(name: str, *args) -> None:
+class LaunchTimer:
+    """Optional per-call timing for bench.py's roofline: while `active`, every C-ABI call is bracketed by a CUDA-event
+    pair on the current (= launching) stream and tagged with the algorithmic FLOPs the caller states.  Off by
+    default - nothing is recorded on the training path."""
+    active = False
+    records: list = []
+
+    @classmethod
+    def start(cls) -> None:
+        cls.active, cls.records = True, []
+
+    @classmethod
+    def stop(cls):
+        """-> [(entry point, tag, flops, milliseconds)] after synchronising the device."""
+        import torch
+        cls.active = False
+        torch.cuda.synchronize()
+        out = [(name, tag, flops, a.elapsed_time(b)) for name, tag, flops, a, b in cls.records]
+        cls.records = []
+        return out
+
+
+def call(name: str, *args, flops: float = 0.0, tag: str = "") -> None:
     """Invoke an int-returning entry point and raise RuntimeError (like the reference's torch ops) on failure."""
-    rc = getattr(load(), name)(*args)
+    if LaunchTimer.active:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(load(), name)(*args)
+        b.record()
+        LaunchTimer.records.append((name, tag, flops, a, b))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != VG_OK:
         raise VaeganB200Error(f"{name} failed ({rc}): {last_error()}")

@@ -465,20 +465,36 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackBatch
         const int tb = static_cast<int>((t / kchunks) % tiles_b);
         const int ts = static_cast<int>(t / (static_cast<long long>(kchunks) * tiles_b));
         const int s0 = ts * kPackT, b0 = tb * kPackT, k0 = kc * kPackK, nk = min(kPackK, kk - k0);
-        const int span = kPackT * nk;                       // (big_c, tap) elements of one small_c row of the tile
-        for (int e = threadIdx.x; e < kPackT * span; e += blockDim.x) {
-            const int s_l = e / span, rem = e - s_l * span;
-            const int bi_l = rem / nk, tp = rem - bi_l * nk;
-            const int s = s0 + s_l, bi = b0 + bi_l;
-            float v = 0.f;
-            if (s < sc && bi < bcv) v = __ldg(it.w + (static_cast<long long>(s) * bcv + bi) * kk + k0 + tp);
-            tile[tp * kPackPlane + s_l * kPackRow + bi_l] = __float2bfloat16_rn(v);
+        if (kk == 16 && (reinterpret_cast<uintptr_t>(it.w) & 15) == 0) {
+            // 4x4 kernels (every stride-2 layer): 16-byte loads of four taps, no integer division
+            for (int e = threadIdx.x; e < kPackT * kPackT * 4; e += blockDim.x) {
+                const int s_l = e >> 7, bi_l = (e >> 2) & 31, q4 = e & 3;
+                const int s = s0 + s_l, bi = b0 + bi_l;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s < sc && bi < bcv)
+                    v = __ldg(reinterpret_cast<const float4*>(it.w + (static_cast<long long>(s) * bcv + bi) * 16) + q4);
+                __nv_bfloat16* t4 = tile + (q4 * 4) * kPackPlane + s_l * kPackRow + bi_l;
+                t4[0] = __float2bfloat16_rn(v.x);
+                t4[kPackPlane] = __float2bfloat16_rn(v.y);
+                t4[2 * kPackPlane] = __float2bfloat16_rn(v.z);
+                t4[3 * kPackPlane] = __float2bfloat16_rn(v.w);
+            }
+        } else {
+            const int span = kPackT * nk;                   // (big_c, tap) elements of one small_c row of the tile
+            for (int e = threadIdx.x; e < kPackT * span; e += blockDim.x) {
+                const int s_l = e / span, rem = e - s_l * span;
+                const int bi_l = rem / nk, tp = rem - bi_l * nk;
+                const int s = s0 + s_l, bi = b0 + bi_l;
+                float v = 0.f;
+                if (s < sc && bi < bcv) v = __ldg(it.w + (static_cast<long long>(s) * bcv + bi) * kk + k0 + tp);
+                tile[tp * kPackPlane + s_l * kPackRow + bi_l] = __float2bfloat16_rn(v);
+            }
         }
         __syncthreads();
         constexpr int kHalf = kPackT / 2;
         if (wd != nullptr) {
             for (int e = threadIdx.x; e < nk * kPackT * kHalf; e += blockDim.x) {
-                const int bp = e % kHalf, s_l = (e / kHalf) % kPackT, tp = e / (kHalf * kPackT);
+                const int bp = e & (kHalf - 1), s_l = (e >> 4) & (kPackT - 1), tp = e >> 9;
                 const int s = s0 + s_l, bi = b0 + 2 * bp;
                 if (s < sc && bi < bc)
                     *reinterpret_cast<__nv_bfloat162*>(wd + (static_cast<long long>(k0 + tp) * sc + s) * bc + bi) =
@@ -487,7 +503,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackBatch
         }
         if (wu != nullptr) {
             for (int e = threadIdx.x; e < nk * kPackT * kHalf; e += blockDim.x) {
-                const int sp = e % kHalf, bi_l = (e / kHalf) % kPackT, tp = e / (kHalf * kPackT);
+                const int sp = e & (kHalf - 1), bi_l = (e >> 4) & (kPackT - 1), tp = e >> 9;
                 const int s = s0 + 2 * sp, bi = b0 + bi_l;
                 if (s < sc && bi < bc) {
                     __nv_bfloat162 h;

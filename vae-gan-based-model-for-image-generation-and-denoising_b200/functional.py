@@ -86,6 +86,19 @@ def pack_weights(w: torch.Tensor, g: VgConvGeom) -> Tuple[torch.Tensor, torch.Te
     return wd, wu
 
 
+def conv_flops(g: VgConvGeom) -> float:
+    """Algorithmic FLOPs of one contraction over this geometry: 2 x MACs over the VALID channels."""
+    bc = g.big_c_valid if g.big_c_valid > 0 else g.big_c
+    return 2.0 * g.batch * g.small_h * g.small_w * g.small_c * bc * g.kernel * g.kernel
+
+
+def _conv_tag(g: VgConvGeom, kind: str) -> str:
+    """Which kernel family the C-ABI dispatches this geometry to (for bench.py's per-kernel accounting)."""
+    if g.small_c == 1 and g.small_h == 1 and g.small_w == 1:
+        return "gemv"
+    return kind
+
+
 def make_epilogue(mode: int, groups: int = 1, channels: int = 0, act: int = ACT_NONE, slope: float = 0.0,
                   sums: Optional[torch.Tensor] = None, x: Optional[torch.Tensor] = None,
                   stats: Optional[torch.Tensor] = None) -> VgEpilogue:
@@ -106,23 +119,25 @@ def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[
     small = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=out_dtype, device=big.device)
     if ep is not None:
         call("vg_conv_down_ex", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), ctypes.byref(ep),
-             _stream())
+             _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
         return small
     ws, nbytes = None, 0
     if big.dtype == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
         nbytes = _lib.load().vg_conv_down_workspace_bytes(ctypes.byref(g))
         ws = _ws(nbytes, big.device)
     call("vg_conv_down", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), int(out_f32), _p(ws),
-         nbytes, _stream())
+         nbytes, _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
     return small
 
 
 def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[VgEpilogue] = None) -> torch.Tensor:
     big = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
     if ep is not None:
-        call("vg_conv_up_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), ctypes.byref(ep), _stream())
+        call("vg_conv_up_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), ctypes.byref(ep), _stream(),
+             flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
     else:
-        call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), _stream())
+        call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), _stream(),
+             flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
     return big
 
 
@@ -133,7 +148,8 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
                          device=small.device)
     nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
     ws = _ws(nbytes, small.device) if nbytes else None
-    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream())
+    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream(),
+         flops=conv_flops(g), tag=_conv_tag(g, "wgrad"))
     if ws is not None and WgradOverlap.stream is not None:
         WgradOverlap.keepalive.append(ws)
     return dw
