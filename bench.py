@@ -242,6 +242,7 @@ def run_gpu_arm(args):
                      "frac": dom["tflops"] / peaks["sustained"], "traffic": dom["traffic"],
                      "kernel": "igemm_fprop_kernel", "launches_per_step": dom["launches"],
                      "gflop_per_launch": dom["gflop_per_launch"], "us_per_launch": dom["us_per_launch"],
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                      "share_of_step": dom["share"], "share_basis": "sum of this kernel's event-bracketed launch times / "
                      "sum over all %d C-ABI calls of the step (%.2f ms serialised; the graph overlaps the wgrad "
                      "stream and replays in %.2f ms)" % (dom["timed_calls"], dom["timed_ms"], dom["graph_ms_per_step"]),
@@ -287,13 +288,13 @@ def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):
         recs = lib.LaunchTimer.stop()
     finally:
         step.use_graph = was_graph
-    all_ms = sum(ms for _, _, _, ms in recs)
+    all_ms = sum(r[-1] for r in recs)
     out = {}
     for kind in ("fprop", "wgrad"):
-        sel = [(f, ms) for _, tag, f, ms in recs if tag == kind]
-        n, flops, ms = len(sel), sum(f for f, _ in sel), sum(m for _, m in sel)
+        sel = [(f, nb, ms) for _, tag, f, nb, ms in recs if tag == kind]
+        n, flops, nb, ms = len(sel), sum(r[0] for r in sel), sum(r[1] for r in sel), sum(r[2] for r in sel)
         out[kind] = {"launches": n, "gflop_per_launch": flops / n / 1e9, "us_per_launch": ms / n * 1e3,
-                     "tflops": flops / (ms * 1e-3) / 1e12, "ms_per_step": ms}
+                     "tflops": flops / (ms * 1e-3) / 1e12, "ms_per_step": ms, "algorithmic_bytes_per_launch": nb / n}
     traffic, src = None, "no ncu capture committed"
     path = os.path.join(ROOT, "profiles", "fprop_traffic.json")
     if os.path.isfile(path):
@@ -303,6 +304,7 @@ def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):
     d = out["fprop"]
     return {"tflops": d["tflops"], "launches": d["launches"], "gflop_per_launch": d["gflop_per_launch"],
             "us_per_launch": d["us_per_launch"], "share": d["ms_per_step"] / all_ms,
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
             "timed_calls": len(recs), "timed_ms": all_ms, "graph_ms_per_step": graph_ms_per_step,
             "traffic": traffic, "traffic_source": src,
             "wgrad": {k: out["wgrad"][k] for k in ("launches", "gflop_per_launch", "us_per_launch", "tflops")}}

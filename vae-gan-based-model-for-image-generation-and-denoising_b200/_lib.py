@@ -131,16 +131,16 @@ class LaunchTimer:
 
     @classmethod
     def stop(cls):
-        """-> [(entry point, tag, flops, milliseconds)] after synchronising the device."""
+        """-> [(entry point, tag, flops, algorithmic bytes, milliseconds)] after synchronising the device."""
         import torch
         cls.active = False
         torch.cuda.synchronize()
-        out = [(name, tag, flops, a.elapsed_time(b)) for name, tag, flops, a, b in cls.records]
+        out = [(name, tag, flops, nb, a.elapsed_time(b)) for name, tag, flops, nb, a, b in cls.records]
         cls.records = []
         return out
 
 
-def call(name: str, *args, flops: float = 0.0, tag: str = "") -> None:
+def call(name: str, *args, flops: float = 0.0, tag: str = "", nbytes: float = 0.0) -> None:
     """Invoke an int-returning entry point and raise RuntimeError (like the reference's torch ops) on failure."""
     if LaunchTimer.active:
         import torch
@@ -148,7 +148,7 @@ def call(name: str, *args, flops: float = 0.0, tag: str = "") -> None:
         a.record()
         rc = getattr(load(), name)(*args)
         b.record()
-        LaunchTimer.records.append((name, tag, flops, a, b))
+        LaunchTimer.records.append((name, tag, flops, nbytes, a, b))
     else:
         rc = getattr(load(), name)(*args)
     if rc != VG_OK:

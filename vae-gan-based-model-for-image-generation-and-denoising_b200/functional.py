@@ -92,6 +92,14 @@ def conv_flops(g: VgConvGeom) -> float:
     return 2.0 * g.batch * g.small_h * g.small_w * g.small_c * bc * g.kernel * g.kernel
 
 
+def conv_bytes(g: VgConvGeom, extra_big: int = 0, extra_small: int = 0) -> float:
+    """Algorithmic HBM bytes of one bf16 contraction: both activation tensors once (+ the saved tensor a fused
+    epilogue reads on the output side) and the packed weights once."""
+    big = g.batch * g.big_h * g.big_w * g.big_c
+    small = g.batch * g.small_h * g.small_w * g.small_c
+    return 2.0 * ((1 + extra_big) * big + (1 + extra_small) * small + g.small_c * g.big_c * g.kernel * g.kernel)
+
+
 def _conv_tag(g: VgConvGeom, kind: str) -> str:
     """Which kernel family the C-ABI dispatches this geometry to (for bench.py's per-kernel accounting)."""
     if g.small_c == 1 and g.small_h == 1 and g.small_w == 1:
@@ -119,14 +127,14 @@ def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[
     small = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=out_dtype, device=big.device)
     if ep is not None:
         call("vg_conv_down_ex", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), ctypes.byref(ep),
-             _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
+             _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, 0, int(ep.mode >= 2)))
         return small
     ws, nbytes = None, 0
     if big.dtype == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
         nbytes = _lib.load().vg_conv_down_workspace_bytes(ctypes.byref(g))
         ws = _ws(nbytes, big.device)
     call("vg_conv_down", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), int(out_f32), _p(ws),
-         nbytes, _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
+         nbytes, _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g))
     return small
 
 
@@ -134,10 +142,10 @@ def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[Vg
     big = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
     if ep is not None:
         call("vg_conv_up_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), ctypes.byref(ep), _stream(),
-             flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
+             flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, int(ep.mode >= 2), 0))
     else:
         call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), _stream(),
-             flops=conv_flops(g), tag=_conv_tag(g, "fprop"))
+             flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g))
     return big
 
 
@@ -149,7 +157,7 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
     nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
     ws = _ws(nbytes, small.device) if nbytes else None
     call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream(),
-         flops=conv_flops(g), tag=_conv_tag(g, "wgrad"))
+         flops=conv_flops(g), tag=_conv_tag(g, "wgrad"), nbytes=conv_bytes(g))
     if ws is not None and WgradOverlap.stream is not None:
         WgradOverlap.keepalive.append(ws)
     return dw
