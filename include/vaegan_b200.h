@@ -196,6 +196,18 @@ int vg_colsum(const void* x, VgDType dt, long long rows, int channels, float* ou
  * The NHWC side may carry dst_channels >= channels per pixel (extra channels are written as zeros / ignored). */
 int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, VgDType dt, int batch, int channels, int h, int w,
                     int dst_channels, int mode, float sigma, int clamp, void* stream);
+/* Space-to-depth image tensors (bf16 path): a <= 16-channel H x W image as [batch][H/2+o][W/2+o][64], block (Y, X),
+ * sub-pixel (sy, sx), channel c at slot (sy*2+sx)*16 + c  <->  pixel (2Y-o+sy, 2X-o+sx), zeros elsewhere (o = origin =
+ * the padding of the 4x4 stride-2 convolution that reads it).  In this form the image-side convolutions of the
+ * reference (main_vae.py:37 first ConvBlock, gan_code.py:49 last ConvTranspose2d, gan_code.py:59 first Conv2d) are
+ * ordinary 64-channel convolutions with 128-byte pixel rows.  Modes as vg_nchw_to_nhwc. */
+int vg_nchw_to_s2d(const float* src, const float* aux, void* dst, int batch, int channels, int h, int w, int origin,
+                   int mode, float sigma, int clamp, void* stream);
+int vg_s2d_to_nchw(const void* src, float* dst, int batch, int channels, int h, int w, int origin, VgAct act,
+                   float slope, void* stream);
+/* dst[i] (+)= sum_{j<fan} src[idx[i*fan+j]] (negative index = no term): builds the equivalent 64-channel weights of
+ * the space-to-depth convolutions from the reference-layout masters and folds their gradients back. */
+int vg_gather_f32(float* dst, const float* src, const int* idx, long long n, int fan, int accumulate, void* stream);
 /* NHWC dtype -> fp32 NCHW with an optional activation (Tanh of gan_code.py:50). */
 int vg_nhwc_to_nchw(const void* src, VgDType dt, int src_channels, float* dst, int batch, int channels, int h, int w,
                     VgAct act, float slope, void* stream);

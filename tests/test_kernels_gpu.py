@@ -134,6 +134,40 @@ def test_pack_weights_bit_exact(sc, bc, bcv, k):
     assert torch.equal(ou.cpu(), o_ref.permute(2, 1, 0).contiguous())
 
 
+@pytest.mark.parametrize("origin", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_s2d_layout_kernels(origin, mode):
+    """vg_nchw_to_s2d / vg_s2d_to_nchw against the CPU definition of the space-to-depth image layout
+    (tests/test_s2d_cpu.py::s2d), including the fused noise (mode 1) and Tanh-backward (mode 2) forms."""
+    from tests.test_s2d_cpu import s2d
+    fn = _fn()
+    gen = torch.Generator().manual_seed(origin * 3 + mode)
+    B, C, H, W = 3, 3, 12, 20
+    src, aux = torch.randn(B, C, H, W, generator=gen), torch.rand(B, C, H, W, generator=gen) * 2 - 1
+    ref = {0: src, 1: (src + 0.05 * aux).clamp(-1, 1), 2: src * (1 - aux * aux)}[mode]
+    got = fn.nchw_to_nhwc(src.cuda(), torch.bfloat16, aux=aux.cuda() if mode else None, mode=mode, sigma=0.05,
+                          clamp=(mode == 1), s2d_origin=origin)
+    torch.cuda.synchronize()
+    assert got.shape == (B, H // 2 + origin, W // 2 + origin, 64)
+    assert torch.equal(got.cpu(), s2d(ref, origin).bfloat16())
+    back = fn.nhwc_to_nchw(got, fn.ACT_TANH, channels=C, s2d_origin=origin)
+    torch.cuda.synchronize()
+    assert torch.allclose(back.cpu(), torch.tanh(ref.bfloat16().float()), atol=1e-6)
+
+
+def test_gather_f32():
+    fn = _fn()
+    gen = torch.Generator().manual_seed(5)
+    src = torch.randn(1000, generator=gen)
+    idx = torch.randint(-1, 1000, (300, 4), generator=gen, dtype=torch.int32)
+    dst = torch.randn(300, generator=gen)
+    ref = dst + torch.where(idx >= 0, src[idx.clamp(min=0).long()], torch.zeros(())).sum(1)
+    d = dst.cuda()
+    fn.call("vg_gather_f32", fn._p(d), fn._p(src.cuda()), fn._p(idx.cuda()), 300, 4, 1, fn._stream())
+    torch.cuda.synchronize()
+    assert torch.allclose(d.cpu(), ref, atol=1e-6)
+
+
 FUSE_CASES = [
     # kind, B, H, W, Cin, Cout, k, s, p, groups, bias
     ("down", 8, 16, 16, 64, 128, 4, 2, 1, 2, False),     # discriminator stage, real/fake pair

@@ -908,6 +908,95 @@ __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const T* __restr
     }
 }
 
+// ---- space-to-depth ("s2d") image tensors.  A C <= 16 channel H x W image is held as bf16 [B][H/2+o][W/2+o][64]:
+// block (Y, X), sub-pixel (sy, sx), channel c sits at slot (sy*2+sx)*16 + c and is pixel (2Y-o+sy, 2X-o+sx); every other
+// slot is zero.  With 128-byte rows the stride-2 4x4 image convolutions become plain 2x2 stride-1 convolutions over 64
+// channels (origin o = the convolution's padding), which the TMA-fed tensor-core kernels run at full row efficiency.
+__global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const float* __restrict__ src,
+                                                              const float* __restrict__ aux,
+                                                              __nv_bfloat16* __restrict__ dst, int B, int C, int H, int W,
+                                                              int o, int mode, float sigma, int clamp) {
+    const int bh = H / 2 + o, bw = W / 2 + o;
+    const long long total = static_cast<long long>(B) * bh * bw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(i % bw);
+        const int Y = static_cast<int>((i / bw) % bh);
+        const long long b = i / (static_cast<long long>(bw) * bh);
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+            const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
+            const bool in = py >= 0 && py < H && px >= 0 && px < W;
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = 0.f;
+                if (in && c < C) {
+                    const long long s = ((b * C + c) * H + py) * W + px;
+                    float t = src[s];
+                    if (mode == 1) {
+                        t = fmaf(sigma, aux[s], t);
+                        if (clamp) t = fminf(1.f, fmaxf(-1.f, t));
+                    } else if (mode == 2) {
+                        const float y = aux[s];
+                        t *= (1.f - y * y);
+                    }
+                    v[c] = t;
+                }
+            }
+            float lo[8], hi[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
+            Vec<__nv_bfloat16>::store(dst + i * 64 + sub * 16, lo);
+            Vec<__nv_bfloat16>::store(dst + i * 64 + sub * 16 + 8, hi);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) s2d_to_nchw_kernel(const __nv_bfloat16* __restrict__ src,
+                                                              float* __restrict__ dst, int B, int C, int H, int W, int o,
+                                                              int act, float slope) {
+    const int bh = H / 2 + o, bw = W / 2 + o;
+    const long long total = static_cast<long long>(B) * bh * bw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(i % bw);
+        const int Y = static_cast<int>((i / bw) % bh);
+        const long long b = i / (static_cast<long long>(bw) * bh);
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+            const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
+            if (py < 0 || py >= H || px < 0 || px >= W) continue;
+            float v[8];
+            Vec<__nv_bfloat16>::load(src + i * 64 + sub * 16, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < C) dst[((b * C + c) * H + py) * W + px] = act_fwd(v[c], act, slope);
+            if (C > 8) {
+                Vec<__nv_bfloat16>::load(src + i * 64 + sub * 16 + 8, v);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (8 + c < C) dst[((b * C + 8 + c) * H + py) * W + px] = act_fwd(v[c], act, slope);
+            }
+        }
+    }
+}
+
+// dst[i] (+)= sum_j src[idx[i*fan + j]]  (idx < 0 = no term): equivalent-weight construction and its gradient
+__global__ void __launch_bounds__(kThreads) gather_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                             const int* __restrict__ idx, long long n, int fan,
+                                                             int accumulate) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc = accumulate ? dst[i] : 0.f;
+        for (int j = 0; j < fan; ++j) {
+            const int k = __ldg(idx + i * fan + j);
+            if (k >= 0) acc += __ldg(src + k);
+        }
+        dst[i] = acc;
+    }
+}
+
 int grid_for(long long n) {
     return static_cast<int>(std::max<long long>(1, std::min<long long>(148 * 8, (n + kThreads - 1) / kThreads)));
 }
@@ -1162,6 +1251,48 @@ extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, Vg
     else
         nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, Cd,
                                                                           HW, mode, sigma, clamp);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_nchw_to_s2d(const float* src, const float* aux, void* dst, int B, int C, int H, int W, int origin,
+                              int mode, float sigma, int clamp, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr || (mode != 0 && aux == nullptr)) return fail(VG_ERR_ARG, "nchw_to_s2d: null pointer");
+    if (C < 1 || C > 16 || (H & 1) || (W & 1) || origin < 0 || origin > 1)
+        return fail(VG_ERR_SHAPE, "nchw_to_s2d: needs <= 16 channels, even H and W, origin 0 or 1");
+    if (reinterpret_cast<uintptr_t>(dst) & 15) return fail(VG_ERR_ALIGN, "nchw_to_s2d: 16-byte alignment");
+    const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
+    nchw_to_s2d_kernel<<<grid_for(blocks), kThreads, 0, as_stream(stream)>>>(
+        src, aux, static_cast<__nv_bfloat16*>(dst), B, C, H, W, origin, mode, sigma, clamp);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_s2d_to_nchw(const void* src, float* dst, int B, int C, int H, int W, int origin, VgAct act, float slope,
+                              void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr) return fail(VG_ERR_ARG, "s2d_to_nchw: null pointer");
+    if (C < 1 || C > 16 || (H & 1) || (W & 1) || origin < 0 || origin > 1)
+        return fail(VG_ERR_SHAPE, "s2d_to_nchw: needs <= 16 channels, even H and W, origin 0 or 1");
+    if (reinterpret_cast<uintptr_t>(src) & 15) return fail(VG_ERR_ALIGN, "s2d_to_nchw: 16-byte alignment");
+    const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
+    s2d_to_nchw_kernel<<<grid_for(blocks), kThreads, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), dst, B, C, H, W, origin, act, slope);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_gather_f32(float* dst, const float* src, const int* idx, long long n, int fan, int accumulate,
+                             void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (dst == nullptr || src == nullptr || idx == nullptr || n < 0 || fan < 1)
+        return fail(VG_ERR_ARG, "gather_f32: bad argument");
+    if (n == 0) return VG_OK;
+    gather_f32_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(dst, src, idx, n, fan, accumulate);
     VG_LAUNCHED();
     return VG_OK;
 }

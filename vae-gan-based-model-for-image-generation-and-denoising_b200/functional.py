@@ -308,9 +308,16 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, mode: int = 0, sigma: float = 0.0,
-                 clamp: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 NCHW -> internal NHWC (channel-padded per `padded_channels`)."""
+                 clamp: bool = False, out: Optional[torch.Tensor] = None, s2d_origin: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCHW -> internal NHWC (channel-padded per `padded_channels`), or, with `s2d_origin` in {0, 1}, the
+    space-to-depth image form [B, H/2+o, W/2+o, 64] (include/vaegan_b200.h, vg_nchw_to_s2d)."""
     B, C, H, W = src.shape
+    if s2d_origin is not None:
+        o = int(s2d_origin)
+        dst = out if out is not None else torch.empty((B, H // 2 + o, W // 2 + o, 64), dtype=torch.bfloat16,
+                                                      device=src.device)
+        call("vg_nchw_to_s2d", _p(src), _p(aux), _p(dst), B, C, H, W, o, mode, float(sigma), int(clamp), _stream())
+        return dst
     Cd = padded_channels(C, dtype)
     dst = out if out is not None else torch.empty((B, H, W, Cd), dtype=dtype, device=src.device)
     call("vg_nchw_to_nhwc", _p(src), _p(aux), _p(dst), _DT[dtype], B, C, H, W, Cd, mode, float(sigma), int(clamp),
@@ -318,9 +325,17 @@ def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, m
     return dst
 
 
-def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0, channels: Optional[int] = None) -> torch.Tensor:
-    """internal NHWC -> fp32 NCHW, keeping the first `channels` channels of a padded tensor."""
+def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0, channels: Optional[int] = None,
+                 s2d_origin: Optional[int] = None) -> torch.Tensor:
+    """internal NHWC -> fp32 NCHW, keeping the first `channels` channels of a padded tensor; `s2d_origin` marks a
+    space-to-depth image tensor (vg_s2d_to_nchw)."""
     B, H, W, Cs = src.shape
+    if s2d_origin is not None:
+        o = int(s2d_origin)
+        H, W = 2 * (H - o), 2 * (W - o)
+        dst = torch.empty((B, channels, H, W), dtype=torch.float32, device=src.device)
+        call("vg_s2d_to_nchw", _p(src), _p(dst), B, channels, H, W, o, act, float(slope), _stream())
+        return dst
     C = channels or Cs
     dst = torch.empty((B, C, H, W), dtype=torch.float32, device=src.device)
     call("vg_nhwc_to_nchw", _p(src), _DT[src.dtype], Cs, _p(dst), B, C, H, W, act, float(slope), _stream())
@@ -352,6 +367,98 @@ class WgradOverlap:
         cls.stream = None
 
 
+# --------------------------------------------------------------------------------------------- space-to-depth layers
+def is_image_s2d(t: torch.Tensor, true_channels: int) -> bool:
+    """An image-side activation (true_channels < 16) is either channel-padded to 16 or in space-to-depth form (64)."""
+    return true_channels < 16 and t.dtype == torch.bfloat16 and t.shape[-1] == 64
+
+
+class S2DWeightMap:
+    """The three image-side convolutions of the reference rewritten as 64-channel convolutions over space-to-depth
+    image tensors, so that their TMA rows are 128 bytes instead of one 32-byte padded pixel:
+
+      Conv2d(C, n, 4, 2, p) (main_vae.py:37 first ConvBlock p=0; gan_code.py:59 p=1)
+          == Conv2d(64, n, 2, 1, 0) over the s2d input with origin p:   weq[n][(sy,sx,c)][by][bx] = w[n][c][2by+sy][2bx+sx]
+      ConvTranspose2d(m, C, 3, 1, 1) (gan_code.py:49)
+          == Conv2d(m, 64, 4, 2, 1) whose OUTPUT is the s2d image (origin 0):
+                                                    weq[(sy,sx,c)][m][KY][KX] = w[m][c][sy+2-KY][sx+2-KX]  (0 outside)
+
+    The masters keep the reference layout; `materialize` gathers the equivalent weights (one tiny kernel) and
+    `scatter` folds the equivalent weight gradient back (each master element is the sum of 1 resp. 4 terms)."""
+
+    @staticmethod
+    def eligible(spec: "ConvSpec") -> bool:
+        if spec.big_c >= 16:
+            return False
+        if spec.kind == "down":
+            return spec.kernel == 4 and spec.stride == 2 and spec.pad in (0, 1)
+        return spec.kernel == 3 and spec.stride == 1 and spec.pad == 1
+
+    def __init__(self, spec: "ConvSpec"):
+        import numpy as np
+        self.spec = spec
+        C = spec.big_c
+        if spec.kind == "down":
+            n = spec.small_c
+            self.eq_spec = ConvSpec("down", n, 64, 2, 1, 0)
+            self.origin = spec.pad
+            fwd = np.full((n, 64, 2, 2), -1, dtype=np.int32)
+            bwd = np.full((n, C, 4, 4, 1), -1, dtype=np.int32)
+            master = np.arange(n * C * 16, dtype=np.int32).reshape(n, C, 4, 4)
+            eq = np.arange(n * 64 * 4, dtype=np.int32).reshape(n, 64, 2, 2)
+            for ky in range(4):
+                for kx in range(4):
+                    by, sy, bx, sx = ky >> 1, ky & 1, kx >> 1, kx & 1
+                    slot = (sy * 2 + sx) * 16
+                    fwd[:, slot:slot + C, by, bx] = master[:, :, ky, kx]
+                    bwd[:, :, ky, kx, 0] = eq[:, slot:slot + C, by, bx]
+        else:
+            m = spec.small_c
+            self.eq_spec = ConvSpec("down", 64, m, 4, 2, 1)
+            self.origin = 0
+            fwd = np.full((64, m, 4, 4), -1, dtype=np.int32)
+            bwd = np.full((m, C, 3, 3, 4), -1, dtype=np.int32)
+            master = np.arange(m * C * 9, dtype=np.int32).reshape(m, C, 3, 3)
+            eq = np.arange(64 * m * 16, dtype=np.int32).reshape(64, m, 4, 4)
+            for sy in range(2):
+                for sx in range(2):
+                    slot = (sy * 2 + sx) * 16
+                    for KY in range(4):
+                        for KX in range(4):
+                            ky, kx = sy + 2 - KY, sx + 2 - KX
+                            if 0 <= ky <= 2 and 0 <= kx <= 2:
+                                fwd[slot:slot + C, :, KY, KX] = master[:, :, ky, kx].T
+                                bwd[:, :, ky, kx, sy * 2 + sx] = eq[slot:slot + C, :, KY, KX].T
+        self.fan = bwd.shape[-1]
+        self._fwd_np, self._bwd_np = fwd.reshape(-1), bwd.reshape(-1)
+        self._dev = {}
+
+    def _tensors(self, device):
+        t = self._dev.get(device)
+        if t is None:
+            e = self.eq_spec
+            t = dict(fwd=torch.from_numpy(self._fwd_np).to(device), bwd=torch.from_numpy(self._bwd_np).to(device),
+                     weq=torch.empty((e.small_c, e.big_c, e.kernel, e.kernel), dtype=torch.float32, device=device),
+                     dweq=torch.empty((e.small_c, e.big_c, e.kernel, e.kernel), dtype=torch.float32, device=device))
+            self._dev[device] = t
+        return t
+
+    def materialize(self, master: torch.Tensor) -> torch.Tensor:
+        t = self._tensors(master.device)
+        call("vg_gather_f32", _p(t["weq"]), _p(_contig(master)), _p(t["fwd"]), t["weq"].numel(), 1, 0, _stream())
+        return t["weq"]
+
+    def grad_buffer(self, device) -> torch.Tensor:
+        t = self._tensors(device)
+        t["dweq"].zero_()
+        return t["dweq"]
+
+    def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
+        """target (master layout, fp32, contiguous) += the equivalent-weight gradient folded back."""
+        t = self._tensors(dweq.device)
+        call("vg_gather_f32", _p(target), _p(dweq), _p(t["bwd"]), target.numel(), self.fan, 1, _stream())
+
+
 # --------------------------------------------------------------------------------------------- weight cache
 class PackedWeights:
     """bf16 K-major copies of one fp32 master weight, refreshed when the master changes.  L1 (drop-in modules):
@@ -376,10 +483,12 @@ class PackedWeights:
             self.wu = torch.empty((kk, big_c, small_c), dtype=torch.bfloat16, device=w.device)
         self.version, self.key = w._version, (w.data_ptr(), small_c, big_c, kernel)
 
-    def get(self, w: torch.Tensor, g: VgConvGeom):
+    def get(self, w: torch.Tensor, g: VgConvGeom, wmap: Optional[S2DWeightMap] = None):
+        """`w` is the fp32 master; with `wmap` the copies are packed from its equivalent space-to-depth weights."""
         key = (w.data_ptr(), g.small_c, g.big_c, g.kernel)
         if self.version != w._version or self.key != key:
-            self.wd, self.wu = pack_weights(w.detach(), g)
+            src = wmap.materialize(w.detach()) if wmap is not None else w.detach()
+            self.wd, self.wu = pack_weights(src, g)
             self.version, self.key = w._version, key
         return self.wd, self.wu
 
@@ -391,9 +500,13 @@ def pack_layers(layers, dtype) -> None:
     items = (_lib.VgPackItem * len(layers))()
     for i, layer in enumerate(layers):
         sp, w = layer.spec, layer.conv.weight
+        wmap = getattr(layer, "wmap", None) if getattr(layer, "s2d_active", False) else None
+        src = w
+        if wmap is not None:                    # image layer running in space-to-depth form: pack its equivalent weights
+            sp, src = wmap.eq_spec, wmap.materialize(w.detach())
         bc = padded_channels(sp.big_c, dtype)
         layer.cache.stage(w, sp.small_c, bc, sp.kernel)
-        items[i] = _lib.VgPackItem(w.data_ptr(), layer.cache.wd.data_ptr(), layer.cache.wu.data_ptr(), sp.small_c, bc,
+        items[i] = _lib.VgPackItem(src.data_ptr(), layer.cache.wd.data_ptr(), layer.cache.wu.data_ptr(), sp.small_c, bc,
                                    sp.big_c if bc != sp.big_c else 0, sp.kernel * sp.kernel)
     call("vg_pack_weights_multi", items, len(layers), _stream())
 
@@ -426,7 +539,9 @@ class ConvLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, spec: ConvSpec, act: int, slope: float, bn, training: bool,
                 cache: PackedWeights, out_f32: bool, groups: int = 1, link_in: Optional[LayerLink] = None,
-                link_out: Optional[LayerLink] = None):
+                link_out: Optional[LayerLink] = None, wmap: Optional[S2DWeightMap] = None):
+        """`wmap`: the layer runs in space-to-depth form - `spec` is then the EQUIVALENT convolution (S2DWeightMap),
+        `weight` still the reference-layout master."""
         """`groups` > 1: the batch holds that many independent sub-batches (e.g. the discriminator's real and fake
         batches of vaegan_code.py:96-97 run through ONE convolution launch); BatchNorm statistics, running-stat
         updates and the BN backward stay per sub-batch, in order, exactly as separate forward calls would."""
@@ -444,7 +559,7 @@ class ConvLayerFn(torch.autograd.Function):
                                    f"{spec.small_c} channels, but got {Cx} channels instead")
             g = spec.geom(B, H, W, padded_channels(spec.big_c, x.dtype))
         if x.dtype == torch.bfloat16:
-            wd, wu = cache.get(weight, g)
+            wd, wu = cache.get(weight, g, wmap)
             w_fwd = wd if spec.kind == "down" else wu
         else:
             w_fwd = _contig(weight.detach())
@@ -497,7 +612,7 @@ class ConvLayerFn(torch.autograd.Function):
         ctx.has_bn, ctx.bn_training, ctx.cache, ctx.out_f32 = bn is not None, training, cache, out_f32
         ctx.groups = groups
         ctx.params = (weight, bias, gamma, beta)
-        ctx.link_in, ctx.link_out = link_in, None
+        ctx.link_in, ctx.link_out, ctx.wmap = link_in, None, wmap
         if (link_out is not None and x.dtype == torch.bfloat16 and not out_f32 and act in (ACT_NONE, ACT_RELU, ACT_LEAKY)
                 and (bn is None or training) and (bn is not None or act != ACT_NONE)):
             link_out.raw, link_out.stats, link_out.act, link_out.slope, link_out.groups = raw, stats, act, slope, groups
@@ -562,17 +677,29 @@ class ConvLayerFn(torch.autograd.Function):
         if need_w:
             main_grad = getattr(weight, "main_grad", None)
             side = WgradOverlap.stream
+            wmap = ctx.wmap
+
+            def run_wgrad():
+                if wmap is None:
+                    return conv_wgrad(small, big, g, main_grad)
+                # space-to-depth layer: gradient of the equivalent weights, folded back into the master layout
+                dweq = conv_wgrad(small, big, g, wmap.grad_buffer(small.device))
+                target = main_grad if main_grad is not None else torch.zeros(weight.shape, dtype=torch.float32,
+                                                                             device=small.device)
+                wmap.scatter(dweq, target)
+                return target
+
             if side is not None and main_grad is not None:
                 side.wait_stream(torch.cuda.current_stream())          # d_raw (and x) are complete
                 with torch.cuda.stream(side):
-                    dw = conv_wgrad(small, big, g, main_grad)
+                    dw = run_wgrad()
                 WgradOverlap.keepalive.append((small, big))
             else:
-                dw = conv_wgrad(small, big, g, main_grad)
+                dw = run_wgrad()
             dw = dw.view(weight.shape)
         if need_x:
             if x.dtype == torch.bfloat16:
-                wd, wu = ctx.cache.get(weight, g)
+                wd, wu = ctx.cache.get(weight, g, ctx.wmap)
                 w_bwd = wu if spec.kind == "down" else wd
             else:
                 w_bwd = _contig(weight.detach())
@@ -593,23 +720,23 @@ class ConvLayerFn(torch.autograd.Function):
                 link_in.sums, link_in.fused = sums, True
         return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
                 _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 class ToNHWCFn(torch.autograd.Function):
     """fp32 NCHW module input -> internal NHWC activation (and the reverse for its gradient)."""
 
     @staticmethod
-    def forward(ctx, x, dtype):
+    def forward(ctx, x, dtype, s2d_origin=None):
         _require_cuda(x, "ToNHWCFn")
         if x.dtype != torch.float32:
             raise _lib.VaeganB200Error(f"module inputs must be float32 (got {x.dtype}), like the reference's loaders")
-        ctx.channels = x.shape[1]
-        return nchw_to_nhwc(_contig(x), dtype)
+        ctx.channels, ctx.s2d_origin = x.shape[1], s2d_origin
+        return nchw_to_nhwc(_contig(x), dtype, s2d_origin=s2d_origin)
 
     @staticmethod
     def backward(ctx, dy):
-        return nhwc_to_nchw(_contig(dy), channels=ctx.channels), None
+        return nhwc_to_nchw(_contig(dy), channels=ctx.channels, s2d_origin=ctx.s2d_origin), None, None
 
 
 class ToNCHWActFn(torch.autograd.Function):
@@ -617,7 +744,9 @@ class ToNCHWActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, act, channels=None):
-        y = nhwc_to_nchw(_contig(x), act, channels=channels)
+        # an image-side tensor (< 16 true channels) with 64 slots per pixel block is in space-to-depth form, origin 0
+        ctx.s2d = 0 if (channels is not None and is_image_s2d(x, channels)) else None
+        y = nhwc_to_nchw(_contig(x), act, channels=channels, s2d_origin=ctx.s2d)
         ctx.act, ctx.dtype = act, x.dtype
         ctx.save_for_backward(y if act == ACT_TANH else None)
         return y
@@ -627,8 +756,8 @@ class ToNCHWActFn(torch.autograd.Function):
         (y,) = ctx.saved_tensors
         dy = _contig(dy)
         if ctx.act == ACT_TANH:
-            return nchw_to_nhwc(dy, ctx.dtype, aux=y, mode=2), None, None
-        return nchw_to_nhwc(dy, ctx.dtype), None, None
+            return nchw_to_nhwc(dy, ctx.dtype, aux=y, mode=2, s2d_origin=ctx.s2d), None, None
+        return nchw_to_nhwc(dy, ctx.dtype, s2d_origin=ctx.s2d), None, None
 
 
 class PointwiseActFn(torch.autograd.Function):

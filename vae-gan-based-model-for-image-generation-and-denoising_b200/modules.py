@@ -66,14 +66,34 @@ class _Layer:
         self.conv, self.bn, self.act, self.slope = conv, bn, act, slope
         self.spec = _spec_of(conv)
         self.cache = F_.PackedWeights()
+        # image-side layers (3 channels) can run as 64-channel convolutions over space-to-depth image tensors
+        self.wmap = None
+        if F_.S2DWeightMap.eligible(self.spec) and (self.spec.kind == "down" or conv.bias is None):
+            self.wmap = F_.S2DWeightMap(self.spec)
+        self.s2d_active = False
+
+    def input_s2d_origin(self, dtype, h: int, w: int):
+        """Space-to-depth origin this layer wants for an IMAGE input of h x w (None = plain channel-padded NHWC)."""
+        if self.wmap is None or self.spec.kind != "down" or dtype != torch.bfloat16 or (h | w) & 1:
+            return None
+        return self.wmap.origin
 
     def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1,
                  link_in=None, link_out=None):
         bn = self.bn
         act = self.act if fuse_act else ACT_NONE
+        spec, wmap = self.spec, None
+        if self.wmap is not None and x.dtype == torch.bfloat16:
+            if spec.kind == "down":
+                s2d = x.shape[-1] == 64                      # the caller converted the image with input_s2d_origin()
+            else:
+                s2d = not ((x.shape[1] | x.shape[2]) & 1)    # the image this layer produces has even extents
+            if s2d:
+                spec, wmap = self.wmap.eq_spec, self.wmap
+        self.s2d_active = wmap is not None
         return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, bn.weight if bn is not None else None,
-                                    bn.bias if bn is not None else None, self.spec, act, self.slope, bn, training,
-                                    self.cache, out_f32, groups, link_in, link_out)
+                                    bn.bias if bn is not None else None, spec, act, self.slope, bn, training,
+                                    self.cache, out_f32, groups, link_in, link_out, wmap)
 
 
 def _run_chain(layers, h, training: bool, groups: int = 1, link=None):
@@ -187,7 +207,11 @@ class Encoder(_KernelModule):
     def forward(self, x):
         if x.dim() != 4:
             raise RuntimeError(f"Expected 4D (batched) input to conv2d, but got input of size: {list(x.shape)}")
-        return self.forward_nhwc(F_.ToNHWCFn.apply(x, self._dtype()))
+        return self.forward_nhwc(F_.ToNHWCFn.apply(x, self._dtype(), self.input_s2d_origin(x.shape[2], x.shape[3])))
+
+    def input_s2d_origin(self, h: int, w: int):
+        """How forward_nhwc wants an h x w image laid out: space-to-depth origin, or None for channel-padded NHWC."""
+        return self.cnn[0]._layer().input_s2d_origin(self._dtype(), h, w)
 
     def forward_nhwc(self, h):
         """Same as forward for an input that is already an internal NHWC activation (used by the fused step)."""
@@ -211,6 +235,7 @@ class _LinearAsConv(_Layer):
         self.conv, self.bn, self.act, self.slope = linear, None, ACT_NONE, 0.0
         self.spec = F_.ConvSpec("down", linear.out_features, linear.in_features // (h * w), h, 1, 0)
         self.cache = F_.PackedWeights()
+        self.wmap, self.s2d_active = None, False
 
 
 # --------------------------------------------------------------------------------------------- generator
@@ -281,7 +306,11 @@ class Discriminator(_KernelModule):
     _layers = Generator._layers
 
     def forward(self, input):
-        return self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype()))
+        return self.forward_nhwc(F_.ToNHWCFn.apply(input, self._dtype(),
+                                                   self.input_s2d_origin(input.shape[2], input.shape[3])))
+
+    def input_s2d_origin(self, h: int, w: int):
+        return self._layers()[0].input_s2d_origin(self._dtype(), h, w)
 
     def forward_nhwc(self, h, groups: int = 1):
         """`groups` independent sub-batches stacked along the batch axis share every convolution launch while

@@ -88,18 +88,19 @@ class _ReconHubFn(torch.autograd.Function):
     reconstruction loss."""
 
     @staticmethod
-    def forward(ctx, recon, real, n_fake, sigma, dtype, recon_loss_out, mse_ws):
+    def forward(ctx, recon, real, n_fake, sigma, dtype, recon_loss_out, mse_ws, s2d_origin=None):
         ctx.save_for_backward(recon, real, recon_loss_out, mse_ws)
-        return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma)
+        ctx.s2d_origin = s2d_origin
+        return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma, s2d_origin=s2d_origin)
 
     @staticmethod
     def backward(ctx, dy):
         recon, real, loss_out, ws = ctx.saved_tensors
-        d_adv = F_.nhwc_to_nchw(dy.contiguous(), channels=recon.shape[1])
+        d_adv = F_.nhwc_to_nchw(dy.contiguous(), channels=recon.shape[1], s2d_origin=ctx.s2d_origin)
         d_total = torch.empty_like(recon)
         call("vg_mse", _p(recon), _p(real), recon.numel(), 1.0, _p(d_adv), _p(d_total), _p(loss_out), _p(ws),
              ws.numel() * 4, _stream())
-        return d_total, None, None, None, None, None, None
+        return d_total, None, None, None, None, None, None, None
 
 
 class VAEGANStep:
@@ -179,20 +180,26 @@ class VAEGANStep:
                 self._randn_into(s["n_den"], 4)
 
         # ---- encode, reparameterise, decode                                         (:74-83)
+        # image-side tensors go to the networks in the layout their first layer asks for (space-to-depth on the
+        # bf16 path: 128-byte TMA rows instead of 32-byte padded pixels)
+        e_fmt = E.input_s2d_origin(real.shape[2], real.shape[3])
+        d_fmt = D.input_s2d_origin(real.shape[2], real.shape[3])
         if self.denoise_sigma > 0:
-            enc_in = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_den"], mode=1, sigma=self.denoise_sigma, clamp=True)
+            enc_in = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_den"], mode=1, sigma=self.denoise_sigma, clamp=True,
+                                     s2d_origin=e_fmt)
         else:
-            enc_in = F_.nchw_to_nhwc(real, self.dtype)
+            enc_in = F_.nchw_to_nhwc(real, self.dtype, s2d_origin=e_fmt)
         mu, logvar = E.forward_nhwc(enc_in)
         z = _ReparamFn.apply(mu, logvar, s["eps"], loss[3:4], s["kl_w"], self.dtype)
         recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH, 3)
 
         # ---- instance noise                                                           (:88-92)
-        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype, loss[2:3], s["mse_ws"])
+        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype, loss[2:3], s["mse_ws"],
+                                        d_fmt)
         # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
         # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2)
         pair = torch.empty((2 * B,) + tuple(recon_noisy.shape[1:]), dtype=self.dtype, device=self.dev)
-        F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B])
+        F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B], s2d_origin=d_fmt)
         pair[B:].copy_(recon_noisy.detach())
         dp = s["dp_pair"]
 
