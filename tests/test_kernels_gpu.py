@@ -221,7 +221,7 @@ def test_fused_bn_stats_epilogue(case):
 
 
 @pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2)])
-@pytest.mark.parametrize("case", FUSE_CASES[:3] + [FUSE_CASES[4]],
+@pytest.mark.parametrize("case", FUSE_CASES[:3] + [FUSE_CASES[4], ("down", 64, 4, 4, 512, 1, 4, 1, 0, 2, False)],
                          ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-g{c[9]}")
 def test_fused_bn_bwd_epilogue(case, act, slope):
     """The dgrad of layer L+1 with VG_EPI_BN_BWD (and VG_EPI_ACT_BWD) against dgrad -> vg_bn_act_bwd / vg_act_bwd:
@@ -262,6 +262,8 @@ def test_fused_bn_bwd_epilogue(case, act, slope):
     torch.cuda.synchronize()
     assert rel_err(dx1.float().cpu(), dx0.float().cpu()) < 1.5e-2          # dz is rounded to bf16 once more
     assert rel_err(dg1.cpu(), dg0.cpu()) < 3e-3 and rel_err(db1.cpu(), db0.cpu()) < 3e-3
+    if cout == 1:
+        return          # the single-output head (GEMV kernels) fuses the BatchNorm form only
     # activation-only form
     ep3 = fn.make_epilogue(fn.EPI_ACT_BWD, 1, C, act, slope, None, raw_l, None)
     assert fn.epilogue_supported(g, kind == "down", ep3)

@@ -128,6 +128,7 @@ static void up_tiling(const VgConvGeom* g, int* tw, int* th, int* tb, int* n_til
 // 0 when `ep` can ride the tensor-core launch of this contraction, else a negative VG_ERR_* (message set).
 static int fuse_check(const VgConvGeom* g, bool up, const VgEpilogue* ep) {
     if (ep == nullptr || ep->mode == VG_EPI_NONE) return VG_OK;
+    if (up && is_gemv(g) && gemv_up_fused_ok(g, ep) && aligned16(ep->x)) return VG_OK;
     if (is_gemv(g) || !(up ? umma_up_ok(g) : umma_down_ok(g)))
         return fail(VG_ERR_SHAPE, "fused epilogue: this geometry does not run on the tensor-core path");
     int tw, th, tb, n_tile, n_total = g->small_c;
@@ -624,6 +625,11 @@ extern "C" int vg_conv_up_ex(const VgConvGeom* g, VgDType dtype, const void* sma
     if (dtype != VG_BF16) return fail(VG_ERR_SHAPE, "fused epilogues exist on the bf16 tensor-core path only");
     rc = fuse_check(g, true, ep);
     if (rc != VG_OK) return rc;
+    if (is_gemv(g) && ep != nullptr && ep->mode != VG_EPI_NONE) {
+        if (!aligned16(w) || !aligned16(big)) return fail(VG_ERR_ALIGN, "up: 16-byte alignment");
+        return gemv_up_fused(g, small, w, big, ep, as_stream(stream));
+    }
+    if (is_gemv(g)) return gemv_up(g, dtype, small, w, big, as_stream(stream));
     return up_umma(g, small, w, big, as_stream(stream), ep);
 }
 

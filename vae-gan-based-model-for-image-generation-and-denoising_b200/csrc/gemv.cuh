@@ -12,5 +12,8 @@ bool is_gemv(const VgConvGeom* g);
 int gemv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w, const float* bias, void* small,
               int out_f32, cudaStream_t st);
 int gemv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big, cudaStream_t st);
+// dgrad with the BatchNorm-backward reduction of the layer below fused in (bf16, VG_EPI_BN_BWD)
+bool gemv_up_fused_ok(const VgConvGeom* g, const VgEpilogue* ep);
+int gemv_up_fused(const VgConvGeom* g, const void* small, const void* w, void* big, const VgEpilogue* ep, cudaStream_t st);
 int gemv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, cudaStream_t st);
 }  // namespace vg
