@@ -108,12 +108,16 @@ int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void
  *   VG_EPI_BN_BWD    acc = dy;    out = dz = dy*act'(x*scale+shift);  sums[g][0][c] += dz,
  *                                 sums[g][1][c] += dz*(x-mean)*rstd                        (dgrad of the next layer)
  *   VG_EPI_ACT_BWD   out = dy*act'(x)                                                      (layer without BatchNorm)
+ *   VG_EPI_ACT_FWD   out = act(conv)  (ReLU / LeakyReLU of a layer without BatchNorm; its backward takes act' from
+ *                                      the sign of the activated output, so the raw output is never stored)
  * `groups` = independent sub-batches along the batch axis with separate statistics; `sums` = fp32
  * [groups][2][channels], zero-initialised by the caller, accumulated with atomics; `x` = the saved raw convolution
  * output (same NHWC shape as this call's output); `stats` = [groups][4][channels] (mean, rstd, scale, shift).
  * vg_conv_epilogue_supported() tells whether a geometry takes the fused form (1) or the caller has to use the
  * stand-alone reduction kernels below (0). */
-typedef enum VgEpilogueMode { VG_EPI_NONE = 0, VG_EPI_BN_STATS = 1, VG_EPI_BN_BWD = 2, VG_EPI_ACT_BWD = 3 } VgEpilogueMode;
+typedef enum VgEpilogueMode {
+    VG_EPI_NONE = 0, VG_EPI_BN_STATS = 1, VG_EPI_BN_BWD = 2, VG_EPI_ACT_BWD = 3, VG_EPI_ACT_FWD = 4
+} VgEpilogueMode;
 typedef struct VgEpilogue {
     int32_t mode;      /* VgEpilogueMode */
     int32_t groups;

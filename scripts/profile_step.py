@@ -49,3 +49,17 @@ for pat, tag in (("channel_reduce_kernel<__nv_bfloat16, 1>", "BN-bwd reduce"), (
     sel = [e for e in evs if pat in e.name]
     per = len(sel) // 3
     print(tag, "per-launch us:", " ".join(f"{e.time_range.elapsed_us():.0f}" for e in sel[-per:]))
+
+# full timeline of the last profiled step: offset, duration, stream, short kernel name
+if os.environ.get("TIMELINE"):
+    per = len(evs) // 3
+    last = evs[-per:]
+    t0 = last[0].time_range.start
+    def short(n):
+        n = n.replace("void ", "").replace("vg::(anonymous namespace)::", "").replace("vg::", "")
+        return n.split("(")[0][:48]
+    with open(os.environ["TIMELINE"], "w") as f:
+        for e in last:
+            stream = getattr(e, "stream", None)
+            f.write(f"{e.time_range.start - t0:9.1f} {e.time_range.elapsed_us():8.1f} {short(e.name)}\n")
+    print("timeline written:", os.environ["TIMELINE"], per, "events")

@@ -221,6 +221,33 @@ def test_fused_bn_stats_epilogue(case):
 
 
 @pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2)])
+@pytest.mark.parametrize("case", [FUSE_CASES[0], FUSE_CASES[2], ("down", 5, 33, 33, 64, 64, 2, 1, 0, 1, False)],
+                         ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}")
+def test_fused_activation_forward_epilogue(case, act, slope):
+    """VG_EPI_ACT_FWD == convolution followed by the stand-alone activation pass, bit for bit (same fp32 accumulator,
+    same single rounding to bf16)."""
+    fn = _fn()
+    kind, B, H, W, cin, cout, k, s, p, _, _ = case
+    gen = torch.Generator().manual_seed(B + cout)
+    x = torch.randn(B, H, W, cin, generator=gen).cuda().bfloat16()
+    if kind == "down":
+        spec, w = fn.ConvSpec("down", cout, cin, k, s, p), torch.randn(cout, cin, k, k, generator=gen).cuda() * 0.1
+    else:
+        spec, w = fn.ConvSpec("up", cin, cout, k, s, p), torch.randn(cin, cout, k, k, generator=gen).cuda() * 0.1
+    g = spec.geom(B, H, W)
+    wd, wu = fn.pack_weights(w, g)
+    ep = fn.make_epilogue(fn.EPI_ACT_FWD, 1, 0, act, slope)
+    assert fn.epilogue_supported(g, kind == "up", ep)
+    conv = (lambda e=None: fn.conv_down(x, wd, g, ep=e)) if kind == "down" else (lambda e=None: fn.conv_up(x, wu, g, ep=e))
+    raw, fused = conv(), conv(ep)
+    ref = torch.where(raw.float() > 0, raw.float(), raw.float() * slope)
+    torch.cuda.synchronize()
+    # the stand-alone path rounds twice (conv -> bf16 -> act -> bf16), the fused one once
+    assert rel_err(fused.float().cpu(), ref.cpu()) < 4e-3
+    assert torch.equal(fused > 0, raw > 0)
+
+
+@pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2)])
 @pytest.mark.parametrize("case", FUSE_CASES[:3] + [FUSE_CASES[4], ("down", 64, 4, 4, 512, 1, 4, 1, 0, 2, False)],
                          ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-g{c[9]}")
 def test_fused_bn_bwd_epilogue(case, act, slope):

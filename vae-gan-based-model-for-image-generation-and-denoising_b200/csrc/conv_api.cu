@@ -113,16 +113,26 @@ bool umma_wgrad_ok(const VgConvGeom* g) {
 
 // ---------------------------------------------------------------------------------------------- fused epilogues
 // Tiling decisions shared by the launchers and by vg_conv_epilogue_supported.
+// Few work items (small late layers): narrower N tiles put more SMs to work; the UMMA time per item falls with N.
+static int shrink_n_tile(int n_total, int n_tile, long long m_items) {
+    while (m_items * (n_total / n_tile) < 148 && n_tile % 64 == 0 && n_total % (n_tile / 2) == 0) n_tile /= 2;
+    return n_tile;
+}
+
 static void down_tiling(const VgConvGeom* g, int* tw, int* th, int* tb, int* n_tile) {
     pick_box(128, g->small_w, g->small_h, tw, th, tb);
-    *n_tile = pick_n_tile(g->small_c);
+    const long long m_items = static_cast<long long>(ceil_div(g->small_w, *tw)) * ceil_div(g->small_h, *th) *
+                              ceil_div(g->batch, *tb);
+    *n_tile = shrink_n_tile(g->small_c, pick_n_tile(g->small_c), m_items);
 }
 static void up_tiling(const VgConvGeom* g, int* tw, int* th, int* tb, int* n_tile, int* n_total) {
     const bool dense = g->small_h == 1 && g->small_w == 1 && g->stride == 1 && g->pad == 0;
     *n_total = dense ? g->kernel * g->kernel * g->big_c : g->big_c;
-    *n_tile = pick_n_tile(*n_total);
     const int grid_h = dense ? 1 : ceil_div(g->big_h, g->stride), grid_w = dense ? 1 : ceil_div(g->big_w, g->stride);
     pick_box(128, grid_w, grid_h, tw, th, tb);
+    const long long m_items = static_cast<long long>(ceil_div(grid_w, *tw)) * ceil_div(grid_h, *th) *
+                              ceil_div(g->batch, *tb) * (dense ? 1 : g->stride * g->stride);
+    *n_tile = shrink_n_tile(*n_total, pick_n_tile(*n_total), m_items);
 }
 
 // 0 when `ep` can ride the tensor-core launch of this contraction, else a negative VG_ERR_* (message set).
@@ -133,7 +143,12 @@ static int fuse_check(const VgConvGeom* g, bool up, const VgEpilogue* ep) {
         return fail(VG_ERR_SHAPE, "fused epilogue: this geometry does not run on the tensor-core path");
     int tw, th, tb, n_tile, n_total = g->small_c;
     if (up) up_tiling(g, &tw, &th, &tb, &n_tile, &n_total); else down_tiling(g, &tw, &th, &tb, &n_tile);
-    if (ep->mode < VG_EPI_BN_STATS || ep->mode > VG_EPI_ACT_BWD) return fail(VG_ERR_ARG, "fused epilogue: bad mode %d", ep->mode);
+    if (ep->mode < VG_EPI_BN_STATS || ep->mode > VG_EPI_ACT_FWD) return fail(VG_ERR_ARG, "fused epilogue: bad mode %d", ep->mode);
+    if (ep->mode == VG_EPI_ACT_FWD) {
+        if (ep->act != VG_ACT_RELU && ep->act != VG_ACT_LEAKY)
+            return fail(VG_ERR_SHAPE, "fused epilogue: only ReLU / LeakyReLU ride the forward epilogue");
+        return VG_OK;
+    }
     if (ep->mode != VG_EPI_BN_STATS) {
         if (ep->x == nullptr) return fail(VG_ERR_ARG, "fused epilogue: saved conv output missing");
         if (ep->act != VG_ACT_NONE && ep->act != VG_ACT_RELU && ep->act != VG_ACT_LEAKY)
@@ -182,9 +197,8 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     const int k = g->kernel, s = g->stride, pad = g->pad;
     p.kchunk = pick_kchunk(g->big_c);
     p.c_chunks = g->big_c / p.kchunk;
-    p.n_tile = pick_n_tile(g->small_c);
+    down_tiling(g, &p.tw, &p.th, &p.tb, &p.n_tile);
     p.n_tiles = g->small_c / p.n_tile;
-    pick_box(128, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
     p.tiles_b = ceil_div(g->batch, p.tb);
@@ -253,11 +267,10 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
     p.kchunk = pick_kchunk(g->small_c);
     p.c_chunks = g->small_c / p.kchunk;
     const int swz = p.kchunk * 2;
-    const int n_total = dense ? k * k * g->big_c : g->big_c;
-    p.n_tile = pick_n_tile(n_total);
+    int n_total = 0;
+    up_tiling(g, &p.tw, &p.th, &p.tb, &p.n_tile, &n_total);
     p.n_tiles = n_total / p.n_tile;
     const int grid_h = dense ? 1 : ceil_div(g->big_h, s), grid_w = dense ? 1 : ceil_div(g->big_w, s);
-    pick_box(128, grid_w, grid_h, &p.tw, &p.th, &p.tb);
     p.tiles_w = ceil_div(grid_w, p.tw);
     p.tiles_h = ceil_div(grid_h, p.th);
     p.tiles_b = ceil_div(g->batch, p.tb);

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     }
                 }
             };
-            if (fmode >= 2) load_x(0);
+            if (fmode == 2 || fmode == 3) load_x(0);
 
             mbar_wait(&tmem_full[acc], (li >> 1) & 1);
             tc_fence_after();
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 int ch0 = 0;
                 if (fmode == 1 || fmode == 2) ch0 = (n0 + c) % fC;
                 float xv[32];
-                if (fmode >= 2) {
+                if (fmode == 2 || fmode == 3) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t w4[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
@@ -325,6 +325,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] *= xv[j] > 0.f ? 1.f : neg_slope;
                     }
+                }
+                if (fmode == 4) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * neg_slope;
                 }
                 uint32_t pk[16];
 #pragma unroll
@@ -688,7 +692,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        for (auto fn : {igemm_fprop_kernel<0>, igemm_fprop_kernel<1>, igemm_fprop_kernel<2>, igemm_fprop_kernel<3>}) {
+        for (auto fn : {igemm_fprop_kernel<0>, igemm_fprop_kernel<1>, igemm_fprop_kernel<2>, igemm_fprop_kernel<3>,
+                        igemm_fprop_kernel<4>}) {
             const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) attr_err = e;
         }
@@ -709,6 +714,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
         case 1: igemm_fprop_kernel<1><<<grid, kIgemmThreads, smem, stream>>>(p); break;
         case 2: igemm_fprop_kernel<2><<<grid, kIgemmThreads, smem, stream>>>(p); break;
         case 3: igemm_fprop_kernel<3><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        case 4: igemm_fprop_kernel<4><<<grid, kIgemmThreads, smem, stream>>>(p); break;
         default: igemm_fprop_kernel<0><<<grid, kIgemmThreads, smem, stream>>>(p); break;
     }
     cudaError_t e = cudaGetLastError();

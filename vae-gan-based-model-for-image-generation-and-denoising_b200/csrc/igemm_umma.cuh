@@ -57,6 +57,7 @@ struct alignas(64) IgemmParams {
     //   mode 2  BatchNorm backward: the accumulator is dy; out = dz = dy * act'(x*scale+shift) with x = fuse_x (the
     //           raw conv output the BatchNorm normalised), sums[g][0][c] += dz, sums[g][1][c] += dz*(x-mean)*rstd
     //   mode 3  activation backward only: out = dy * act'(x)
+    //   mode 4  activation forward: out = act(acc) for ReLU / LeakyReLU layers without BatchNorm
     // CTAs accumulate in shared memory and flush once with fp32 atomics into `fuse_sums` (caller zero-initialises).
     int fuse_mode, fuse_groups, fuse_group_batch, fuse_c;
     float* fuse_sums;          // [groups][2][fuse_c]

@@ -40,14 +40,18 @@ __device__ __forceinline__ F block_sum(F v, F* smem /* [32] */) {
     return r;
 }
 
-// ---- reparameterisation + KL (single block: B*nz is a few 10^4 elements)
+// ---- reparameterisation + KL: one element per thread; block partials meet in a double accumulator and the block
+// that arrives last (ticket) writes the KL term and re-arms both (one step at a time per process uses this kernel)
+__device__ double g_kl_acc;
+__device__ unsigned int g_kl_ticket;
+
 template <typename T>
-__global__ void __launch_bounds__(1024) reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
-                                                          const float* __restrict__ eps, int n, int batch,
-                                                          T* __restrict__ z, float* __restrict__ kl_out) {
+__global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                                         const float* __restrict__ eps, int n, int batch,
+                                                         T* __restrict__ z, float* __restrict__ kl_out) {
     __shared__ double red[32];
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float m = mu[i];
         const float lv = fminf(10.f, fmaxf(-10.f, logvar[i]));
         const float sd = expf(0.5f * lv);
@@ -55,8 +59,18 @@ __global__ void __launch_bounds__(1024) reparam_fwd_kernel(const float* __restri
         if constexpr (sizeof(T) == 4) z[i] = zz; else z[i] = __float2bfloat16_rn(zz);
         acc += static_cast<double>(1.f + lv - m * m - expf(lv));
     }
-    const double tot = block_sum(acc, red);
-    if (threadIdx.x == 0 && kl_out != nullptr) *kl_out = static_cast<float>(-0.5 * tot / batch);
+    const double part = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_kl_acc, part);
+        __threadfence();
+        if (atomicAdd(&g_kl_ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const double tot = atomicAdd(&g_kl_acc, 0.0);
+            if (kl_out != nullptr) *kl_out = static_cast<float>(-0.5 * tot / batch);
+            g_kl_acc = 0.0;
+            g_kl_ticket = 0;
+        }
+    }
 }
 
 template <typename T>
@@ -246,11 +260,11 @@ extern "C" int vg_reparam_fwd(const float* mu, const float* logvar, const float*
         return fail(VG_ERR_ARG, "reparam_fwd: null pointer");
     const int n = batch * nz;
     if (z_dt == VG_BF16)
-        reparam_fwd_kernel<__nv_bfloat16><<<1, 1024, 0, as_stream(stream)>>>(mu, logvar, eps, n, batch,
-                                                                             static_cast<__nv_bfloat16*>(z), kl_out);
+        reparam_fwd_kernel<__nv_bfloat16><<<std::max(1, std::min(148, (n + 255) / 256)), 256, 0, as_stream(stream)>>>(
+            mu, logvar, eps, n, batch, static_cast<__nv_bfloat16*>(z), kl_out);
     else
-        reparam_fwd_kernel<float><<<1, 1024, 0, as_stream(stream)>>>(mu, logvar, eps, n, batch, static_cast<float*>(z),
-                                                                     kl_out);
+        reparam_fwd_kernel<float><<<std::max(1, std::min(148, (n + 255) / 256)), 256, 0, as_stream(stream)>>>(
+            mu, logvar, eps, n, batch, static_cast<float*>(z), kl_out);
     VG_LAUNCHED();
     return VG_OK;
 }

@@ -13,8 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_ACT_BWD, EPI_BN_BWD, EPI_BN_STATS, VG_BF16,
-                   VG_F32, VgConvGeom, VgEpilogue, call)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_ACT_BWD, EPI_ACT_FWD, EPI_BN_BWD,
+                   EPI_BN_STATS, VG_BF16, VG_F32, VgConvGeom, VgEpilogue, call)
 
 _DT = {torch.float32: VG_F32, torch.bfloat16: VG_BF16}
 PRECISION_DTYPE = {"fp32": torch.float32, "bf16": torch.bfloat16}
@@ -573,6 +573,13 @@ class ConvLayerFn(torch.autograd.Function):
             ep = make_epilogue(EPI_BN_STATS, groups, C, sums=sums)
             if not epilogue_supported(g, spec.kind == "up", ep):
                 ep = sums = None
+        # ReLU / LeakyReLU without BatchNorm: applied in the epilogue; only the activated tensor is kept (its sign is
+        # all the backward needs)
+        act_in_epilogue = False
+        if bn is None and act in (ACT_RELU, ACT_LEAKY) and x.dtype == torch.bfloat16 and not out_f32:
+            ep_act = make_epilogue(EPI_ACT_FWD, 1, 0, act, slope)
+            if epilogue_supported(g, spec.kind == "up", ep_act):
+                ep, act_in_epilogue = ep_act, True
         if spec.kind == "down":
             raw = conv_down(x, w_fwd, g, bias.detach() if bias is not None else None, out_f32=out_f32, ep=ep)
         else:
@@ -604,7 +611,7 @@ class ConvLayerFn(torch.autograd.Function):
             else:
                 stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
                 y = scale_shift_act(raw, stats[2], stats[3], act, slope)
-        elif act != ACT_NONE:
+        elif act != ACT_NONE and not act_in_epilogue:
             y = scale_shift_act(raw, None, None, act, slope)
         else:
             y = raw
