@@ -327,8 +327,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     }
                 }
                 if (fmode == 4) {
+                    // same two roundings as conv -> bf16 -> activation -> bf16 (what the reference's bf16 pipeline and
+                    // the stand-alone activation pass do), so fused and unfused layers are bit-identical
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * neg_slope;
+                    for (int j = 0; j < 32; ++j) {
+                        const float r = __bfloat162float(__float2bfloat16_rn(f[j]));
+                        f[j] = r > 0.f ? r : r * neg_slope;
+                    }
                 }
                 uint32_t pk[16];
 #pragma unroll

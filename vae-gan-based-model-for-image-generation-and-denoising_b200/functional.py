@@ -622,7 +622,9 @@ class ConvLayerFn(torch.autograd.Function):
         ctx.link_in, ctx.link_out, ctx.wmap = link_in, None, wmap
         if (link_out is not None and x.dtype == torch.bfloat16 and not out_f32 and act in (ACT_NONE, ACT_RELU, ACT_LEAKY)
                 and (bn is None or training) and (bn is not None or act != ACT_NONE)):
-            link_out.raw, link_out.stats, link_out.act, link_out.slope, link_out.groups = raw, stats, act, slope, groups
+            # (a detached alias: when `raw` is also this function's OUTPUT it acquires grad_fn -> ctx -> link -> raw,
+            # a reference cycle that would keep a whole step's tensors alive until the garbage collector runs)
+            link_out.raw, link_out.stats, link_out.act, link_out.slope, link_out.groups = raw.detach(), stats, act, slope, groups
             ctx.link_out = link_out
         ctx.save_for_backward(x, raw, stats)
         return y
