@@ -131,8 +131,10 @@ def test_graph_replay_equals_eager_and_device_noise_runs():
         # avalanches through bf16 rounding - scripts/debug_determinism.py)
         # (since the BatchNorm sums ride the convolution epilogues they are fp32 atomics as well; with batch 8 the
         # discriminator's last BatchNorm sees 128 values per channel, so the later steps are compared loosely)
-        tol = 1e-2 if it == 0 else 1.5e-1
         for k in la:
+            # first step: d_loss_0 / recon / kl are computed before any parameter moved; d_loss_1 / adv / total follow
+            # one resp. two discriminator Adam steps and already carry the sign-flip noise
+            tol = (1e-2 if k in ("d_loss_0", "recon", "kl") else 5e-2) if it == 0 else 1.5e-1
             assert abs(float(la[k]) - float(lb[k])) <= tol * abs(float(la[k])) + 1e-5, (it, k)
     # noise drawn on the device (Philox) instead of injected: runs, finite, and differs from step to step
     real = vo.make_inputs(batch, hw, nz)[0].cuda()

@@ -89,7 +89,9 @@ def pack_weights(w: torch.Tensor, g: VgConvGeom) -> Tuple[torch.Tensor, torch.Te
 def conv_flops(g: VgConvGeom) -> float:
     """Algorithmic FLOPs of one contraction over this geometry: 2 x MACs over the VALID channels."""
     bc = g.big_c_valid if g.big_c_valid > 0 else g.big_c
-    return 2.0 * g.batch * g.small_h * g.small_w * g.small_c * bc * g.kernel * g.kernel
+    # space-to-depth layers run an EQUIVALENT 64-channel convolution; `algo_scale` (set by ConvLayerFn) brings the
+    # count back to the reference layer's own MACs
+    return 2.0 * g.batch * g.small_h * g.small_w * g.small_c * bc * g.kernel * g.kernel * getattr(g, "algo_scale", 1.0)
 
 
 def conv_bytes(g: VgConvGeom, extra_big: int = 0, extra_small: int = 0) -> float:
@@ -558,6 +560,10 @@ class ConvLayerFn(torch.autograd.Function):
                 raise RuntimeError(f"Given transposed=1, weight of size {list(weight.shape)}, expected input with "
                                    f"{spec.small_c} channels, but got {Cx} channels instead")
             g = spec.geom(B, H, W, padded_channels(spec.big_c, x.dtype))
+        if wmap is not None:
+            o, e = wmap.spec, wmap.eq_spec
+            g.algo_scale = (o.small_c * o.big_c * o.kernel ** 2 * (4 if o.kind == "up" else 1)) / \
+                           (e.small_c * e.big_c * e.kernel ** 2)
         if x.dtype == torch.bfloat16:
             wd, wu = cache.get(weight, g, wmap)
             w_fwd = wd if spec.kind == "down" else wu
