@@ -45,6 +45,27 @@ static int pick_tps(int kchunk, int c_chunks, int taps) {
     return 1;
 }
 
+// Small weight tensors stay resident in shared memory (IgemmParams::b_resident): the CTA's consecutive work items share
+// the (phase, N tile) slabs, so only the activation tiles stream through the ring - the N <= 64 / K <= 512 layers are
+// bound by the L2 -> shared-memory fill rate, and the weights were a third of it.
+static void pick_resident(IgemmParams& p, int extra_smem) {
+    p.b_resident = 0;
+    const int tps = p.tps > 1 ? p.tps : 1;
+    const long long m_items = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b;
+    const int res = p.taps_per_phase * p.c_chunks * p.n_tile * p.kchunk * 2;
+    const int a_stage = 128 * p.kchunk * 2;
+    // Measured (round 1): NOT a win.  With one CTA per SM (64 KB of slabs) the single MMA-issuing thread leaves the
+    // tensor pipe idle between stages and the 128->64 generator stage runs 1.7x slower; with two CTAs per SM (<= 48 KB)
+    // the step is 1 % slower than with streamed weights - these layers are bound by the per-stage issue latency, not by
+    // the fill rate.  Kept behind VG_BRES=1 for experiments.
+    static const bool enabled = getenv("VG_BRES") != nullptr;
+    if (!enabled || tps != 1 || p.ksplit > 1 || m_items < 148 * 4 || res > 48 * 1024) return;
+    const int budget = 110 * 1024 - 2048 - extra_smem - res;
+    if (budget / a_stage < 4) return;
+    p.b_resident = 1;
+    p.stages = std::min(8, budget / a_stage);
+}
+
 static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30, int extra_smem = 0) {
     // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question:
     // narrow accumulators leave room for two CTAs per SM (110 KB each), wide ones take the whole SM.
@@ -249,6 +270,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
         p.ksplit = ks;
         p.splitk_acc = static_cast<float*>(ws);
     }
+    pick_resident(p, igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
     note_launch(p.ksplit > 1 ? 2 : 1);
@@ -343,6 +365,7 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
     p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
                            igemm_fuse_smem_bytes(p));
+    pick_resident(p, igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();

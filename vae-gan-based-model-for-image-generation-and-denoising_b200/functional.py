@@ -160,7 +160,7 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
     ws = _ws(nbytes, small.device) if nbytes else None
     call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream(),
          flops=conv_flops(g), tag=_conv_tag(g, "wgrad"), nbytes=conv_bytes(g))
-    if ws is not None and WgradOverlap.stream is not None:
+    if ws is not None and WgradOverlap.streams:
         WgradOverlap.keepalive.append(ws)
     return dw
 
@@ -347,26 +347,39 @@ def nhwc_to_nchw(src: torch.Tensor, act: int = ACT_NONE, slope: float = 0.0, cha
 # --------------------------------------------------------------------------------------------- side stream for wgrad
 class WgradOverlap:
     """Weight gradients are off the backward critical path (BN-backward -> dgrad -> BN-backward ...), and they are
-    tensor/L2-bound while the BatchNorm passes are HBM-bound.  The fused step therefore issues every wgrad on a
-    second stream (a parallel branch of the captured CUDA graph) and joins it before the optimizer.  Tensors the
-    side stream reads are kept alive until the join, so the caching allocator cannot hand their memory out early."""
-    stream: Optional["torch.cuda.Stream"] = None
+    tensor/L2-bound while the BatchNorm passes are HBM-bound.  The fused step therefore issues every wgrad on side
+    streams (parallel branches of the captured CUDA graph), round-robin, and joins them before the optimizer: the
+    many small weight-gradient launches of the encoder / discriminator tail then overlap EACH OTHER as well.
+    Tensors the side streams read are kept alive until the join, so the caching allocator cannot hand their memory
+    out early."""
+    streams: list = []
     keepalive: list = []
+    _next = 0
 
     @classmethod
-    def enable(cls, stream):
-        cls.stream, cls.keepalive = stream, []
+    def enable(cls, streams):
+        cls.streams = list(streams) if isinstance(streams, (list, tuple)) else [streams]
+        cls.keepalive, cls._next = [], 0
+
+    @classmethod
+    def pick(cls):
+        """Next side stream (None when overlap is off)."""
+        if not cls.streams:
+            return None
+        s = cls.streams[cls._next % len(cls.streams)]
+        cls._next += 1
+        return s
 
     @classmethod
     def join(cls):
-        if cls.stream is not None:
-            torch.cuda.current_stream().wait_stream(cls.stream)
+        for s in cls.streams:
+            torch.cuda.current_stream().wait_stream(s)
         cls.keepalive = []
 
     @classmethod
     def disable(cls):
         cls.join()
-        cls.stream = None
+        cls.streams = []
 
 
 # --------------------------------------------------------------------------------------------- space-to-depth layers
@@ -683,18 +696,23 @@ class ConvLayerFn(torch.autograd.Function):
             d_raw = dy if dy.dtype == x.dtype else scale_shift_act(dy, None, None, ACT_NONE, 0.0, out_dtype=x.dtype)
 
         # ---- bias, weight and input gradients
-        if bias is not None and ctx.needs_input_grad[2]:
+        want_bias = bias is not None and ctx.needs_input_grad[2]
+        if want_bias:
             dbias = getattr(bias, "main_grad", None)
             if dbias is None:
                 dbias = torch.zeros_like(bias, dtype=torch.float32)
+        bias_with_wgrad = want_bias and need_w       # the bias gradient then rides the weight-gradient stream
+        if want_bias and not bias_with_wgrad:
             colsum(d_raw, dbias)
         small, big = (d_raw, x) if spec.kind == "down" else (x, d_raw)
         if need_w:
             main_grad = getattr(weight, "main_grad", None)
-            side = WgradOverlap.stream
+            side = WgradOverlap.pick() if main_grad is not None else None
             wmap = ctx.wmap
 
             def run_wgrad():
+                if bias_with_wgrad:
+                    colsum(d_raw, dbias)
                 if wmap is None:
                     return conv_wgrad(small, big, g, main_grad)
                 # space-to-depth layer: gradient of the equivalent weights, folded back into the master layout

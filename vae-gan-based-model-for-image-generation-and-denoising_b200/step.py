@@ -125,7 +125,9 @@ class VAEGANStep:
         self.opt_D = _FlatAdam(discriminator, lr, betas, eps)
         self.use_graph = use_cuda_graph
         self.seed = seed
-        self.wgrad_stream = torch.cuda.Stream(device=self.dev) if overlap_wgrad else None
+        # side streams (parallel branches of the captured graph): weight gradients round-robin, plus the start-of-step
+        # weight packing and noise generation that the encoder's forward pass does not wait for
+        self.wgrad_streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)] if overlap_wgrad else []
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -157,8 +159,8 @@ class VAEGANStep:
 
     # ------------------------------------------------------------------------------------------ the schedule
     def _run(self, gen_noise: bool):
-        if self.wgrad_stream is not None:
-            F_.WgradOverlap.enable(self.wgrad_stream)
+        if self.wgrad_streams:
+            F_.WgradOverlap.enable(self.wgrad_streams)
         try:
             self._run_body(gen_noise)
         finally:
@@ -170,14 +172,35 @@ class VAEGANStep:
         real, loss = s["real"], s["losses"]
         B = real.shape[0]
         F_.SumsArena.reset(self.dev)   # channel-sum scratch of the fused conv epilogues: one memset per step
-        for net in (E, G, D):          # every replay starts from freshly packed bf16 weights (one launch per net)
-            net.repack_weights()
-        if gen_noise:                  # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
+        # every replay starts from freshly packed bf16 weights (one launch per net): the encoder's are needed at once,
+        # the generator's and the discriminator's are packed on the second stream under the encoder's forward pass
+        E.repack_weights()
+        sides = self.wgrad_streams
+        cur = torch.cuda.current_stream()
+
+        def noise():                   # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
             self._randn_into(s["eps"], 1)
             self._randn_into(s["n_real"], 2)
             self._randn_into(s["n_fake"], 3)
             if s["n_den"] is not None:
                 self._randn_into(s["n_den"], 4)
+
+        if sides:
+            for st in sides[:2]:
+                st.wait_stream(cur)
+            with torch.cuda.stream(sides[0]):
+                G.repack_weights()
+                D.repack_weights()
+            if gen_noise and s["n_den"] is not None:
+                noise()                         # the denoising noise feeds the encoder's input: nothing to hide it under
+            elif gen_noise:
+                with torch.cuda.stream(sides[1]):
+                    noise()
+        else:
+            G.repack_weights()
+            D.repack_weights()
+            if gen_noise:
+                noise()
 
         # ---- encode, reparameterise, decode                                         (:74-83)
         # image-side tensors go to the networks in the layout their first layer asks for (space-to-depth on the
@@ -191,6 +214,8 @@ class VAEGANStep:
             enc_in = F_.nchw_to_nhwc(real, self.dtype, s2d_origin=e_fmt)
         mu, logvar = E.forward_nhwc(enc_in)
         z = _ReparamFn.apply(mu, logvar, s["eps"], loss[3:4], s["kl_w"], self.dtype)
+        for st in sides[:2]:
+            cur.wait_stream(st)                                  # packed generator / discriminator weights, noise
         recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH, 3)
 
         # ---- instance noise                                                           (:88-92)
