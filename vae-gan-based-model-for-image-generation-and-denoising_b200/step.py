@@ -71,14 +71,8 @@ class _ReparamFn(torch.autograd.Function):
         ctx.save_for_backward(mu, logvar, eps, kl_weight_dev)
         return z
 
-    # called (once) when the gradient w.r.t. z arrives, i.e. when the generator's backward pass has been issued
-    on_generator_done = None
-
     @staticmethod
     def backward(ctx, dz):
-        cb, _ReparamFn.on_generator_done = _ReparamFn.on_generator_done, None
-        if cb is not None:
-            cb()
         mu, logvar, eps, klw = ctx.saved_tensors
         B, nz = mu.shape
         dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
@@ -134,9 +128,6 @@ class VAEGANStep:
         # side streams (parallel branches of the captured graph): weight gradients round-robin, plus the start-of-step
         # weight packing and noise generation that the encoder's forward pass does not wait for
         self.wgrad_streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)] if overlap_wgrad else []
-        # the generator's all-reduce + Adam start as soon as its backward is issued, under the encoder's backward
-        self.update_stream = torch.cuda.Stream(device=self.dev) if overlap_wgrad else None
-        self._g_updated = False
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -195,7 +186,7 @@ class VAEGANStep:
                 self._randn_into(s["n_den"], 4)
 
         if sides:
-            for st in sides:                    # fork every side stream here: all of them belong to the capture
+            for st in sides[:2]:
                 st.wait_stream(cur)
             with torch.cuda.stream(sides[0]):
                 G.repack_weights()
@@ -256,41 +247,21 @@ class VAEGANStep:
         d_params = list(D.parameters())
         for p in d_params:             # weight gradients of D are never used in this phase (reference discards them)
             p.requires_grad_(False)
-        self._g_updated = False
-        if self.update_stream is not None:
-            _ReparamFn.on_generator_done = self._update_generator_early
         try:
             p_fake = D.forward_nhwc(recon_noisy)
             call("vg_bce", _p(p_fake), B, self.real_label, self.alpha_adv, _p(loss[4:5]), 0, _p(s["dp_a"]), _stream())
             torch.autograd.backward([p_fake], [s["dp_a"]])
         finally:
-            _ReparamFn.on_generator_done = None
             for p in d_params:
                 p.requires_grad_(True)
         call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
              _p(loss[5:6]), _stream())
         F_.WgradOverlap.join()
         self._allreduce(self.opt_E)
+        self._allreduce(self.opt_G)
         self.opt_E.step(1.0 / self.world)
-        if self._g_updated:
-            torch.cuda.current_stream().wait_stream(self.update_stream)
-        else:
-            self._allreduce(self.opt_G)
-            self.opt_G.step(1.0 / self.world)
+        self.opt_G.step(1.0 / self.world)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
-
-    def _update_generator_early(self):
-        """Runs inside the backward pass at the moment dL/dz reaches the reparameterisation: every generator kernel
-        (dgrad chain on this stream, weight gradients on the side streams) has been issued, the encoder's backward is
-        still to come.  The generator's gradient all-reduce and Adam go to their own stream behind all of those."""
-        upd, cur = self.update_stream, torch.cuda.current_stream()
-        upd.wait_stream(cur)
-        for st in self.wgrad_streams:
-            upd.wait_stream(st)
-        with torch.cuda.stream(upd):
-            self._allreduce(self.opt_G)
-            self.opt_G.step(1.0 / self.world)
-        self._g_updated = True
 
     # ------------------------------------------------------------------------------------------ public API
     def step(self, real: torch.Tensor, epoch: int, eps: Optional[torch.Tensor] = None,
