@@ -186,7 +186,7 @@ class VAEGANStep:
                 self._randn_into(s["n_den"], 4)
 
         if sides:
-            for st in sides[:2]:
+            for st in sides:                    # fork every side stream here: all of them belong to the capture
                 st.wait_stream(cur)
             with torch.cuda.stream(sides[0]):
                 G.repack_weights()
