@@ -1,0 +1,116 @@
+"""GPU: the configurations SURVEY.md section 8(d) names besides the bench workload and the section 8(f) "next" rows -
+cfg 4 (128x128 nets of double width, latent 256), cfg 5 (decoder-only generation, eval-mode BatchNorm folded,
+main_vae.py:348-374), the validation / denoise pass (vaegan_code.py:147-171) and checkpoint + optimizer-state resume
+(vaegan_code.py:193; main_vae.py:246-249) - each against the oracle on identical weights and inputs."""
+import copy
+
+import pytest
+import torch
+
+from tests.util import make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _step_cls():
+    from importlib import import_module
+    import vaegan_b200  # noqa: F401
+    return import_module("vaegan_b200.step").VAEGANStep
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16", 2e-2)])
+def test_cfg4_wide_128px_step(prec, tol):
+    """BASELINE config 4 shapes: hw 128, ngf = ndf = 128, encoder channels x2, latent 256 (batch 4 here)."""
+    from oracle import vaegan_oracle as vo
+    hw, nz, width, batch, epoch = 128, 256, 2, 4, 50
+    o_nets, nets = make_pair(hw, nz, prec, width=width)
+    real, eps, n_real, n_fake = vo.make_inputs(batch, hw, nz)
+    res = vo.reference_step(*o_nets, *vo.make_optimizers(*o_nets), real, epoch, eps, n_real, n_fake)
+    step = _step_cls()(*nets, use_cuda_graph=False)
+    losses = step.step(real.cuda(), epoch, eps.cuda(), n_real.cuda(), n_fake.cuda())
+    torch.cuda.synchronize()
+    for k, v in res.losses.items():
+        assert abs(float(losses[k]) - v) <= tol * abs(v) + 1e-6, (k, float(losses[k]), v)
+    if prec == "fp32":
+        out = step.last_outputs()
+        assert rel_err(out["recon"], res.recon) < 2e-4 and rel_err(out["mu"], res.mu) < 2e-4
+
+
+@pytest.mark.parametrize("batch", [1, 2, 64, 130])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_cfg5_generation_eval_mode(batch, prec, tol):
+    """Decoder-only generation: Generator.eval() under no_grad, z ~ N(0, I); BatchNorm runs on its running statistics
+    folded into one scale/shift pass (main_vae.py:360-366)."""
+    o_nets, nets = make_pair(64, 128, prec)
+    g_ref, g = o_nets[1], nets[1]
+    # make the running statistics non-trivial: one training forward on both sides first
+    zt = torch.randn(16, 128, 1, 1, generator=torch.Generator().manual_seed(3))
+    g_ref.train(); g.train()
+    with torch.no_grad():
+        g_ref(zt); g(zt.cuda())
+    g_ref.eval(); g.eval()
+    z = torch.randn(batch, 128, 1, 1, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref, out = g_ref(z), g(z.cuda())
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape == (batch, 3, 64, 64) and out.dtype == torch.float32
+    assert float((out.cpu() - ref).abs().max()) < tol            # Tanh output, |.| <= 1
+    # eval mode must not touch the running statistics
+    for (k, a), (_, b) in zip(g.state_dict().items(), g_ref.state_dict().items()):
+        if "running" in k or "num_batches" in k:
+            assert rel_err(a.float(), b.float()) < (1e-5 if prec == "fp32" else 2e-2), k
+
+
+def test_validation_denoise_pass_fp32():
+    """vaegan_code.py:147-171: eval-mode encoder on clamp(x + 0.05 n), reparameterise, eval-mode decoder, MSE + KL."""
+    o_nets, nets = make_pair(64, 128, "fp32")
+    (e_ref, g_ref, _), (e, g, _) = o_nets, nets
+    gen = torch.Generator().manual_seed(9)
+    img = torch.rand(6, 3, 64, 64, generator=gen) * 2 - 1
+    noisy = torch.clamp(img + 0.05 * torch.randn(img.shape, generator=gen), -1.0, 1.0)
+    eps = torch.randn(6, 128, generator=gen)
+
+    def run(enc, dec, dev):
+        enc.eval(); dec.eval()
+        with torch.no_grad():
+            mu, logvar = enc(noisy.to(dev))
+            logvar = torch.clamp(logvar, min=-10, max=10)
+            z = (mu + torch.exp(0.5 * logvar) * eps.to(dev)).unsqueeze(-1).unsqueeze(-1)
+            recon = dec(z)
+            recon_loss = torch.nn.functional.mse_loss(recon, img.to(dev), reduction="mean")
+            kl = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
+        return recon.cpu(), float(recon_loss), float(kl)
+
+    r0, m0, k0 = run(e_ref, g_ref, "cpu")
+    r1, m1, k1 = run(e, g, "cuda")
+    assert rel_err(r1, r0) < 1e-4 and abs(m1 - m0) <= 1e-4 * abs(m0) and abs(k1 - k0) <= 1e-4 * abs(k0)
+
+
+def test_checkpoint_and_optimizer_state_resume():
+    """Three steps in one go == two steps, checkpoint (module state_dicts with the reference's keys + the fused step's
+    optimizer / noise state), fresh objects, load, third step."""
+    from oracle import vaegan_oracle as vo
+    hw, nz, batch = 64, 128, 8
+    _, nets_a = make_pair(hw, nz, "fp32")
+    _, nets_b = make_pair(hw, nz, "fp32")
+    _, nets_c = make_pair(hw, nz, "fp32", seed=7)          # different initial weights: must be overwritten by the load
+    sa, sb = _step_cls()(*nets_a, use_cuda_graph=False), _step_cls()(*nets_b, use_cuda_graph=False)
+    inputs = [tuple(t.cuda() for t in vo.make_inputs(batch, hw, nz, seed=20 + i)) for i in range(3)]
+    for i in range(3):
+        la = sa.step(inputs[i][0], 50, *inputs[i][1:])
+    for i in range(2):
+        sb.step(inputs[i][0], 50, *inputs[i][1:])
+    ckpt = {"E": copy.deepcopy(nets_b[0].state_dict()), "G": copy.deepcopy(nets_b[1].state_dict()),
+            "D": copy.deepcopy(nets_b[2].state_dict()), "step": copy.deepcopy(sb.state_dict())}
+    assert ckpt["step"]["opt_D"]["step"] == 4 and ckpt["step"]["opt_G"]["step"] == 2        # 2 D updates per step
+    sc = _step_cls()(*nets_c, use_cuda_graph=False)
+    for net, key in zip(nets_c, "EGD"):
+        net.load_state_dict(ckpt[key])
+    sc.load_state_dict(ckpt["step"])
+    lc = sc.step(inputs[2][0], 50, *inputs[2][1:])
+    torch.cuda.synchronize()
+    for k in la:
+        assert abs(float(la[k]) - float(lc[k])) <= 2e-4 * abs(float(la[k])) + 1e-6, k
+    for (k, a), (_, c) in zip(nets_a[1].state_dict().items(), nets_c[1].state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert float((a - c).abs().max()) <= 1e-4 * float(a.abs().max()) + 2e-4 * 0.5, k   # within lr/2 (sign noise)

@@ -15,14 +15,14 @@ def cosine(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a @ b) / (a.norm() * b.norm() + 1e-300))
 
 
-def make_pair(hw=64, nz=128, precision="fp32", seed=42, device="cuda"):
+def make_pair(hw=64, nz=128, precision="fp32", seed=42, device="cuda", width=1):
     """(oracle nets on CPU, vaegan_b200 nets on `device`) with identical weights and buffers."""
     import vaegan_b200 as vb
     from oracle import vaegan_oracle as vo
-    o_nets = vo.build_nets(vo.NetConfig(hw=hw, nz=nz, seed=seed))
-    e = vb.Encoder([3, hw, hw], nz, precision=precision)
-    g = vb.Generator(nz=nz, hw=hw, precision=precision)
-    d = vb.Discriminator(hw=hw, precision=precision)
+    o_nets = vo.build_nets(vo.NetConfig(hw=hw, nz=nz, width=width, seed=seed))
+    e = vb.Encoder([3, hw, hw], nz, width=width, precision=precision)
+    g = vb.Generator(nz=nz, ngf=64 * width, hw=hw, precision=precision)
+    d = vb.Discriminator(ndf=64 * width, hw=hw, precision=precision)
     for mine, ref in zip((e, g, d), o_nets):
         mine.load_state_dict(copy.deepcopy(ref.state_dict()))
         mine.to(device)

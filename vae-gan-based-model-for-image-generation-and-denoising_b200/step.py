@@ -38,6 +38,7 @@ class _FlatAdam:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4        # keep every view 16-byte aligned
         self.n = total
+        self.offsets, self.sizes, self.shapes = offs, [p.numel() for p in params], [tuple(p.shape) for p in params]
         self.params = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -53,6 +54,22 @@ class _FlatAdam:
 
     def zero_grad(self):
         self.grads.zero_()      # cudaMemsetAsync
+
+    def state_dict(self):
+        """Per-parameter moments in `net.parameters()` order and the step count - the content of
+        torch.optim.Adam.state_dict()['state'] for the same network."""
+        views = lambda flat: [flat[o:o + n].view(shape).clone() for o, n, shape in zip(self.offsets, self.sizes, self.shapes)]
+        return {"step": int(self.step_count), "exp_avg": views(self.exp_avg), "exp_avg_sq": views(self.exp_avg_sq)}
+
+    def load_state_dict(self, sd):
+        for key, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            if len(sd[key]) != len(self.offsets):
+                raise RuntimeError(f"optimizer state has {len(sd[key])} tensors, the network has {len(self.offsets)} parameters")
+            for t, o, n, shape in zip(sd[key], self.offsets, self.sizes, self.shapes):
+                if tuple(t.shape) != shape:
+                    raise RuntimeError(f"size mismatch in optimizer state: {tuple(t.shape)} vs parameter {shape}")
+                flat[o:o + n].view(shape).copy_(t)
+        self.step_count.fill_(int(sd["step"]))
 
     def step(self, grad_scale: float):
         call("vg_adam_step", _p(self.params), _p(self.grads), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
@@ -273,7 +290,9 @@ class VAEGANStep:
         nz = self.E.fc_mu.out_features
         injected = eps is not None
         if self._static is None or self._static["real"].shape != real.shape:
+            old_rng = int(self._static["rng_offset"]) if self._static is not None else getattr(self, "_pending_rng", 0)
             self._static = self._alloc_static(batch, hw, nz)
+            self._static["rng_offset"].fill_(old_rng)
             self._graph = None
         s = self._static
         s["real"].copy_(real, non_blocking=True)
@@ -328,6 +347,25 @@ class VAEGANStep:
             for b, saved in zip(net.buffers(), bufs):
                 b.copy_(saved)
         self._static["rng_offset"].copy_(st["rng"])
+
+    # checkpoint / resume (vaegan_code.py:193 saves only the decoder; a resumable run also needs the optimizer state)
+    def state_dict(self):
+        """State of the fused step beyond the three modules' own (reference-keyed) state_dicts: the three Adam states
+        and the device noise counter.  Save it next to encoder / decoder / discriminator .state_dict()."""
+        rng = int(self._static["rng_offset"]) if self._static is not None else getattr(self, "_pending_rng", 0)
+        return {"opt_E": self.opt_E.state_dict(), "opt_G": self.opt_G.state_dict(), "opt_D": self.opt_D.state_dict(),
+                "rng_offset": rng, "seed": self.seed}
+
+    def load_state_dict(self, sd):
+        """Load after the modules' own load_state_dict (their parameters are views of this step's flat buffers, so that
+        copy lands in place)."""
+        self.opt_E.load_state_dict(sd["opt_E"])
+        self.opt_G.load_state_dict(sd["opt_G"])
+        self.opt_D.load_state_dict(sd["opt_D"])
+        self.seed = sd.get("seed", self.seed)
+        self._pending_rng = int(sd.get("rng_offset", 0))
+        if self._static is not None:
+            self._static["rng_offset"].fill_(self._pending_rng)
 
     def last_outputs(self):
         """mu, logvar, recon of the most recent step (device tensors; static under CUDA-graph replay)."""
