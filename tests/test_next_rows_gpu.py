@@ -87,17 +87,16 @@ def test_validation_denoise_pass_fp32():
 
 
 def test_checkpoint_and_optimizer_state_resume():
-    """Three steps in one go == two steps, checkpoint (module state_dicts with the reference's keys + the fused step's
-    optimizer / noise state), fresh objects, load, third step."""
+    """Two steps, checkpoint (module state_dicts with the reference's keys + the fused step's optimizer / noise
+    state), fresh objects with different weights, load: the restored state is bit-identical, and the third step from
+    the restored objects agrees with the third step of the original run (to the run-to-run noise of fp32 atomics
+    feeding Adam's sign-like first updates)."""
     from oracle import vaegan_oracle as vo
     hw, nz, batch = 64, 128, 8
-    _, nets_a = make_pair(hw, nz, "fp32")
     _, nets_b = make_pair(hw, nz, "fp32")
     _, nets_c = make_pair(hw, nz, "fp32", seed=7)          # different initial weights: must be overwritten by the load
-    sa, sb = _step_cls()(*nets_a, use_cuda_graph=False), _step_cls()(*nets_b, use_cuda_graph=False)
+    sb = _step_cls()(*nets_b, use_cuda_graph=False)
     inputs = [tuple(t.cuda() for t in vo.make_inputs(batch, hw, nz, seed=20 + i)) for i in range(3)]
-    for i in range(3):
-        la = sa.step(inputs[i][0], 50, *inputs[i][1:])
     for i in range(2):
         sb.step(inputs[i][0], 50, *inputs[i][1:])
     ckpt = {"E": copy.deepcopy(nets_b[0].state_dict()), "G": copy.deepcopy(nets_b[1].state_dict()),
@@ -107,10 +106,13 @@ def test_checkpoint_and_optimizer_state_resume():
     for net, key in zip(nets_c, "EGD"):
         net.load_state_dict(ckpt[key])
     sc.load_state_dict(ckpt["step"])
-    lc = sc.step(inputs[2][0], 50, *inputs[2][1:])
-    torch.cuda.synchronize()
-    for k in la:
-        assert abs(float(la[k]) - float(lc[k])) <= 2e-4 * abs(float(la[k])) + 1e-6, k
-    for (k, a), (_, c) in zip(nets_a[1].state_dict().items(), nets_c[1].state_dict().items()):
-        if a.dtype.is_floating_point:
-            assert float((a - c).abs().max()) <= 1e-4 * float(a.abs().max()) + 2e-4 * 0.5, k   # within lr/2 (sign noise)
+    for ob, oc in ((sb.opt_E, sc.opt_E), (sb.opt_G, sc.opt_G), (sb.opt_D, sc.opt_D)):
+        assert torch.equal(ob.params, oc.params) and torch.equal(ob.exp_avg, oc.exp_avg)
+        assert torch.equal(ob.exp_avg_sq, oc.exp_avg_sq) and int(ob.step_count) == int(oc.step_count)
+    for nb, nc in zip(nets_b, nets_c):
+        for (k, a), (_, c) in zip(nb.state_dict().items(), nc.state_dict().items()):
+            assert torch.equal(a, c), k
+    lb = {k: float(v) for k, v in sb.step(inputs[2][0], 50, *inputs[2][1:]).items()}
+    lc = {k: float(v) for k, v in sc.step(inputs[2][0], 50, *inputs[2][1:]).items()}
+    for k in lb:
+        assert abs(lb[k] - lc[k]) <= 1e-2 * abs(lb[k]) + 1e-6, (k, lb[k], lc[k])
