@@ -211,6 +211,22 @@ def run_gpu_arm(args):
     # Every rank runs it (the step contains the gradient all-reduce).
     dom = _dominant_kernel(torch, step, dev_pool[0], epoch, ms_per_step)
 
+    # ---- e2e with the images shipped as decoded uint8 NHWC (1 byte per value) and normalised on the device
+    u8_pool = [((h.permute(0, 2, 3, 1) * 0.5 + 0.5) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+               for h in host_pool]
+    for i in range(3):
+        step.step(u8_pool[i % n_pool], epoch)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        losses = step.step(u8_pool[i % n_pool], epoch)
+        _ = float(losses["total"])
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * B * args.steps / float(t)
+
     if rank != 0:
         _finish(world)
         return 0
@@ -236,6 +252,9 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * HW * HW * 4,
                 "d2h_bytes_per_step": 4},
+        "e2e_uint8_input": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * HW * HW,
+                            "d2h_bytes_per_step": 4,
+                            "what": "same step, host batch = decoded uint8 NHWC images, ToTensor+Normalize on the device"},
         "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else None,
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["sustained"], "unit": "TFLOP/s",

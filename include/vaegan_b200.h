@@ -209,6 +209,10 @@ int vg_nchw_to_s2d(const float* src, const float* aux, void* dst, int batch, int
                    int mode, float sigma, int clamp, void* stream);
 int vg_s2d_to_nchw(const void* src, float* dst, int batch, int channels, int h, int w, int origin, VgAct act,
                    float slope, void* stream);
+/* uint8 NHWC image batch -> fp32 NCHW, y = (x/255 - mean)/std: the reference's ToTensor + Normalize((0.5,)*3,
+ * (0.5,)*3) (dataset_code.py:147-150) on the device, so the host ships 1 byte per value instead of 4. */
+int vg_u8_nhwc_to_nchw(const void* src, float* dst, int batch, int channels, int h, int w, float mean, float std,
+                       void* stream);
 /* dst[i] (+)= sum_{j<fan} src[idx[i*fan+j]] (negative index = no term): builds the equivalent 64-channel weights of
  * the space-to-depth convolutions from the reference-layout masters and folds their gradients back. */
 int vg_gather_f32(float* dst, const float* src, const int* idx, long long n, int fan, int accumulate, void* stream);

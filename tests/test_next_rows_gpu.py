@@ -116,3 +116,22 @@ def test_checkpoint_and_optimizer_state_resume():
     lc = {k: float(v) for k, v in sc.step(inputs[2][0], 50, *inputs[2][1:]).items()}
     for k in lb:
         assert abs(lb[k] - lc[k]) <= 1e-2 * abs(lb[k]) + 1e-6, (k, lb[k], lc[k])
+
+
+def test_uint8_nhwc_input_path():
+    """Section 8(f) rank 4: decoded uint8 NHWC images normalised on the device (dataset_code.py:147-150's ToTensor +
+    Normalize(0.5, 0.5)) give the same step as the fp32 NCHW tensor the reference's loader would have produced."""
+    from oracle import vaegan_oracle as vo
+    hw, nz, batch = 64, 128, 8
+    _, nets_a = make_pair(hw, nz, "fp32")
+    _, nets_b = make_pair(hw, nz, "fp32")
+    sa, sb = _step_cls()(*nets_a, use_cuda_graph=False), _step_cls()(*nets_b, use_cuda_graph=False)
+    img = torch.randint(0, 256, (batch, hw, hw, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    as_loader = (img.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
+    _, eps, n_real, n_fake = vo.make_inputs(batch, hw, nz)
+    la = sa.step(img.cuda(), 50, eps.cuda(), n_real.cuda(), n_fake.cuda())
+    lb = sb.step(as_loader.cuda(), 50, eps.cuda(), n_real.cuda(), n_fake.cuda())
+    torch.cuda.synchronize()
+    assert float((sa._static["real"] - sb._static["real"]).abs().max()) <= 2.4e-7        # one fp32 ulp near 1
+    for k in la:
+        assert abs(float(la[k]) - float(lb[k])) <= 1e-5 * abs(float(lb[k])) + 1e-7, k

@@ -982,6 +982,20 @@ __global__ void __launch_bounds__(kThreads) s2d_to_nchw_kernel(const __nv_bfloat
     }
 }
 
+// uint8 NHWC image batch (what an image decoder produces; dataset_code.py:147-150 then applies ToTensor + Normalize)
+// -> fp32 NCHW, y = (x/255 - mean) / std.  One thread per pixel: coalesced 3-byte reads, W-contiguous writes.
+__global__ void __launch_bounds__(kThreads) u8_nhwc_to_nchw_kernel(const unsigned char* __restrict__ src,
+                                                                  float* __restrict__ dst, int B, int C, long long HW,
+                                                                  float mean, float inv_std) {
+    const long long total = static_cast<long long>(B) * HW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / HW, p = i - b * HW;
+        for (int c = 0; c < C; ++c)
+            dst[(b * C + c) * HW + p] = (static_cast<float>(src[i * C + c]) * (1.f / 255.f) - mean) * inv_std;
+    }
+}
+
 // dst[i] (+)= sum_j src[idx[i*fan + j]]  (idx < 0 = no term): equivalent-weight construction and its gradient
 __global__ void __launch_bounds__(kThreads) gather_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                              const int* __restrict__ idx, long long n, int fan,
@@ -1281,6 +1295,19 @@ extern "C" int vg_s2d_to_nchw(const void* src, float* dst, int B, int C, int H, 
     const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
     s2d_to_nchw_kernel<<<grid_for(blocks), kThreads, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(src), dst, B, C, H, W, origin, act, slope);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_u8_nhwc_to_nchw(const void* src, float* dst, int B, int C, int H, int W, float mean, float std,
+                                  void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr) return fail(VG_ERR_ARG, "u8_nhwc_to_nchw: null pointer");
+    if (std == 0.f) return fail(VG_ERR_ARG, "u8_nhwc_to_nchw: std must not be zero");
+    const long long HW = static_cast<long long>(H) * W;
+    u8_nhwc_to_nchw_kernel<<<grid_for(B * HW), kThreads, 0, as_stream(stream)>>>(
+        static_cast<const unsigned char*>(src), dst, B, C, HW, mean, 1.f / std);
     VG_LAUNCHED();
     return VG_OK;
 }

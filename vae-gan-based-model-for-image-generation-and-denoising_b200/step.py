@@ -286,16 +286,30 @@ class VAEGANStep:
              n_denoise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """One training step on `real` (fp32 NCHW in [-1, 1], device or pinned host tensor).  Noise tensors may be
         injected (parity tests) - otherwise they are drawn on the device.  Returns 0-d device tensors."""
-        batch, _, hw, _ = real.shape
+        u8 = real.dtype == torch.uint8          # decoded images [B, H, W, 3]: normalised on the device
+        if u8:
+            batch, hw, _, ch = real.shape
+            if ch != 3:
+                raise RuntimeError(f"uint8 input must be NHWC with 3 channels, got {list(real.shape)}")
+            shape = (batch, 3, hw, hw)
+        else:
+            batch, _, hw, _ = real.shape
+            shape = tuple(real.shape)
         nz = self.E.fc_mu.out_features
         injected = eps is not None
-        if self._static is None or self._static["real"].shape != real.shape:
+        if self._static is None or tuple(self._static["real"].shape) != shape:
             old_rng = int(self._static["rng_offset"]) if self._static is not None else getattr(self, "_pending_rng", 0)
             self._static = self._alloc_static(batch, hw, nz)
             self._static["rng_offset"].fill_(old_rng)
             self._graph = None
         s = self._static
-        s["real"].copy_(real, non_blocking=True)
+        if u8:
+            if s.get("real_u8") is None or s["real_u8"].shape != real.shape:
+                s["real_u8"] = torch.empty(real.shape, dtype=torch.uint8, device=self.dev)
+            s["real_u8"].copy_(real, non_blocking=True)
+            call("vg_u8_nhwc_to_nchw", _p(s["real_u8"]), _p(s["real"]), batch, 3, hw, hw, 0.5, 0.5, _stream())
+        else:
+            s["real"].copy_(real, non_blocking=True)
         s["kl_w"].fill_(self.alpha_kl * min(1.0, epoch / self.kl_warmup) if self.kl_warmup > 0 else self.alpha_kl)
         if injected:
             s["eps"].copy_(eps, non_blocking=True)
