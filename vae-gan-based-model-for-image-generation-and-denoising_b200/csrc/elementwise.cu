@@ -725,13 +725,19 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
     for (int j = 0; j < V; ++j) {
         const int c = c0 + j;
         const float* sg = sums + static_cast<long long>(grp) * 2 * C;
-        const double m = static_cast<double>(sg[c]) * inv_n;
-        double var = static_cast<double>(sg[C + c]) * inv_n - m * m;
-        if (var < 0.0) var = 0.0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        // The fp32 sums carry ~1e-7 relative error already; a double-precision divide + square root per channel in every
+        // thread's prologue was a multi-microsecond latency in front of each (short) apply pass.  fp32 with one
+        // Newton step on rsqrt is within 2 ulp of the double result.
+        const float mf = sg[c] * static_cast<float>(inv_n);
+        const float var_f = fmaxf(fmaf(-mf, mf, sg[C + c] * static_cast<float>(inv_n)), 0.f);
+        float rstd = rsqrtf(var_f + eps);
+        rstd = rstd * fmaf(-0.5f * (var_f + eps) * rstd, rstd, 1.5f);
+        const double m = static_cast<double>(mf);
+        const double var = static_cast<double>(var_f);
+        (void)var;
         const float g = gamma ? __ldg(gamma + c) : 1.f, bt = beta ? __ldg(beta + c) : 0.f;
         sc[j] = g * rstd;
-        sh[j] = bt - static_cast<float>(m) * sc[j];
+        sh[j] = bt - mf * sc[j];
         if (publisher) {
             float* st = stats + static_cast<long long>(grp) * 4 * C;
             st[c] = static_cast<float>(m);
