@@ -720,6 +720,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
     const int c0 = static_cast<int>((tid * V) % C);
     const double inv_n = 1.0 / static_cast<double>(rows);
     const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
+    // the first batch of activation loads is issued BEFORE the finalisation below waits on the sums: short passes were
+    // paying a full dependent round trip (sums -> math -> first load) on top of ~3 us of streaming
+    float v[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (tid + u * stride < nvec) Vec<T>::load(x + (tid + u * stride) * V, v[u]);
     float sc[V], sh[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -763,10 +769,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
     }
     if (blockIdx.x == 0 && grp == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += groups;
     for (long long i = tid; i < nvec; i += stride * U) {
-        float v[U][V];
+        if (i != tid) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (i + u * stride < nvec) Vec<T>::load(x + (i + u * stride) * V, v[u]);
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride < nvec) Vec<T>::load(x + (i + u * stride) * V, v[u]);
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (i + u * stride >= nvec) continue;
@@ -796,6 +803,13 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
     const int c0 = static_cast<int>((tid * V) % C);
     const float inv_n = 1.f / static_cast<float>(rows);
     const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
+    float xv[U][V], dv[U][V];           // first batch in flight while the per-channel coefficients are fetched
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (tid + u * stride < nvec) {
+            Vec<T>::load(x + (tid + u * stride) * V, xv[u]);
+            Vec<T>::load(dz + (tid + u * stride) * V, dv[u]);
+        }
     float sc[V], kx[V], k0[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -811,13 +825,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
         }
     }
     for (long long i = tid; i < nvec; i += stride * U) {
-        float xv[U][V], dv[U][V];
+        if (i != tid) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (i + u * stride < nvec) {
-                Vec<T>::load(x + (i + u * stride) * V, xv[u]);
-                Vec<T>::load(dz + (i + u * stride) * V, dv[u]);
-            }
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride < nvec) {
+                    Vec<T>::load(x + (i + u * stride) * V, xv[u]);
+                    Vec<T>::load(dz + (i + u * stride) * V, dv[u]);
+                }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (i + u * stride >= nvec) continue;
