@@ -88,8 +88,14 @@ class _ReparamFn(torch.autograd.Function):
         ctx.save_for_backward(mu, logvar, eps, kl_weight_dev)
         return z
 
+    # called (once) when the gradient w.r.t. z arrives, i.e. when the generator's backward pass has been issued
+    on_generator_done = None
+
     @staticmethod
     def backward(ctx, dz):
+        cb, _ReparamFn.on_generator_done = _ReparamFn.on_generator_done, None
+        if cb is not None:
+            cb()
         mu, logvar, eps, klw = ctx.saved_tensors
         B, nz = mu.shape
         dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
@@ -145,6 +151,10 @@ class VAEGANStep:
         # side streams (parallel branches of the captured graph): weight gradients round-robin, plus the start-of-step
         # weight packing and noise generation that the encoder's forward pass does not wait for
         self.wgrad_streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)] if overlap_wgrad else []
+        # data parallel: the generator's gradient all-reduce (the largest message) starts as soon as its backward has
+        # been issued and runs under the encoder's backward pass on its own stream
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if (overlap_wgrad and self.world > 1) else None
+        self._g_reduced = False
         self._graph = None
         self._static = None
         self.launches_per_step = None
@@ -264,21 +274,41 @@ class VAEGANStep:
         d_params = list(D.parameters())
         for p in d_params:             # weight gradients of D are never used in this phase (reference discards them)
             p.requires_grad_(False)
+        self._g_reduced = False
+        if self.comm_stream is not None:
+            _ReparamFn.on_generator_done = self._reduce_generator_early
         try:
             p_fake = D.forward_nhwc(recon_noisy)
             call("vg_bce", _p(p_fake), B, self.real_label, self.alpha_adv, _p(loss[4:5]), 0, _p(s["dp_a"]), _stream())
             torch.autograd.backward([p_fake], [s["dp_a"]])
         finally:
+            _ReparamFn.on_generator_done = None
             for p in d_params:
                 p.requires_grad_(True)
         call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
              _p(loss[5:6]), _stream())
         F_.WgradOverlap.join()
         self._allreduce(self.opt_E)
-        self._allreduce(self.opt_G)
+        if self._g_reduced:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            self._allreduce(self.opt_G)
         self.opt_E.step(1.0 / self.world)
         self.opt_G.step(1.0 / self.world)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
+
+    def _reduce_generator_early(self):
+        """Runs inside the backward pass when dL/dz reaches the reparameterisation: every generator kernel (dgrad
+        chain on this stream, weight gradients on the side streams) has been issued and the encoder's backward is
+        still to come - the generator's gradient all-reduce goes to its own stream behind all of those.  (Its Adam
+        stays at the end of the step: launched here it saturates HBM and delays the encoder's chain of small kernels.)"""
+        comm, cur = self.comm_stream, torch.cuda.current_stream()
+        comm.wait_stream(cur)
+        for st in self.wgrad_streams:
+            comm.wait_stream(st)
+        with torch.cuda.stream(comm):
+            self._allreduce(self.opt_G)
+        self._g_reduced = True
 
     # ------------------------------------------------------------------------------------------ public API
     def step(self, real: torch.Tensor, epoch: int, eps: Optional[torch.Tensor] = None,
