@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HW, NZ, BATCH_PER_GPU = 64, 128, 256
+METRIC = "VAE-GAN train images/sec (64x64, latent 128, batch 256/GPU)"
 STEP_GFLOP_PER_IMAGE = 6.245          # algorithmic conv+linear FLOPs of one step / image
 
 
@@ -66,11 +67,13 @@ def run_reference_arm(args):
     steps = max(1, min(args.steps, 8))
     rate, sec, cores = _cpu_step_rate(sample_batch, timed=steps, warm=max(1, min(args.warmup, 2)))
     line = {
-        "impl": "reference", "metric": "VAE-GAN train images/sec (64x64, latent 128)", "value": rate,
+        "impl": "reference", "metric": METRIC, "value": rate,
         "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN, latent 128", "batch_per_gpu": BATCH_PER_GPU,
+        "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN (SURVEY A.1), latent 128",
+                   "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * args.gpus,
+                   "parallelism": f"dp{args.gpus}",
                    "note": "reference CPU arithmetic (torch CPU/oneDNN) on the oracle's line-by-line restatement of "
                            "vaegan_code.py:66-135"},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
@@ -241,7 +244,7 @@ def run_gpu_arm(args):
                "sample": "cfg1: 3 timed steps (median) of 64 images, fp32, same nets, oracle restatement of "
                          "vaegan_code.py:66-135 on torch CPU"}
     line = {
-        "metric": "VAE-GAN train images/sec (64x64, latent 128, batch 256/GPU)", "value": value, "unit": "images/s",
+        "metric": METRIC, "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN (SURVEY A.1), latent 128",
