@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HW, NZ, BATCH_PER_GPU = 64, 128, 256
-METRIC = "VAE-GAN train images/sec (64x64, latent 128, batch 256/GPU)"
+METRIC = "VAE-GAN train imgs/sec, 64x64 b256, 1/2/4/8 B200; conv tensor-pipe % of peak"     # BASELINE.json "metric", verbatim
 STEP_GFLOP_PER_IMAGE = 6.245          # algorithmic conv+linear FLOPs of one step / image
 
 
