@@ -59,11 +59,18 @@ static void pick_resident(IgemmParams& p, int extra_smem) {
     // the step is 1 % slower than with streamed weights - these layers are bound by the per-stage issue latency, not by
     // the fill rate.  Kept behind VG_BRES=1 for experiments.
     static const bool enabled = getenv("VG_BRES") != nullptr;
-    if (!enabled || tps != 1 || p.ksplit > 1 || m_items < 148 * 4 || res > 48 * 1024) return;
+    if (!enabled || tps != 1 || p.cps > 1 || p.ksplit > 1 || m_items < 148 * 4 || res > 48 * 1024) return;
     const int budget = 110 * 1024 - 2048 - extra_smem - res;
     if (budget / a_stage < 4) return;
     p.b_resident = 1;
     p.stages = std::min(8, budget / a_stage);
+}
+
+// Channel chunks per stage (IgemmParams::cps), experiment switch VG_CPS=<n>.
+static int pick_cps(const IgemmParams& p) {
+    static const int want = getenv("VG_CPS") ? atoi(getenv("VG_CPS")) : 1;
+    if (want <= 1 || p.tps > 1 || p.kchunk != 64 || p.n_tile > 64 || p.c_chunks % want != 0) return 1;
+    return want;
 }
 
 static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30, int extra_smem = 0) {
@@ -254,8 +261,9 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
             t.brow = (ky * k + kx) * g->small_c;
         }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
-                           igemm_fuse_smem_bytes(p));
+    p.cps = pick_cps(p);
+    p.stages = pick_stages(p.tps * p.cps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile,
+                           p.taps_per_phase / p.tps * p.c_chunks / p.cps, igemm_fuse_smem_bytes(p));
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -269,6 +277,11 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     if (ks > 1 && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
         p.ksplit = ks;
         p.splitk_acc = static_cast<float*>(ws);
+        if (p.cps > 1) {
+            p.cps = 1;
+            p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
+                                   igemm_fuse_smem_bytes(p));
+        }
     }
     pick_resident(p, igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
@@ -363,8 +376,9 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.osy = p.osx = s;
     }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
-                           igemm_fuse_smem_bytes(p));
+    p.cps = pick_cps(p);
+    p.stages = pick_stages(p.tps * p.cps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile,
+                           p.taps_per_phase / p.tps * p.c_chunks / p.cps, igemm_fuse_smem_bytes(p));
     pick_resident(p, igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_bytes = p.kchunk * 2;
-    const int tps = p.tps > 1 ? p.tps : 1;
+    const int cps = p.cps > 1 ? p.cps : 1;
+    const int tps = (p.tps > 1 ? p.tps : 1) * cps;                      // operand slabs per stage (taps or channel chunks)
     const int a_sub = 128 * row_bytes, b_sub = p.n_tile * row_bytes;   // one tap's operand tiles
     const int a_stage = tps * a_sub;
     const bool bres = p.b_resident != 0;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int total_items = m_tiles * p.n_tiles * p.num_phases * ksplit;
-    const int total_iters = p.taps_per_phase / tps * p.c_chunks;
+    const int total_iters = p.taps_per_phase * p.c_chunks / tps;
     const uint32_t ncols = tmem_cols_for(2 * p.n_tile);
 
     if (warp == 0 && lane == 0) {
@@ -163,9 +164,23 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                                         taps[t].brow + n0);
                 }
                 int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
+                if (cps > 1) { tap_i = 0; c = 0; }        // (never combined with split-K)
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty[s], par ^ 1);
                     mbar_expect_tx(&full[s], a_stage + b_stage);
+                    if (cps > 1) {
+                        // `cps` consecutive channel chunks of ONE tap share the stage
+                        const IgemmTap tap = taps[tap_i];
+                        for (int t = 0; t < cps; ++t) {
+                            tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], (c + t) * p.kchunk,
+                                        j0 + tap.dx, i0 + tap.dy, b0);
+                            tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], (c + t) * p.kchunk, tap.brow + n0);
+                        }
+                        c += cps;
+                        if (c >= p.c_chunks) { c = 0; ++tap_i; }
+                        if (++s == stages) { s = 0; par ^= 1; }
+                        continue;
+                    }
                     for (int t = 0; t < tps; ++t) {
                         const IgemmTap tap = taps[tap_i + t];
                         tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
@@ -216,7 +231,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     mbar_wait(&full[s], par);
                     tc_fence_after();
                     if (bres) b_lo = b_lo0 + static_cast<uint32_t>(it) * b_t;      // slab (tap, chunk) = iteration index
-                    if (ksteps == 4) {
+                    if (ksteps == 4 && tps == 1) {
                         umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
                         umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
                         umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
@@ -728,7 +743,7 @@ static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_b
 // dynamic shared memory of an fprop-type launch: ring (A + B, or A only with resident weights), resident weight
 // slabs, barriers, fused-epilogue tables
 int igemm_total_smem(const IgemmParams& p) {
-    const int tps = p.tps > 1 ? p.tps : 1;
+    const int tps = (p.tps > 1 ? p.tps : 1) * (p.cps > 1 ? p.cps : 1);
     const int a_stage = tps * 128 * p.kchunk * 2, b_sub = p.n_tile * p.kchunk * 2;
     const int ring = p.stages * (a_stage + (p.b_resident ? 0 : tps * b_sub));
     const int resident = p.b_resident ? p.taps_per_phase * p.c_chunks * b_sub : 0;
