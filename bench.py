@@ -86,7 +86,9 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms in the background; stop(t0, t1) keeps the samples whose timestamp lies inside
+    the measured window [t0, t1] (datetime.now() taken after a device synchronise at both ends)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -94,39 +96,46 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, seen = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
+            seen += 1
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                if t0 is not None and not (t0 <= ts <= t1):
+                    continue
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[3:7]):
+            for nm, val in zip(names, parts[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed window"],
+                    "samples": 0, "samples_total": seen}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_total": seen,
+                "window": "resident loop + e2e loop (the same step under continuous load)"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -171,6 +180,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import datetime
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # polling starts now; samples are windowed later
     # ---- warm-up (includes CUDA-graph capture), then count kernel launches of one step
     for i in range(max(3, args.warmup)):
         step.step(dev_pool[i % n_pool], epoch)
@@ -178,8 +189,8 @@ def run_gpu_arm(args):
     launches_per_step = step.launches_per_step
 
     # ---- value: inputs resident in HBM, K steps, CUDA events, max over ranks
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
+    t_window0 = datetime.datetime.now()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -187,7 +198,6 @@ def run_gpu_arm(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler is not None else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -204,6 +214,7 @@ def run_gpu_arm(args):
         _ = float(losses["total"])                       # device -> host read of the step result
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(t_window0, datetime.datetime.now()) if sampler is not None else None
     t = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
