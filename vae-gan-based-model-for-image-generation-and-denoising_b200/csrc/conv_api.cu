@@ -460,6 +460,18 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     // dw[m][n][tap..tap+3] contiguous and 16-byte aligned when k*k is a multiple of 4
     p.vec4_taps = (k * k) % 4 == 0 && p.taps_per_cta % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0 &&
                   (p.s_m % 4) == 0;
+    {
+        // CTA pairs sharing the Q operand (experiment switch VG_WGRAD2=1)
+        static const bool want_pair = getenv("VG_WGRAD2") != nullptr;
+        const int n_atoms = p.n_tile / p.q_atom_c;
+        p.pair = want_pair && p.m_tiles % 2 == 0 && p.m_atoms * p.p_atom_c == 128 && g->small_c % 128 == 0 &&
+                 (p.merge * n_atoms) % 2 == 0 && p.taps_per_cta % p.merge == 0 && p.num_taps % p.taps_per_cta == 0;
+        if (p.pair) {
+            // each CTA of a pair holds half of every Q stage: the same shared memory carries a ring twice as deep
+            const int a_stage_b = p.tw * p.th * p.tb * 256, b_half = p.merge * p.n_tile * p.tw * p.th * p.tb;
+            p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage_b) / b_half));
+        }
+    }
     if (p.splits > 1) {
         const size_t need = wgrad_partial_bytes(p);
         if (ws_needed != nullptr) { *ws_needed = need; return VG_OK; }

@@ -444,7 +444,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
-__global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+// PAIR = true: launched as clusters of two CTAs along grid.y holding consecutive M tiles of the same N tile; the pair
+// issues M = 256 UMMAs (cta_group::2).  Each CTA loads its own P tile and HALF of the Q atoms of every stage, so the
+// Q operand - the bulk of the L2 -> shared-memory traffic that bounds this kernel - is fetched once per pair.
+template <bool PAIR>
+__device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     const int merge = p.merge > 1 ? p.merge : 1;
     const int a_stage = kpix * 256;                                  // room for all 128 M rows (128 ch x 2 B) per pixel
     const int tap_bytes = n_atoms * q_atom_bytes;                    // one tap's Q tile
-    const int b_stage = merge * tap_bytes;
+    const int b_stage = merge * tap_bytes / (PAIR ? 2 : 1);          // a pair CTA holds half of the stage's Q atoms
     const int SA = p.stages_a, SB = p.stages_b;
     uint8_t* sA = smem;
     uint8_t* sB = smem + SA * a_stage;
@@ -467,8 +471,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     uint64_t* tmem_full = empty_b + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-    const int split = blockIdx.x;
-    const int m_tile = blockIdx.y / p.n_tiles, n_tile_idx = blockIdx.y % p.n_tiles;
+    // plain: grid = (splits, tiles, tap groups).  pairs: grid = (tiles, splits, tap groups) with the cluster along x
+    // (a CTA pair is two consecutive x ranks) and tile = n_tile_idx * m_tiles + m_tile, i.e. M tiles 2j and 2j+1
+    const int split = PAIR ? blockIdx.y : blockIdx.x;
+    const int tile_idx = PAIR ? blockIdx.x : blockIdx.y;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int m_tile = PAIR ? tile_idx % p.m_tiles : tile_idx / p.n_tiles;
+    const int n_tile_idx = PAIR ? tile_idx / p.m_tiles : tile_idx % p.n_tiles;
     const int m0 = m_tile * p.m_atoms * p.p_atom_c, n0 = n_tile_idx * p.n_tile;
     const int tap0 = blockIdx.z * p.taps_per_cta;
     const int ntap = min(p.taps_per_cta, p.num_taps - tap0);
@@ -487,11 +496,12 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, ncols);
-        tmem_relinquish();
+        if (PAIR) { tmem_alloc_pair(tmem_slot, ncols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, ncols); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -506,7 +516,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 const int j0 = tj * p.tw, i0 = ti * p.th, b0 = tb_i * p.tb;
                 mbar_wait(&empty_a[sa], par_a ^ 1);
-                if (p.debug_flags & 8) {
+                if (PAIR) {
+                    // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
+                    if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
+                    for (int a = 0; a < p.m_atoms; ++a)
+                        tma_load_4d_pair(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c,
+                                         j0, i0, b0);
+                } else if (p.debug_flags & 8) {
                     mbar_arrive(&full_a[sa]);
                 } else {
                     mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
@@ -517,7 +533,18 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const int cnt = min(merge, ntap - tl);
                     mbar_wait(&empty_b[sb], par_b ^ 1);
-                    if (p.debug_flags & 8) {
+                    if (PAIR) {
+                        // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
+                        const int half = cnt * n_atoms / 2;
+                        if (rank == 0) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                        for (int h = 0; h < half; ++h) {
+                            const int idx = static_cast<int>(rank) * half + h;
+                            const int j = idx / n_atoms, a = idx - j * n_atoms;
+                            const IgemmTap tap = p.taps[tap0 + tl + j];
+                            tma_load_4d_pair(sB + sb * b_stage + h * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
+                                             n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                        }
+                    } else if (p.debug_flags & 8) {
                         mbar_arrive(&full_b[sb]);
                     } else {
                         mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
@@ -535,10 +562,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_full = make_idesc_bf16(128, merge * p.n_tile, 1, 1);
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc_full = make_idesc_bf16(PAIR ? 256 : 128, merge * p.n_tile, 1, 1);
             const int tail = ntap % merge;
-            const uint32_t idesc_tail = make_idesc_bf16(128, (tail ? tail : merge) * p.n_tile, 1, 1);
+            const uint32_t idesc_tail = make_idesc_bf16(PAIR ? 256 : 128, (tail ? tail : merge) * p.n_tile, 1, 1);
             const uint32_t p_layout = p.p_atom_c == 64 ? 2u : 4u;
             const uint32_t q_layout = p.q_atom_c == 64 ? 2u : (p.q_atom_c == 32 ? 4u : 6u);
             const int ksteps = kpix / 16;
@@ -560,7 +587,11 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                     const uint32_t idesc = (tl + merge <= ntap) ? idesc_full : idesc_tail;
                     mbar_wait(&full_b[sb], par_b);
                     tc_fence_after();
-                    if (p.debug_flags & 4) {
+                    if (PAIR) {
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
+                        umma_commit_pair(&empty_b[sb]);
+                    } else if (p.debug_flags & 4) {
                         mbar_arrive(&empty_b[sb]);
                     } else {
                         if (ksteps == 8) {
@@ -583,12 +614,14 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
                     b_lo += b_step;
                     if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
                 }
-                if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
+                if (PAIR) umma_commit_pair(&empty_a[sa]);
+                else if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
                 else umma_commit(&empty_a[sa]);
                 a_lo += a_step;
                 if (++sa == SA) { sa = 0; par_a ^= 1; a_lo = a_lo0; }
             }
-            umma_commit(tmem_full);
+            if (PAIR) umma_commit_pair(tmem_full);
+            else umma_commit(tmem_full);
         }
     } else {
         const int q = warp & 3;
@@ -601,7 +634,8 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (p.splits > 1) {
             // partial tile -> workspace: [cta][tap_local][row][n_tile]; each thread writes its row contiguously
-            const long long cta = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            const long long y_canon = static_cast<long long>(m_tile) * p.n_tiles + n_tile_idx;
+            const long long cta = (static_cast<long long>(blockIdx.z) * (p.m_tiles * p.n_tiles) + y_canon) * p.splits + split;
             float* base = p.partial + cta * static_cast<long long>(p.taps_per_cta) * 128 * p.n_tile;
             for (int tl = 0; tl < ntap; ++tl) {
                 float4* dst = reinterpret_cast<float4*>(base + (static_cast<long long>(tl) * 128 + row) * p.n_tile);
@@ -673,7 +707,20 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if (PAIR) {
+        cluster_sync_all();            // the peer's shared memory / barriers stay alive until both CTAs are done
+        if (warp == 1) tmem_dealloc_pair(tmem_base, ncols);
+    } else {
+        if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    }
+}
+
+__global__ void __launch_bounds__(kIgemmThreads) igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    wgrad_body<false>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads)
+    igemm_wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
+    wgrad_body<true>(p);
 }
 
 // dw[m][n][tap] += sum over splits of partial[cta(split, mn, group)][tap_local][row][col]
@@ -793,15 +840,25 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const cudaError_t e2 =
+            cudaFuncSetAttribute(igemm_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess) attr_err = e2;
     });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     const int kpix = p.tw * p.th * p.tb;
-    const int smem = p.stages_a * kpix * 256 + p.stages_b * (p.merge > 1 ? p.merge : 1) * p.n_tile * kpix * 2 + 1024 +
-                     kBarrierBytes;
+    const int smem = p.stages_a * kpix * 256 +
+                     p.stages_b * (p.merge > 1 ? p.merge : 1) * p.n_tile * kpix * 2 / (p.pair ? 2 : 1) + 1024 + kBarrierBytes;
     const int tap_groups = (p.num_taps + p.taps_per_cta - 1) / p.taps_per_cta;
     dim3 grid(p.splits, p.m_tiles * p.n_tiles, tap_groups);
-    igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (p.pair) {
+        const dim3 pgrid(p.m_tiles * p.n_tiles, p.splits, tap_groups);          // cluster (2, 1, 1) from the kernel attribute
+        igemm_wgrad_pair_kernel<<<pgrid, kIgemmThreads, smem, stream>>>(p);
+        e = cudaGetLastError();
+    } else {
+        igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess || p.splits <= 1) return static_cast<int>(e);
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * p.num_taps / (p.vec4_taps ? 4 : 1);
     const bool chunked = p.splits >= 16 && total <= 32768;   // few outputs, many splits
