@@ -445,6 +445,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.splits = base_ctas >= 100 ? 1 : std::max(1, std::min(total_tiles, 148 / base_ctas));
     const int a_stage = kpix * 256, b_stage = p.merge * p.n_tile * kpix * 2;
     p.stages_a = kpix >= 128 ? 2 : 3;
+    if (const char* sa = getenv("VG_WGRAD_SA")) p.stages_a = std::max(2, atoi(sa));      // experiment switch
     p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;
     {

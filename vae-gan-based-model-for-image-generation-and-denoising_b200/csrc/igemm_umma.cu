@@ -448,6 +448,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // issues M = 256 UMMAs (cta_group::2).  Each CTA loads its own P tile and HALF of the Q atoms of every stage, so the
 // Q operand - the bulk of the L2 -> shared-memory traffic that bounds this kernel - is fetched once per pair.
 template <bool PAIR>
+// experiment switch: -DVG_WGRAD_SPIN=1 makes the producer / MMA threads of the weight-gradient kernel busy-poll
+// (measured: no difference - the per-stage time of this kernel is not barrier-wake-up latency)
+#ifndef VG_WGRAD_SPIN
+#define VG_WGRAD_SPIN 0
+#endif
+#if VG_WGRAD_SPIN
+#define WGRAD_WAIT mbar_wait_spin
+#else
+#define WGRAD_WAIT mbar_wait
+#endif
 __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -515,7 +525,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             int ti = t0 % p.tiles_h, tb_i = t0 / p.tiles_h;
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 const int j0 = tj * p.tw, i0 = ti * p.th, b0 = tb_i * p.tb;
-                mbar_wait(&empty_a[sa], par_a ^ 1);
+                WGRAD_WAIT(&empty_a[sa], par_a ^ 1);
                 if (PAIR) {
                     // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
                     if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
@@ -532,7 +542,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 }
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const int cnt = min(merge, ntap - tl);
-                    mbar_wait(&empty_b[sb], par_b ^ 1);
+                    WGRAD_WAIT(&empty_b[sb], par_b ^ 1);
                     if (PAIR) {
                         // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
                         const int half = cnt * n_atoms / 2;
@@ -580,12 +590,12 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             int sa = 0, sb = 0;
             uint32_t par_a = 0, par_b = 0, a_lo = a_lo0, b_lo = b_lo0;
             for (int pt = pt_begin; pt < pt_end; ++pt) {
-                mbar_wait(&full_a[sa], par_a);
+                WGRAD_WAIT(&full_a[sa], par_a);
                 const uint32_t acc = pt != pt_begin;
                 uint32_t d_tmem = tmem_base;
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const uint32_t idesc = (tl + merge <= ntap) ? idesc_full : idesc_tail;
-                    mbar_wait(&full_b[sb], par_b);
+                    WGRAD_WAIT(&full_b[sb], par_b);
                     tc_fence_after();
                     if (PAIR) {
                         for (int k = 0; k < ksteps; ++k)

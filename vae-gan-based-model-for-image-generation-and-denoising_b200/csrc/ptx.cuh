@@ -68,6 +68,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Busy-polling wait (mbarrier.test_wait never suspends the thread): for the single-thread producer / MMA roles whose
+// barrier round trips sit on the critical path - try_wait parks the thread for a system-dependent time when the phase
+// is not complete yet, which costs microseconds per miss on shallow rings.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > VG_WAIT_CYCLES) {
+            printf("vg: mbarrier spin-wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
