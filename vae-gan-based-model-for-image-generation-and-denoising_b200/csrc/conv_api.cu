@@ -45,34 +45,6 @@ static int pick_tps(int kchunk, int c_chunks, int taps) {
     return 1;
 }
 
-// Small weight tensors stay resident in shared memory (IgemmParams::b_resident): the CTA's consecutive work items share
-// the (phase, N tile) slabs, so only the activation tiles stream through the ring - the N <= 64 / K <= 512 layers are
-// bound by the L2 -> shared-memory fill rate, and the weights were a third of it.
-static void pick_resident(IgemmParams& p, int extra_smem) {
-    p.b_resident = 0;
-    const int tps = p.tps > 1 ? p.tps : 1;
-    const long long m_items = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b;
-    const int res = p.taps_per_phase * p.c_chunks * p.n_tile * p.kchunk * 2;
-    const int a_stage = 128 * p.kchunk * 2;
-    // Measured (round 1): NOT a win.  With one CTA per SM (64 KB of slabs) the single MMA-issuing thread leaves the
-    // tensor pipe idle between stages and the 128->64 generator stage runs 1.7x slower; with two CTAs per SM (<= 48 KB)
-    // the step is 1 % slower than with streamed weights - these layers are bound by the per-stage issue latency, not by
-    // the fill rate.  Kept behind VG_BRES=1 for experiments.
-    static const bool enabled = getenv("VG_BRES") != nullptr;
-    if (!enabled || tps != 1 || p.cps > 1 || p.ksplit > 1 || m_items < 148 * 4 || res > 48 * 1024) return;
-    const int budget = 110 * 1024 - 2048 - extra_smem - res;
-    if (budget / a_stage < 4) return;
-    p.b_resident = 1;
-    p.stages = std::min(8, budget / a_stage);
-}
-
-// Channel chunks per stage (IgemmParams::cps), experiment switch VG_CPS=<n>.
-static int pick_cps(const IgemmParams& p) {
-    static const int want = getenv("VG_CPS") ? atoi(getenv("VG_CPS")) : 1;
-    if (want <= 1 || p.tps > 1 || p.kchunk != 64 || p.n_tile > 64 || p.c_chunks % want != 0) return 1;
-    return want;
-}
-
 static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30, int extra_smem = 0) {
     // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question:
     // narrow accumulators leave room for two CTAs per SM (110 KB each), wide ones take the whole SM.
@@ -142,8 +114,10 @@ bool umma_wgrad_ok(const VgConvGeom* g) {
 // ---------------------------------------------------------------------------------------------- fused epilogues
 // Tiling decisions shared by the launchers and by vg_conv_epilogue_supported.
 // Few work items (small late layers): narrower N tiles put more SMs to work; the UMMA time per item falls with N.
+// Only well below one wave: 128 items of N = 256 on 148 SMs beat 256 items of N = 128 (47 vs 60 us on the
+// 512->1024 4x4 layer) - wide tiles need fewer issue slots and fewer fill bytes per FLOP.
 static int shrink_n_tile(int n_total, int n_tile, long long m_items) {
-    while (m_items * (n_total / n_tile) < 148 && n_tile % 64 == 0 && n_total % (n_tile / 2) == 0) n_tile /= 2;
+    while (m_items * (n_total / n_tile) < 96 && n_tile % 64 == 0 && n_total % (n_tile / 2) == 0) n_tile /= 2;
     return n_tile;
 }
 
@@ -261,9 +235,8 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
             t.brow = (ky * k + kx) * g->small_c;
         }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.cps = pick_cps(p);
-    p.stages = pick_stages(p.tps * p.cps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile,
-                           p.taps_per_phase / p.tps * p.c_chunks / p.cps, igemm_fuse_smem_bytes(p));
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
+                           igemm_fuse_smem_bytes(p));
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -277,13 +250,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     if (ks > 1 && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
         p.ksplit = ks;
         p.splitk_acc = static_cast<float*>(ws);
-        if (p.cps > 1) {
-            p.cps = 1;
-            p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
-                                   igemm_fuse_smem_bytes(p));
-        }
     }
-    pick_resident(p, igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
     note_launch(p.ksplit > 1 ? 2 : 1);
@@ -376,10 +343,8 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.osy = p.osx = s;
     }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
-    p.cps = pick_cps(p);
-    p.stages = pick_stages(p.tps * p.cps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile,
-                           p.taps_per_phase / p.tps * p.c_chunks / p.cps, igemm_fuse_smem_bytes(p));
-    pick_resident(p, igemm_fuse_smem_bytes(p));
+    p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
+                           igemm_fuse_smem_bytes(p));
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();

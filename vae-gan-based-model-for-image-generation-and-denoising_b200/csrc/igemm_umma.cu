@@ -13,6 +13,12 @@
 
 namespace vg {
 
+// tcgen05.fence::after_thread_sync after every "stage full" wait of the MMA-issuing thread: the operands arrive through
+// the async proxy (TMA -> mbarrier complete_tx) and are consumed by tcgen05.mma in the same proxy, so the fence orders
+// nothing that the mbarrier does not already order.  -DVG_STAGE_FENCE=1 restores it (experiment switch).
+#ifndef VG_STAGE_FENCE
+#define VG_STAGE_FENCE 0
+#endif
 static constexpr int kIgemmThreads = 192;
 static constexpr int kMaxStages = 24;
 static constexpr int kBarrierBytes = (4 * kMaxStages + 4) * 8 + 16;
@@ -59,23 +65,18 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_bytes = p.kchunk * 2;
-    const int cps = p.cps > 1 ? p.cps : 1;
-    const int tps = (p.tps > 1 ? p.tps : 1) * cps;                      // operand slabs per stage (taps or channel chunks)
+    const int tps = p.tps > 1 ? p.tps : 1;
     const int a_sub = 128 * row_bytes, b_sub = p.n_tile * row_bytes;   // one tap's operand tiles
     const int a_stage = tps * a_sub;
-    const bool bres = p.b_resident != 0;
-    const int b_res_bytes = bres ? p.taps_per_phase * p.c_chunks * b_sub : 0;
-    const int b_stage = bres ? 0 : tps * b_sub;
+    const int b_stage = tps * b_sub;
     const int stages = p.stages;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + stages * a_stage;         // B ring, or the resident weight slabs
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage + b_res_bytes);
+    uint8_t* sB = smem + stages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint64_t* bres_full = tmem_empty + 2;          // resident weights landed / may be overwritten
-    uint64_t* bres_empty = bres_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_empty + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     // fused-epilogue scratch: per-CTA channel sums [groups][2][C], then (mode 2) per-channel (mean, rstd, scale, shift)
     constexpr int fmode = FMODE;
     const int fC = p.fuse_c;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int total_items = m_tiles * p.n_tiles * p.num_phases * ksplit;
-    const int total_iters = p.taps_per_phase * p.c_chunks / tps;
+    const int total_iters = p.taps_per_phase / tps * p.c_chunks;
     const uint32_t ncols = tmem_cols_for(2 * p.n_tile);
 
     if (warp == 0 && lane == 0) {
@@ -109,8 +110,6 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
         }
-        mbar_init(bres_full, 1);
-        mbar_init(bres_empty, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -143,52 +142,22 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         if (lane == 0) {
             int s = 0;
             uint32_t par = 0;
-            int res_group = -1;
-            uint32_t res_par = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 int i0, j0, b0, n0, phase, it_begin, iters;
                 decode(item, i0, j0, b0, n0, phase, it_begin, iters);
                 const IgemmTap* taps = &p.taps[phase * p.taps_per_phase];
-                if (bres && phase * p.n_tiles + n0 / p.n_tile != res_group) {
-                    // new (phase, N tile): once the MMA thread has retired every instruction that read the old slabs,
-                    // load all weight slabs of the new one
-                    if (res_group >= 0) {
-                        mbar_wait(bres_empty, res_par);
-                        res_par ^= 1;
-                    }
-                    res_group = phase * p.n_tiles + n0 / p.n_tile;
-                    mbar_expect_tx(bres_full, b_res_bytes);
-                    for (int t = 0; t < p.taps_per_phase; ++t)
-                        for (int cc = 0; cc < p.c_chunks; ++cc)
-                            tma_load_2d(sB + (t * p.c_chunks + cc) * b_sub, &p.bmap, bres_full, cc * p.kchunk,
-                                        taps[t].brow + n0);
-                }
                 int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
-                if (cps > 1) { tap_i = 0; c = 0; }        // (never combined with split-K)
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty[s], par ^ 1);
                     mbar_expect_tx(&full[s], a_stage + b_stage);
-                    if (cps > 1) {
-                        // `cps` consecutive channel chunks of ONE tap share the stage
-                        const IgemmTap tap = taps[tap_i];
-                        for (int t = 0; t < cps; ++t) {
-                            tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], (c + t) * p.kchunk,
-                                        j0 + tap.dx, i0 + tap.dy, b0);
-                            tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], (c + t) * p.kchunk, tap.brow + n0);
-                        }
-                        c += cps;
-                        if (c >= p.c_chunks) { c = 0; ++tap_i; }
-                        if (++s == stages) { s = 0; par ^= 1; }
-                        continue;
-                    }
                     for (int t = 0; t < tps; ++t) {
                         const IgemmTap tap = taps[tap_i + t];
                         tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
                                     j0 + tap.dx, i0 + tap.dy, b0);
-                        if (!p.b_merged && !bres)
+                        if (!p.b_merged)
                             tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
                     }
-                    if (p.b_merged && !bres)
+                    if (p.b_merged)
                         tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, taps[tap_i].brow + n0);
                     if (++c == p.c_chunks) { c = 0; tap_i += tps; }
                     if (++s == stages) { s = 0; par ^= 1; }
@@ -211,27 +180,19 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             int s = 0;
             uint32_t par = 0, a_lo = a_lo0, b_lo = b_lo0;
             int li = 0;
-            int res_group = -1;
-            uint32_t res_par = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
                 int i0, j0, b0, n0, phase, it_begin, iters;
                 decode(item, i0, j0, b0, n0, phase, it_begin, iters);
                 const int acc = li & 1;
-                if (bres && phase * p.n_tiles + n0 / p.n_tile != res_group) {
-                    if (res_group >= 0) umma_commit(bres_empty);     // arrives when the old slabs' readers are done
-                    res_group = phase * p.n_tiles + n0 / p.n_tile;
-                    mbar_wait(bres_full, res_par);
-                    res_par ^= 1;
-                    tc_fence_after();
-                }
                 mbar_wait(&tmem_empty[acc], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.n_tile;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&full[s], par);
+#if VG_STAGE_FENCE
                     tc_fence_after();
-                    if (bres) b_lo = b_lo0 + static_cast<uint32_t>(it) * b_t;      // slab (tap, chunk) = iteration index
-                    if (ksteps == 4 && tps == 1) {
+#endif
+                    if (ksteps == 4) {
                         umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
                         umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
                         umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
@@ -596,7 +557,9 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const uint32_t idesc = (tl + merge <= ntap) ? idesc_full : idesc_tail;
                     WGRAD_WAIT(&full_b[sb], par_b);
+#if VG_STAGE_FENCE
                     tc_fence_after();
+#endif
                     if (PAIR) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
@@ -797,14 +760,11 @@ __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float*
 // ------------------------------------------------------------------------------------------------
 static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_bytes + 1024 + kBarrierBytes; }
 
-// dynamic shared memory of an fprop-type launch: ring (A + B, or A only with resident weights), resident weight
-// slabs, barriers, fused-epilogue tables
+// dynamic shared memory of an fprop-type launch: operand ring, barriers, fused-epilogue tables
 int igemm_total_smem(const IgemmParams& p) {
-    const int tps = (p.tps > 1 ? p.tps : 1) * (p.cps > 1 ? p.cps : 1);
-    const int a_stage = tps * 128 * p.kchunk * 2, b_sub = p.n_tile * p.kchunk * 2;
-    const int ring = p.stages * (a_stage + (p.b_resident ? 0 : tps * b_sub));
-    const int resident = p.b_resident ? p.taps_per_phase * p.c_chunks * b_sub : 0;
-    return ring + resident + 1024 + kBarrierBytes + igemm_fuse_smem_bytes(p);
+    const int tps = p.tps > 1 ? p.tps : 1;
+    const int stage = tps * (128 + p.n_tile) * p.kchunk * 2;
+    return p.stages * stage + 1024 + kBarrierBytes + igemm_fuse_smem_bytes(p);
 }
 
 int launch_igemm(const IgemmParams& p, cudaStream_t stream) {

@@ -38,10 +38,6 @@ struct alignas(64) IgemmParams {
     int n_tiles;   // grid.y: N_total / n_tile
     int stages;
     int b_merged;  // the tps weight slabs of a stage are adjacent rows of the packed tensor: ONE TMA box loads them
-    int b_resident;  // weights stay in shared memory: all (tap, channel-chunk) slabs of the current (phase, N tile) are
-                     // loaded once and reused by every work item of the CTA that shares them; the ring carries only A
-    int cps;       // channel chunks per pipeline stage (> 1 only with tps == 1 and c_chunks > 1): halves the barrier
-                   // round trips per byte on the narrow-N layers whose stages carry little tensor work
     int tps;       // taps per pipeline stage (> 1 only when c_chunks == 1: narrow-channel layers, amortises the
                    // per-stage barrier / issue overhead over several K=16..32 slabs)
     // output: NHWC tensor, element (b, y, x, n) with y = i*osy + ay[phase], x = j*osx + ax[phase]
