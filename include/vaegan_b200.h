@@ -213,6 +213,13 @@ int vg_s2d_to_nchw(const void* src, float* dst, int batch, int channels, int h, 
  * (0.5,)*3) (dataset_code.py:147-150) on the device, so the host ships 1 byte per value instead of 4. */
 int vg_u8_nhwc_to_nchw(const void* src, float* dst, int batch, int channels, int h, int w, float mean, float std,
                        void* stream);
+/* nn.Linear over a flattened feature map as one dense GEMM over the NHWC activation (fc_mu / fc_logvar of
+ * main_vae.py:47-48 when the feature map is large or the latent size is not a multiple of 32, e.g. the reference's own
+ * 256x256 encoder: 14x14x256 -> 100).  mode 0 builds the GEMM operand W'[n_rows][kk*C] ((h, w, c) order, rows >=
+ * n_valid zero) from the master W[n_valid][C*kk] ((c, h, w) order, main_vae.py:53); mode 1 adds dW' back into the
+ * master-layout gradient. */
+int vg_linear_permute(const float* src, float* dst, int n_valid, int n_rows, int channels, int kk, int mode,
+                      void* stream);
 /* dst[i] (+)= sum_{j<fan} src[idx[i*fan+j]] (negative index = no term): builds the equivalent 64-channel weights of
  * the space-to-depth convolutions from the reference-layout masters and folds their gradients back. */
 int vg_gather_f32(float* dst, const float* src, const int* idx, long long n, int fan, int accumulate, void* stream);

@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 from importlib import import_module
 import vaegan_b200 as vb
 VAEGANStep = import_module("vaegan_b200.step").VAEGANStep
-HW, NZ, B = 64, 128, int(os.environ.get("BATCH", "256"))
+HW, NZ, B = int(os.environ.get("HW", "64")), int(os.environ.get("NZ", "128")), int(os.environ.get("BATCH", "256"))
 torch.manual_seed(42)
 enc = vb.Encoder([3, HW, HW], NZ); gen = vb.Generator(nz=NZ, hw=HW); dis = vb.Discriminator(hw=HW)
 gen.apply(vb.weights_init); dis.apply(vb.weights_init)

@@ -197,3 +197,34 @@ def test_modules_bf16_vs_emulated_oracle(net):
     for k, c in cos_emu.items():
         assert c > floor, f"{net} {k}: cosine vs bf16-emulated oracle {c:.5f}"
     assert vals[len(vals) // 2] > (0.9985 if net == "G" else 0.9995)
+
+
+@pytest.mark.parametrize("hw,nz", [(64, 100), (256, 100)])
+def test_encoder_bf16_linear_heads_as_gemm(hw, nz):
+    """fc_mu / fc_logvar through functional.LinearGemmMap (one dense GEMM over the NHWC feature map with padded rows):
+    the reference's default latent size 100 is not a multiple of 32, and its own 256x256 encoder flattens a
+    14x14x256 map (196 taps).  Outputs and gradients against the oracle with bf16 rounding at the same points."""
+    from oracle import vaegan_oracle as vo
+    batch = 4
+    o_nets, nets = make_pair(hw, nz, "bf16")
+    ref32, mine = o_nets[0], nets[0]
+    ref16 = copy.deepcopy(ref32)
+    vo.attach_bf16_emulation(ref16)
+    x = torch.rand(batch, 3, hw, hw, generator=torch.Generator().manual_seed(21)) * 2 - 1
+
+    def run(m, xin):
+        mu, lv = m(xin)
+        g = torch.Generator().manual_seed(22)
+        loss = (mu * torch.randn(mu.shape, generator=g).to(mu.device)).sum() + \
+               (lv * torch.randn(lv.shape, generator=g).to(lv.device)).sum()
+        loss.backward()
+        return (mu, lv), {k.replace("parametrizations.weight.original", "weight"): p.grad for k, p in m.named_parameters()}
+
+    o16, g16 = run(ref16, x)
+    om, gm = run(mine, x.cuda())
+    assert mine._head_layers()[0].s2d_active            # the GEMM form was actually taken
+    for a, b in zip(om, o16):
+        assert a.shape == b.shape == (batch, nz) and rel_err(a, b) < 2e-2
+    for k in ("fc_mu.weight", "fc_mu.bias", "fc_logvar.weight", "fc_logvar.bias", "cnn.3.conv.weight", "cnn.0.conv.weight"):
+        assert gm[k].shape == g16[k].shape
+        assert cosine(gm[k], g16[k]) > 0.999, (k, cosine(gm[k], g16[k]))

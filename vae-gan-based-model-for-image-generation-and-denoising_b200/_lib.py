@@ -75,6 +75,7 @@ PROTOTYPES = {
     "vg_nchw_to_s2d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "vg_s2d_to_nchw": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "vg_u8_nhwc_to_nchw": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
+    "vg_linear_permute": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "vg_gather_f32": (c_int, [_P, _P, _P, c_longlong, c_int, c_int, _P]),
     "vg_nhwc_to_nchw": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "vg_reparam_fwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),

@@ -1017,6 +1017,40 @@ __global__ void __launch_bounds__(kThreads) u8_nhwc_to_nchw_kernel(const unsigne
     }
 }
 
+// nn.Linear over a flattened NCHW feature map (main_vae.py:47-48,53) as ONE dense GEMM over the NHWC activation:
+// the master W[n][c*kk + tap] (reference (c, h, w) flatten order) and the GEMM operand W'[n][tap*C + c] ((h, w, c) order,
+// rows n_valid..n_pad-1 zero) differ by a per-row [C][kk] <-> [kk][C] transpose.  32x32 shared-memory tiles, both
+// sides coalesced.  mode 0: dst = W' built from src = W;  mode 1: dst = dW (master layout) += src = dW'.
+__global__ void __launch_bounds__(256) linear_permute_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            int n_valid, int C, int kk, int mode) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, tap0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+    const long long row = static_cast<long long>(n) * C * kk;
+    if (mode == 0) {
+        for (int r = ty; r < 32; r += 8) {                             // read W[n][c0+r][tap0+tx]
+            const int c = c0 + r, tap = tap0 + tx;
+            tile[r][tx] = (n < n_valid && c < C && tap < kk) ? src[row + static_cast<long long>(c) * kk + tap] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {                             // write W'[n][(tap0+r)*C + c0+tx]
+            const int tap = tap0 + r, c = c0 + tx;
+            if (tap < kk && c < C) dst[row + static_cast<long long>(tap) * C + c] = tile[tx][r];
+        }
+    } else {
+        if (n >= n_valid) return;
+        for (int r = ty; r < 32; r += 8) {                             // read dW'[n][(tap0+r)*C + c0+tx]
+            const int tap = tap0 + r, c = c0 + tx;
+            tile[r][tx] = (tap < kk && c < C) ? src[row + static_cast<long long>(tap) * C + c] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {                             // dW[n][(c0+r)*kk + tap0+tx] +=
+            const int c = c0 + r, tap = tap0 + tx;
+            if (c < C && tap < kk) dst[row + static_cast<long long>(c) * kk + tap] += tile[tx][r];
+        }
+    }
+}
+
 // dst[i] (+)= sum_j src[idx[i*fan + j]]  (idx < 0 = no term): equivalent-weight construction and its gradient
 __global__ void __launch_bounds__(kThreads) gather_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                              const int* __restrict__ idx, long long n, int fan,
@@ -1329,6 +1363,18 @@ extern "C" int vg_u8_nhwc_to_nchw(const void* src, float* dst, int B, int C, int
     const long long HW = static_cast<long long>(H) * W;
     u8_nhwc_to_nchw_kernel<<<grid_for(B * HW), kThreads, 0, as_stream(stream)>>>(
         static_cast<const unsigned char*>(src), dst, B, C, HW, mean, 1.f / std);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_linear_permute(const float* src, float* dst, int n_valid, int n_rows, int C, int kk, int mode,
+                                 void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (src == nullptr || dst == nullptr || n_valid < 1 || n_rows < n_valid || C < 1 || kk < 1 || (mode != 0 && mode != 1))
+        return fail(VG_ERR_ARG, "linear_permute: bad argument");
+    const dim3 grid((kk + 31) / 32, (C + 31) / 32, mode == 0 ? n_rows : n_valid);
+    linear_permute_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, n_valid, C, kk, mode);
     VG_LAUNCHED();
     return VG_OK;
 }

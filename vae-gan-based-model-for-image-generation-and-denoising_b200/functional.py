@@ -474,6 +474,49 @@ class S2DWeightMap:
         call("vg_gather_f32", _p(target), _p(dweq), _p(t["bwd"]), target.numel(), self.fan, 1, _stream())
 
 
+class LinearGemmMap:
+    """nn.Linear over a flattened feature map (fc_mu / fc_logvar, main_vae.py:47-48,53) as ONE dense GEMM
+    [B, h*w*C] x [h*w*C, n_pad] over the NHWC activation, for the cases the full-extent-convolution form does not put
+    on the tensor cores: more than 64 taps (the reference's own 256x256 encoder flattens 14x14x256) or a latent size
+    that is not a multiple of 32 (its default 100).  Same interface as S2DWeightMap: the master keeps the reference
+    layout [n, C*h*w]; `materialize` builds the GEMM operand ((h, w, c) order, zero rows up to n_pad), `scatter` folds
+    the gradient back."""
+
+    @staticmethod
+    def needed(spec: "ConvSpec") -> bool:
+        return spec.kernel * spec.kernel > 64 or spec.small_c % 32 != 0
+
+    def __init__(self, spec: "ConvSpec"):
+        self.spec = spec
+        self.n, self.C, self.kk = spec.small_c, spec.big_c, spec.kernel * spec.kernel
+        self.n_pad = (self.n + 63) // 64 * 64
+        self.eq_spec = ConvSpec("down", self.n_pad, self.C * self.kk, 1, 1, 0)
+        self.origin = 0
+        self._dev = {}
+
+    def _tensors(self, device):
+        t = self._dev.get(device)
+        if t is None:
+            shape = (self.n_pad, self.C * self.kk, 1, 1)
+            t = dict(weq=torch.empty(shape, dtype=torch.float32, device=device),
+                     dweq=torch.empty(shape, dtype=torch.float32, device=device))
+            self._dev[device] = t
+        return t
+
+    def materialize(self, master: torch.Tensor) -> torch.Tensor:
+        t = self._tensors(master.device)
+        call("vg_linear_permute", _p(_contig(master)), _p(t["weq"]), self.n, self.n_pad, self.C, self.kk, 0, _stream())
+        return t["weq"]
+
+    def grad_buffer(self, device) -> torch.Tensor:
+        t = self._tensors(device)
+        t["dweq"].zero_()
+        return t["dweq"]
+
+    def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
+        call("vg_linear_permute", _p(dweq), _p(target), self.n, self.n_pad, self.C, self.kk, 1, _stream())
+
+
 # --------------------------------------------------------------------------------------------- weight cache
 class PackedWeights:
     """bf16 K-major copies of one fp32 master weight, refreshed when the master changes.  L1 (drop-in modules):
@@ -599,8 +642,13 @@ class ConvLayerFn(torch.autograd.Function):
             ep_act = make_epilogue(EPI_ACT_FWD, 1, 0, act, slope)
             if epilogue_supported(g, spec.kind == "up", ep_act):
                 ep, act_in_epilogue = ep_act, True
+        bias_k = bias.detach() if bias is not None else None
+        if bias_k is not None and bias_k.numel() < spec.small_c:           # padded GEMM rows (LinearGemmMap)
+            padded = torch.zeros(spec.small_c, dtype=torch.float32, device=x.device)
+            padded[:bias_k.numel()].copy_(bias_k)
+            bias_k = padded
         if spec.kind == "down":
-            raw = conv_down(x, w_fwd, g, bias.detach() if bias is not None else None, out_f32=out_f32, ep=ep)
+            raw = conv_down(x, w_fwd, g, bias_k, out_f32=out_f32, ep=ep)
         else:
             raw = conv_up(x, w_fwd, g, ep=ep)
         stats = None
@@ -702,8 +750,16 @@ class ConvLayerFn(torch.autograd.Function):
             if dbias is None:
                 dbias = torch.zeros_like(bias, dtype=torch.float32)
         bias_with_wgrad = want_bias and need_w       # the bias gradient then rides the weight-gradient stream
+        def bias_sum(t, target):
+            if target.numel() == t.shape[-1]:
+                colsum(t, target)
+            else:                                   # padded GEMM rows: reduce all columns, keep the real ones
+                tmp = torch.zeros(t.shape[-1], dtype=torch.float32, device=t.device)
+                colsum(t, tmp)
+                target.add_(tmp[:target.numel()])
+
         if want_bias and not bias_with_wgrad:
-            colsum(d_raw, dbias)
+            bias_sum(d_raw, dbias)
         small, big = (d_raw, x) if spec.kind == "down" else (x, d_raw)
         if need_w:
             main_grad = getattr(weight, "main_grad", None)
@@ -712,7 +768,7 @@ class ConvLayerFn(torch.autograd.Function):
 
             def run_wgrad():
                 if bias_with_wgrad:
-                    colsum(d_raw, dbias)
+                    bias_sum(d_raw, dbias)
                 if wmap is None:
                     return conv_wgrad(small, big, g, main_grad)
                 # space-to-depth layer: gradient of the equivalent weights, folded back into the master layout

@@ -235,7 +235,21 @@ class _LinearAsConv(_Layer):
         self.conv, self.bn, self.act, self.slope = linear, None, ACT_NONE, 0.0
         self.spec = F_.ConvSpec("down", linear.out_features, linear.in_features // (h * w), h, 1, 0)
         self.cache = F_.PackedWeights()
-        self.wmap, self.s2d_active = None, False
+        # large feature maps / latent sizes that are not a multiple of 32 run as one dense GEMM (bf16 path)
+        self.wmap = F_.LinearGemmMap(self.spec) if F_.LinearGemmMap.needed(self.spec) else None
+        self.s2d_active = False
+
+    def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1,
+                 link_in=None, link_out=None):
+        if self.wmap is None or x.dtype != torch.bfloat16:
+            self.s2d_active = False
+            return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, None, None, self.spec, ACT_NONE, 0.0, None,
+                                        training, self.cache, out_f32, 1, None, None, None)
+        self.s2d_active = True                       # pack_layers: pack the GEMM operand, not the conv form
+        flat = x.reshape(x.shape[0], 1, 1, -1)       # NHWC flatten = (h, w, c) order, what LinearGemmMap packs for
+        y = F_.ConvLayerFn.apply(flat, self.conv.weight, self.conv.bias, None, None, self.wmap.eq_spec, ACT_NONE, 0.0,
+                                 None, training, self.cache, out_f32, 1, None, None, self.wmap)
+        return y[..., :self.spec.small_c]
 
 
 # --------------------------------------------------------------------------------------------- generator
