@@ -228,3 +228,32 @@ def test_encoder_bf16_linear_heads_as_gemm(hw, nz):
     for k in ("fc_mu.weight", "fc_mu.bias", "fc_logvar.weight", "fc_logvar.bias", "cnn.3.conv.weight", "cnn.0.conv.weight"):
         assert gm[k].shape == g16[k].shape
         assert cosine(gm[k], g16[k]) > 0.999, (k, cosine(gm[k], g16[k]))
+
+
+@pytest.mark.parametrize("net,hw,nz,batch", [("G", 64, 100, 8), ("D", 256, 100, 2)])
+def test_odd_width_layers_stay_on_tensor_cores(net, hw, nz, batch):
+    """The reference's default latent size (100) feeds the generator's first ConvTranspose2d through zero-padded
+    latent channels (functional.PadRowsMap), and its native 256x256 discriminator starts with 16 output channels
+    (16-channel MN-major atoms in the weight-gradient kernel): outputs and gradients against the bf16-emulated oracle."""
+    from oracle import vaegan_oracle as vo
+    o_nets, nets = make_pair(hw, nz, "bf16")
+    idx = "EGD".index(net)
+    ref16, mine = copy.deepcopy(o_nets[idx]), nets[idx]
+    vo.attach_bf16_emulation(ref16)
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(batch, nz, 1, 1, generator=gen) if net == "G" else torch.rand(batch, 3, hw, hw, generator=gen) * 2 - 1
+
+    def run(m, xin):
+        xin = xin.clone().requires_grad_(True)
+        out = m(xin)
+        out.backward(torch.randn(out.shape, generator=torch.Generator().manual_seed(32)).to(out.device))
+        return out, {k.replace("parametrizations.weight.original", "weight"): p.grad for k, p in m.named_parameters()}, xin.grad
+
+    o16, g16, dx16 = run(ref16, x)
+    om, gm, dxm = run(mine, x.cuda())
+    assert rel_err(om, o16) < 3e-2
+    first = "main.0.weight"
+    assert gm[first].shape == g16[first].shape and cosine(gm[first], g16[first]) > 0.998, cosine(gm[first], g16[first])
+    assert dxm.shape == dx16.shape and cosine(dxm, dx16) > 0.995
+    if net == "G":
+        assert mine._layers()[0].active_wmap is not None        # the padded form was taken

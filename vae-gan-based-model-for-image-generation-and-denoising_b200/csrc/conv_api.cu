@@ -107,7 +107,7 @@ static int wgrad_n_tile(int big_c) {
     return 0;
 }
 bool umma_wgrad_ok(const VgConvGeom* g) {
-    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 16 && g->small_c % 32 == 0 &&
+    return (g->stride == 1 || g->stride == 2) && g->kernel * g->kernel <= 16 && g->small_c % 16 == 0 &&
            wgrad_n_tile(g->big_c) != 0;
 }
 
@@ -369,7 +369,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
     p.tiles_b = ceil_div(g->batch, p.tb);
-    p.p_atom_c = g->small_c % 64 == 0 ? 64 : 32;
+    p.p_atom_c = g->small_c % 64 == 0 ? 64 : (g->small_c % 32 == 0 ? 32 : 16);
     p.m_atoms = std::min(128, g->small_c) / p.p_atom_c;
     p.m_tiles = ceil_div(g->small_c, p.m_atoms * p.p_atom_c);
     p.n_tile = wgrad_n_tile(g->big_c);

@@ -537,7 +537,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             const uint32_t idesc_full = make_idesc_bf16(PAIR ? 256 : 128, merge * p.n_tile, 1, 1);
             const int tail = ntap % merge;
             const uint32_t idesc_tail = make_idesc_bf16(PAIR ? 256 : 128, (tail ? tail : merge) * p.n_tile, 1, 1);
-            const uint32_t p_layout = p.p_atom_c == 64 ? 2u : 4u;
+            const uint32_t p_layout = p.p_atom_c == 64 ? 2u : (p.p_atom_c == 32 ? 4u : 6u);
             const uint32_t q_layout = p.q_atom_c == 64 ? 2u : (p.q_atom_c == 32 ? 4u : 6u);
             const int ksteps = kpix / 16;
             // one UMMA consumes 16 pixel rows: two 8-row groups (SBO apart); MN atoms are LBO apart.  Descriptors of

@@ -517,6 +517,48 @@ class LinearGemmMap:
         call("vg_linear_permute", _p(dweq), _p(target), self.n, self.n_pad, self.C, self.kk, 1, _stream())
 
 
+class PadRowsMap:
+    """A convolution whose small-side channel count is not a multiple of 16 (the generator's first
+    ConvTranspose2d(nz, ...) with the reference's default latent size 100, gan_code.py:19 / vaegan_code.py:26) run
+    with zero-padded small-side channels: equivalent weights = the master plus zero rows, the activation on that side is
+    padded by the caller.  Same interface as S2DWeightMap."""
+
+    @staticmethod
+    def needed(spec: "ConvSpec") -> bool:
+        return spec.small_c % 16 != 0 and spec.small_c > 16
+
+    def __init__(self, spec: "ConvSpec"):
+        self.spec = spec
+        self.n, self.row = spec.small_c, spec.big_c * spec.kernel * spec.kernel
+        self.n_pad = (self.n + 63) // 64 * 64
+        self.eq_spec = ConvSpec(spec.kind, self.n_pad, spec.big_c, spec.kernel, spec.stride, spec.pad)
+        self.origin = 0
+        self._dev = {}
+
+    def _tensors(self, device):
+        t = self._dev.get(device)
+        if t is None:
+            e = self.eq_spec
+            shape = (e.small_c, e.big_c, e.kernel, e.kernel)
+            t = dict(weq=torch.empty(shape, dtype=torch.float32, device=device),
+                     dweq=torch.empty(shape, dtype=torch.float32, device=device))
+            self._dev[device] = t
+        return t
+
+    def materialize(self, master: torch.Tensor) -> torch.Tensor:
+        t = self._tensors(master.device)      # (kk = 1: a row-wise copy with zero rows appended)
+        call("vg_linear_permute", _p(_contig(master)), _p(t["weq"]), self.n, self.n_pad, self.row, 1, 0, _stream())
+        return t["weq"]
+
+    def grad_buffer(self, device) -> torch.Tensor:
+        t = self._tensors(device)
+        t["dweq"].zero_()
+        return t["dweq"]
+
+    def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
+        call("vg_linear_permute", _p(dweq), _p(target), self.n, self.n_pad, self.row, 1, 1, _stream())
+
+
 # --------------------------------------------------------------------------------------------- weight cache
 class PackedWeights:
     """bf16 K-major copies of one fp32 master weight, refreshed when the master changes.  L1 (drop-in modules):
@@ -558,7 +600,7 @@ def pack_layers(layers, dtype) -> None:
     items = (_lib.VgPackItem * len(layers))()
     for i, layer in enumerate(layers):
         sp, w = layer.spec, layer.conv.weight
-        wmap = getattr(layer, "wmap", None) if getattr(layer, "s2d_active", False) else None
+        wmap = getattr(layer, "active_wmap", None)      # the equivalent-weights form the layer last ran in, if any
         src = w
         if wmap is not None:                    # image layer running in space-to-depth form: pack its equivalent weights
             sp, src = wmap.eq_spec, wmap.materialize(w.detach())

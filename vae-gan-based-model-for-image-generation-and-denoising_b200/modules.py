@@ -70,6 +70,8 @@ class _Layer:
         self.wmap = None
         if F_.S2DWeightMap.eligible(self.spec) and (self.spec.kind == "down" or conv.bias is None):
             self.wmap = F_.S2DWeightMap(self.spec)
+        # small-side channels that are not a multiple of 16 (latent size 100 into the generator's first layer)
+        self.padmap = F_.PadRowsMap(self.spec) if (self.spec.kind == "up" and F_.PadRowsMap.needed(self.spec)) else None
         self.s2d_active = False
 
     def input_s2d_origin(self, dtype, h: int, w: int):
@@ -83,6 +85,9 @@ class _Layer:
         bn = self.bn
         act = self.act if fuse_act else ACT_NONE
         spec, wmap = self.spec, None
+        if self.padmap is not None and x.dtype == torch.bfloat16:
+            spec, wmap = self.padmap.eq_spec, self.padmap
+            x = torch.nn.functional.pad(x, (0, self.padmap.n_pad - self.padmap.n))      # zero channels; backward slices
         if self.wmap is not None and x.dtype == torch.bfloat16:
             if spec.kind == "down":
                 s2d = x.shape[-1] == 64                      # the caller converted the image with input_s2d_origin()
@@ -90,7 +95,7 @@ class _Layer:
                 s2d = not ((x.shape[1] | x.shape[2]) & 1)    # the image this layer produces has even extents
             if s2d:
                 spec, wmap = self.wmap.eq_spec, self.wmap
-        self.s2d_active = wmap is not None
+        self.s2d_active, self.active_wmap = wmap is not None, wmap
         return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, bn.weight if bn is not None else None,
                                     bn.bias if bn is not None else None, spec, act, self.slope, bn, training,
                                     self.cache, out_f32, groups, link_in, link_out, wmap)
@@ -241,6 +246,7 @@ class _LinearAsConv(_Layer):
 
     def __call__(self, x, training: bool, out_f32: bool = False, fuse_act: bool = True, groups: int = 1,
                  link_in=None, link_out=None):
+        self.active_wmap = self.wmap if x.dtype == torch.bfloat16 else None
         if self.wmap is None or x.dtype != torch.bfloat16:
             self.s2d_active = False
             return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, None, None, self.spec, ACT_NONE, 0.0, None,
