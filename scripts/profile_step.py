@@ -8,7 +8,9 @@ import vaegan_b200 as vb
 VAEGANStep = import_module("vaegan_b200.step").VAEGANStep
 HW, NZ, B = int(os.environ.get("HW", "64")), int(os.environ.get("NZ", "128")), int(os.environ.get("BATCH", "256"))
 torch.manual_seed(42)
-enc = vb.Encoder([3, HW, HW], NZ); gen = vb.Generator(nz=NZ, hw=HW); dis = vb.Discriminator(hw=HW)
+WIDTH = int(os.environ.get("WIDTH", "1"))
+enc = vb.Encoder([3, HW, HW], NZ, width=WIDTH); gen = vb.Generator(nz=NZ, ngf=64 * WIDTH, hw=HW)
+dis = vb.Discriminator(ndf=64 * WIDTH, hw=HW)
 gen.apply(vb.weights_init); dis.apply(vb.weights_init)
 for m in (enc, gen, dis): m.cuda()
 step = VAEGANStep(enc, gen, dis, use_cuda_graph=True)
