@@ -618,11 +618,6 @@ def _accumulate_or_return(param: Optional[torch.Tensor], grad: Optional[torch.Te
     return None if (param is not None and getattr(param, "main_grad", None) is not None) else grad
 
 
-# One-shot callbacks run at the START of a layer's backward, keyed by id(weight): the fused step uses it to start the
-# discriminator's gradient all-reduce when only its first layer's weight gradient is still to come.
-before_backward_of: dict = {}
-
-
 class LayerLink:
     """Hand-shake between two CONSECUTIVE layers of a sequential chain (the output of the first feeds the second and
     nothing else).  The producer records what its backward needs (raw conv output, BatchNorm statistics,
@@ -747,9 +742,6 @@ class ConvLayerFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, raw, stats = ctx.saved_tensors
         weight, bias, gamma, beta = ctx.params
-        hook = before_backward_of.pop(id(weight), None) if before_backward_of else None
-        if hook is not None:
-            hook()
         spec, g, act, slope = ctx.spec, ctx.g, ctx.act, ctx.slope
         dy = _contig(dy)
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]

@@ -262,19 +262,9 @@ class VAEGANStep:
             slot = loss[it:it + 1] if it < 2 else None
             call("vg_bce", _p(p_pair[:B]), B, self.real_label, 1.0, _p(slot), 0, _p(dp[:B]), _stream())
             call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
-            self._d_reduced = False
-            if self.comm_stream is not None:
-                # everything but the first layer's weight gradient is final when that layer's backward starts
-                F_.before_backward_of[id(D._layers()[0].conv.weight)] = self._reduce_discriminator_early
             torch.autograd.backward([p_pair], [dp])
-            F_.before_backward_of.clear()
             F_.WgradOverlap.join()
-            if self._d_reduced:
-                head = self.opt_D.offsets[1]
-                torch.distributed.all_reduce(self.opt_D.grads[:head], group=self.pg)
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
-            else:
-                self._allreduce(self.opt_D)
+            self._allreduce(self.opt_D)
             self.opt_D.step(1.0 / self.world)
             D.repack_weights()
 
@@ -306,18 +296,6 @@ class VAEGANStep:
         self.opt_E.step(1.0 / self.world)
         self.opt_G.step(1.0 / self.world)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
-
-    def _reduce_discriminator_early(self):
-        """Start of the first discriminator layer's backward: every other gradient of D has been issued.  All-reduce
-        them (all but the first parameter of the flat buffer) on the communication stream under that last weight
-        gradient; the first parameter follows after the join."""
-        comm, cur = self.comm_stream, torch.cuda.current_stream()
-        comm.wait_stream(cur)
-        for st in self.wgrad_streams:
-            comm.wait_stream(st)
-        with torch.cuda.stream(comm):
-            torch.distributed.all_reduce(self.opt_D.grads[self.opt_D.offsets[1]:], group=self.pg)
-        self._d_reduced = True
 
     def _reduce_generator_early(self):
         """Runs inside the backward pass when dL/dz reaches the reparameterisation: every generator kernel (dgrad
