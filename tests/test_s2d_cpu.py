@@ -79,3 +79,41 @@ def test_eligibility():
     assert ok(fn.ConvSpec("up", 64, 3, 3, 1, 1))
     assert not ok(fn.ConvSpec("down", 64, 64, 4, 2, 1)) and not ok(fn.ConvSpec("down", 64, 3, 3, 1, 1))
     assert not ok(fn.ConvSpec("up", 64, 3, 4, 2, 1))
+
+
+def test_linear_over_nchw_flatten_is_gemm_over_nhwc_flatten():
+    """The identity behind functional.LinearGemmMap / vg_linear_permute: nn.Linear on x.view(B, -1) of an NCHW map
+    (main_vae.py:53) == a GEMM on the NHWC flatten with W'[n][tap*C + c] = W[n][c*kk + tap] and zero rows up to n_pad;
+    the gradient folds back through the same index map."""
+    fn = _fn()
+    g = torch.Generator().manual_seed(3)
+    B, C, h, nz = 3, 16, 5, 100
+    m = fn.LinearGemmMap(fn.ConvSpec("down", nz, C, h, 1, 0))
+    assert m.n_pad == 128 and m.eq_spec == fn.ConvSpec("down", 128, C * h * h, 1, 1, 0)
+    assert fn.LinearGemmMap.needed(fn.ConvSpec("down", 100, 256, 14, 1, 0))          # reference encoder, 256x256
+    assert fn.LinearGemmMap.needed(fn.ConvSpec("down", 128, 256, 14, 1, 0))          # 196 taps
+    assert not fn.LinearGemmMap.needed(fn.ConvSpec("down", 128, 256, 2, 1, 0))       # cfg 2 heads stay convolutions
+    x = torch.randn(B, C, h, h, generator=g)
+    W = torch.randn(nz, C * h * h, generator=g)
+    kk = h * h
+    Wp = torch.zeros(m.n_pad, kk * C)
+    Wp[:nz] = W.view(nz, C, kk).permute(0, 2, 1).reshape(nz, kk * C)                  # what mode 0 of the kernel writes
+    y_ref = F.linear(x.view(B, -1), W)
+    y_eq = x.permute(0, 2, 3, 1).reshape(B, -1) @ Wp.t()
+    assert torch.allclose(y_eq[:, :nz], y_ref, atol=1e-4) and float(y_eq[:, nz:].abs().max()) == 0.0
+    dWp = torch.randn(m.n_pad, kk * C, generator=g)
+    folded = dWp[:nz].view(nz, kk, C).permute(0, 2, 1).reshape(nz, C * kk)            # what mode 1 adds to dW
+    Wr = W.clone().requires_grad_(True)
+    Wq = torch.zeros(m.n_pad, kk * C)
+    Wq = torch.cat([Wr.view(nz, C, kk).permute(0, 2, 1).reshape(nz, kk * C), torch.zeros(m.n_pad - nz, kk * C)])
+    (Wq * dWp).sum().backward()
+    assert torch.allclose(folded, Wr.grad, atol=1e-6)
+
+
+def test_pad_rows_map_shapes():
+    fn = _fn()
+    m = fn.PadRowsMap(fn.ConvSpec("up", 100, 1024, 4, 1, 0))
+    assert m.n_pad == 128 and m.eq_spec == fn.ConvSpec("up", 128, 1024, 4, 1, 0) and m.row == 1024 * 16
+    assert fn.PadRowsMap.needed(fn.ConvSpec("up", 100, 1024, 4, 1, 0))
+    assert not fn.PadRowsMap.needed(fn.ConvSpec("up", 128, 1024, 4, 1, 0))
+    assert not fn.PadRowsMap.needed(fn.ConvSpec("down", 64, 3, 4, 2, 1))
