@@ -83,3 +83,31 @@ def test_discriminator_rejects_small_images_like_reference():
     with pytest.raises(RuntimeError, match="Kernel size can't be greater than actual input size"):
         for layer in spec_chain:
             h, w = layer.spec.out_hw(h, w)
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/vaegan_b200.h compiles as C (no C++ / torch types at the boundary) and the POD structs have the size
+    and field offsets the ctypes mirror assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from importlib import import_module
+    import vaegan_b200  # noqa: F401
+    _lib = import_module("vaegan_b200._lib")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vaegan_b200.h"\n'
+                   'int main(void) {\n'
+                   '  printf("%zu %zu %zu\\n", sizeof(VgConvGeom), sizeof(VgPackItem), sizeof(VgEpilogue));\n'
+                   '  printf("%zu %zu %zu %zu\\n", offsetof(VgConvGeom, big_c_valid), offsetof(VgPackItem, small_c),\n'
+                   '         offsetof(VgEpilogue, sums), offsetof(VgEpilogue, stats));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes, offs = [int(v) for v in out[:3]], [int(v) for v in out[3:]]
+    assert sizes == [ctypes.sizeof(_lib.VgConvGeom), ctypes.sizeof(_lib.VgPackItem), ctypes.sizeof(_lib.VgEpilogue)]
+    assert offs == [_lib.VgConvGeom.big_c_valid.offset, _lib.VgPackItem.small_c.offset, _lib.VgEpilogue.sums.offset,
+                    _lib.VgEpilogue.stats.offset]
