@@ -21,7 +21,14 @@ harness: $(LIB) tests/native/igemm_harness.cu
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -std=c++17 -o build/igemm_harness tests/native/igemm_harness.cu -L$(PKG) -lvaegan_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
 
+# experiment build: the weight-gradient kernel's producer / issuer threads time their own phases (build/trace/)
+trace:
+	@mkdir -p build/trace
+	for f in $(SRCS); do $(NVCC) $(NVFLAGS) -DVG_WGRAD_TRACE=1 -c $$f -o build/trace/$$(basename $$f .cu).o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o build/trace/libvaegan_b200.so build/trace/*.o
+	$(NVCC) $(ARCH) -O2 -std=c++17 -DVG_WGRAD_TRACE=1 -o build/trace/igemm_harness tests/native/igemm_harness.cu -Lbuild/trace -lvaegan_b200 -Xlinker -rpath -Xlinker '$$ORIGIN'
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all harness clean
+.PHONY: all harness trace clean

@@ -198,6 +198,9 @@ static bool run_case(const Case& c, bool verbose_fail) {
     return ok;
 }
 
+#ifdef VG_WGRAD_TRACE
+extern "C" int vg_debug_wgrad_trace(unsigned long long* out8, int reset);
+#endif
 static void perf_case(const char* name, VgConvGeom g, int iters) {
     const int kk = g.kernel * g.kernel;
     const size_t n_big = (size_t)g.batch * g.big_h * g.big_w * g.big_c;
@@ -241,6 +244,16 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
         ms /= iters;
         printf("  perf %-28s %-5s %8.1f us  %7.1f TFLOP/s\n", name, op == 0 ? "down" : (op == 1 ? "up" : "wgrad"),
                ms * 1e3, flops / (ms * 1e-3) / 1e12);
+#ifdef VG_WGRAD_TRACE
+        if (op == 2) {
+            unsigned long long t[8];
+            vg_debug_wgrad_trace(t, 1);
+            const double n = iters + 3;
+            printf("    trace (cycles per launch, CTA 0): producer wait_empty_b %.0f  q_tma %.0f  wait_empty_a %.0f  p_tma %.0f"
+                   " | issuer wait_full_b %.0f  umma %.0f  commit %.0f  wait_full_a %.0f\n",
+                   t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n, t[5] / n, t[6] / n, t[7] / n);
+        }
+#endif
     }
     cudaFree(d_big); cudaFree(d_small); cudaFree(d_wd); cudaFree(d_wu); cudaFree(d_w); cudaFree(d_dw); cudaFree(d_wws);
 }

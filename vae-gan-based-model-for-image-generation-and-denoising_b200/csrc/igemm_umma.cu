@@ -405,10 +405,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
-// PAIR = true: launched as clusters of two CTAs along grid.y holding consecutive M tiles of the same N tile; the pair
-// issues M = 256 UMMAs (cta_group::2).  Each CTA loads its own P tile and HALF of the Q atoms of every stage, so the
-// Q operand - the bulk of the L2 -> shared-memory traffic that bounds this kernel - is fetched once per pair.
-template <bool PAIR>
 // experiment switch: -DVG_WGRAD_SPIN=1 makes the producer / MMA threads of the weight-gradient kernel busy-poll
 // (measured: no difference - the per-stage time of this kernel is not barrier-wake-up latency)
 #ifndef VG_WGRAD_SPIN
@@ -419,6 +415,29 @@ template <bool PAIR>
 #else
 #define WGRAD_WAIT mbar_wait
 #endif
+// -DVG_WGRAD_TRACE=1 (make trace): CTA (0,0,0) accumulates the cycles its producer / issuer threads spend per phase
+//   [0] producer: wait empty_b   [1] producer: expect_tx + Q TMA issue   [2] producer: wait empty_a   [3] P TMA issue
+//   [4] issuer: wait full_b      [5] issuer: UMMA issue                  [6] issuer: commit + ring    [7] wait full_a
+#ifndef VG_WGRAD_TRACE
+#define VG_WGRAD_TRACE 0
+#endif
+#if VG_WGRAD_TRACE
+__device__ unsigned long long g_wgrad_trace[8];
+#define TR_BEGIN() long long tr_t = clock64()
+#define TR_ADD(i)                                               \
+    do {                                                        \
+        const long long tr_n = clock64();                       \
+        if (tr_on) g_wgrad_trace[i] += tr_n - tr_t;             \
+        tr_t = tr_n;                                            \
+    } while (0)
+#else
+#define TR_BEGIN() (void)0
+#define TR_ADD(i) (void)0
+#endif
+// PAIR = true: launched as clusters of two CTAs along grid.x holding consecutive M tiles of the same N tile; the pair
+// issues M = 256 UMMAs (cta_group::2).  Each CTA loads its own P tile and HALF of the Q atoms of every stage, so the
+// Q operand - the bulk of the L2 -> shared-memory traffic that bounds this kernel - is fetched once per pair.
+template <bool PAIR>
 __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -484,9 +503,13 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             int tj = t0 % p.tiles_w;
             t0 /= p.tiles_w;
             int ti = t0 % p.tiles_h, tb_i = t0 / p.tiles_h;
+            const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            (void)tr_on;
+            TR_BEGIN();
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 const int j0 = tj * p.tw, i0 = ti * p.th, b0 = tb_i * p.tb;
                 WGRAD_WAIT(&empty_a[sa], par_a ^ 1);
+                TR_ADD(2);
                 if (PAIR) {
                     // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
                     if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
@@ -501,9 +524,11 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                         tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0,
                                     i0, b0);
                 }
+                TR_ADD(3);
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const int cnt = min(merge, ntap - tl);
                     WGRAD_WAIT(&empty_b[sb], par_b ^ 1);
+                    TR_ADD(0);
                     if (PAIR) {
                         // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
                         const int half = cnt * n_atoms / 2;
@@ -527,6 +552,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                         }
                     }
                     if (++sb == SB) { sb = 0; par_b ^= 1; }
+                    TR_ADD(1);
                 }
                 if (++sa == SA) { sa = 0; par_a ^= 1; }
                 if (++tj == p.tiles_w) { tj = 0; if (++ti == p.tiles_h) { ti = 0; ++tb_i; } }
@@ -550,8 +576,12 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             const uint32_t a_k = (16 * p_row) >> 4, b_k = (16 * q_row) >> 4;
             int sa = 0, sb = 0;
             uint32_t par_a = 0, par_b = 0, a_lo = a_lo0, b_lo = b_lo0;
+            const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            (void)tr_on;
+            TR_BEGIN();
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 WGRAD_WAIT(&full_a[sa], par_a);
+                TR_ADD(7);
                 const uint32_t acc = pt != pt_begin;
                 uint32_t d_tmem = tmem_base;
                 for (int tl = 0; tl < ntap; tl += merge) {
@@ -560,6 +590,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
 #if VG_STAGE_FENCE
                     tc_fence_after();
 #endif
+                    TR_ADD(4);
                     if (PAIR) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
@@ -581,11 +612,13 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                             for (int k = 0; k < ksteps; ++k)
                                 umma_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
                         }
+                        TR_ADD(5);
                         umma_commit(&empty_b[sb]);
                     }
                     d_tmem += merge * p.n_tile;
                     b_lo += b_step;
                     if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
+                    TR_ADD(6);
                 }
                 if (PAIR) umma_commit_pair(&empty_a[sa]);
                 else if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
@@ -849,6 +882,18 @@ size_t wgrad_partial_bytes(const WgradParams& p) {
     return static_cast<size_t>(p.splits) * p.m_tiles * p.n_tiles * tap_groups * p.taps_per_cta * 128 * p.n_tile *
            sizeof(float);
 }
+
+#if VG_WGRAD_TRACE
+extern "C" int vg_debug_wgrad_trace(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_wgrad_trace, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_wgrad_trace, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int igemm_smem_bytes(int stages, int stage_bytes) { return smem_bytes_for(stages, stage_bytes); }
 
