@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role branches, and every
+    // address / descriptor computed inside them, on the uniform datapath instead of "waterfall" R2UR loops)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int row_bytes = p.kchunk * 2;
     const int tps = p.tps > 1 ? p.tps : 1;
     const int a_sub = 128 * row_bytes, b_sub = p.n_tile * row_bytes;   // one tap's operand tiles
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     // item -> coordinates (m fastest: consecutive CTAs share the same weight tile)
     auto decode = [&](int item, int& i0, int& j0, int& b0, int& n0, int& phase, int& it_begin, int& iters) {
@@ -138,8 +140,13 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         iters = static_cast<int>(static_cast<long long>(total_iters) * (kslice + 1) / ksplit) - it_begin;
     };
 
+    // Producer and issuer warps run their loops with ALL 32 lanes (warp-uniform control flow and address arithmetic)
+    // and only elect lane 0 around the barrier-arrive / TMA / tcgen05 instructions themselves.  With the whole loop
+    // inside `if (lane == 0)` every operand lives in per-thread registers and each tcgen05.mma costs the thread ~77
+    // cycles, each 4-D TMA ~300 (trace build, round 1): the operands have to be moved to uniform registers one by one.
+    const bool leader = lane == 0;
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int s = 0;
             uint32_t par = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -149,23 +156,25 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty[s], par ^ 1);
-                    mbar_expect_tx(&full[s], a_stage + b_stage);
+                    if (leader) mbar_expect_tx(&full[s], a_stage + b_stage);
                     for (int t = 0; t < tps; ++t) {
                         const IgemmTap tap = taps[tap_i + t];
-                        tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
-                                    j0 + tap.dx, i0 + tap.dy, b0);
-                        if (!p.b_merged)
+                        if (leader)
+                            tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
+                                        j0 + tap.dx, i0 + tap.dy, b0);
+                        if (!p.b_merged && leader)
                             tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
                     }
-                    if (p.b_merged)
+                    if (p.b_merged && leader)
                         tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, taps[tap_i].brow + n0);
+                    __syncwarp();
                     if (++c == p.c_chunks) { c = 0; tap_i += tps; }
                     if (++s == stages) { s = 0; par ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
             const uint32_t layout = p.kchunk == 64 ? 2u : (p.kchunk == 32 ? 4u : 6u);
             const uint32_t sbo = 8 * row_bytes;
@@ -192,23 +201,27 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
 #if VG_STAGE_FENCE
                     tc_fence_after();
 #endif
-                    if (ksteps == 4) {
-                        umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
-                        umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                        umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                        umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
-                    } else {
-                        for (int t = 0; t < tps; ++t)
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_bf16_lohi(d_tmem, a_lo + t * a_t + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi, idesc,
-                                               (it | t | k) != 0);
+                    if (leader) {
+                        if (ksteps == 4) {
+                            umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
+                            umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                            umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                            umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                        } else {
+                            for (int t = 0; t < tps; ++t)
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16_lohi(d_tmem, a_lo + t * a_t + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi,
+                                                   idesc, (it | t | k) != 0);
+                        }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    __syncwarp();
                     a_lo += a_step;
                     b_lo += b_step;
                     if (++s == stages) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
                 }
-                umma_commit(&tmem_full[acc]);   // (with zero iterations this arrives immediately)
+                if (leader) umma_commit(&tmem_full[acc]);   // (with zero iterations this arrives immediately)
+                __syncwarp();
             }
         }
     } else {
@@ -442,7 +455,9 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role branches, and every
+    // address / descriptor computed inside them, on the uniform datapath instead of "waterfall" R2UR loops)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int kpix = p.tw * p.th * p.tb;
     const int p_row = p.p_atom_c * 2, q_row = p.q_atom_c * 2;       // bytes per pixel row inside one atom
     const int p_atom_bytes = kpix * p_row, q_atom_bytes = kpix * q_row;
@@ -493,17 +508,18 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     __syncthreads();
     if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything arrives on them remotely
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    const bool leader = lane == 0;        // see igemm_fprop_kernel: all lanes run the loops, lane 0 issues
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int sa = 0, sb = 0;
             uint32_t par_a = 0, par_b = 0;
             int t0 = pt_begin;
             int tj = t0 % p.tiles_w;
             t0 /= p.tiles_w;
             int ti = t0 % p.tiles_h, tb_i = t0 / p.tiles_h;
-            const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            const bool tr_on = leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
             (void)tr_on;
             TR_BEGIN();
             for (int pt = pt_begin; pt < pt_end; ++pt) {
@@ -512,18 +528,21 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 TR_ADD(2);
                 if (PAIR) {
                     // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
-                    if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
+                    if (rank == 0 && leader) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
                     for (int a = 0; a < p.m_atoms; ++a)
-                        tma_load_4d_pair(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c,
-                                         j0, i0, b0);
+                        if (leader)
+                            tma_load_4d_pair(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa],
+                                             m0 + a * p.p_atom_c, j0, i0, b0);
                 } else if (p.debug_flags & 8) {
-                    mbar_arrive(&full_a[sa]);
+                    if (leader) mbar_arrive(&full_a[sa]);
                 } else {
-                    mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
+                    if (leader) mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
                     for (int a = 0; a < p.m_atoms; ++a)
-                        tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c, j0,
-                                    i0, b0);
+                        if (leader)
+                            tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c,
+                                        j0, i0, b0);
                 }
+                __syncwarp();
                 TR_ADD(3);
                 for (int tl = 0; tl < ntap; tl += merge) {
                     const int cnt = min(merge, ntap - tl);
@@ -532,25 +551,28 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                     if (PAIR) {
                         // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
                         const int half = cnt * n_atoms / 2;
-                        if (rank == 0) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                        if (rank == 0 && leader) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
                         for (int h = 0; h < half; ++h) {
                             const int idx = static_cast<int>(rank) * half + h;
                             const int j = idx / n_atoms, a = idx - j * n_atoms;
                             const IgemmTap tap = p.taps[tap0 + tl + j];
-                            tma_load_4d_pair(sB + sb * b_stage + h * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
-                                             n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                            if (leader)
+                                tma_load_4d_pair(sB + sb * b_stage + h * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
+                                                 n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
                         }
                     } else if (p.debug_flags & 8) {
-                        mbar_arrive(&full_b[sb]);
+                        if (leader) mbar_arrive(&full_b[sb]);
                     } else {
-                        mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                        if (leader) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
                         for (int j = 0; j < cnt; ++j) {
                             const IgemmTap tap = p.taps[tap0 + tl + j];
                             for (int a = 0; a < n_atoms; ++a)
-                                tma_load_4d(sB + sb * b_stage + j * tap_bytes + a * q_atom_bytes, &p.qmap[tap.view],
-                                            &full_b[sb], n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                                if (leader)
+                                    tma_load_4d(sB + sb * b_stage + j * tap_bytes + a * q_atom_bytes, &p.qmap[tap.view],
+                                                &full_b[sb], n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
                         }
                     }
+                    __syncwarp();
                     if (++sb == SB) { sb = 0; par_b ^= 1; }
                     TR_ADD(1);
                 }
@@ -559,7 +581,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             const uint32_t idesc_full = make_idesc_bf16(PAIR ? 256 : 128, merge * p.n_tile, 1, 1);
             const int tail = ntap % merge;
             const uint32_t idesc_tail = make_idesc_bf16(PAIR ? 256 : 128, (tail ? tail : merge) * p.n_tile, 1, 1);
@@ -576,7 +598,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
             const uint32_t a_k = (16 * p_row) >> 4, b_k = (16 * q_row) >> 4;
             int sa = 0, sb = 0;
             uint32_t par_a = 0, par_b = 0, a_lo = a_lo0, b_lo = b_lo0;
-            const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            const bool tr_on = leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
             (void)tr_on;
             TR_BEGIN();
             for (int pt = pt_begin; pt < pt_end; ++pt) {
@@ -591,7 +613,9 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                     tc_fence_after();
 #endif
                     TR_ADD(4);
-                    if (PAIR) {
+                    if (!leader) {
+                        // (only lane 0 issues; the other lanes follow the ring with it)
+                    } else if (PAIR) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
                         umma_commit_pair(&empty_b[sb]);
@@ -615,19 +639,25 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                         TR_ADD(5);
                         umma_commit(&empty_b[sb]);
                     }
+                    __syncwarp();
                     d_tmem += merge * p.n_tile;
                     b_lo += b_step;
                     if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
                     TR_ADD(6);
                 }
-                if (PAIR) umma_commit_pair(&empty_a[sa]);
-                else if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
-                else umma_commit(&empty_a[sa]);
+                if (leader) {
+                    if (PAIR) umma_commit_pair(&empty_a[sa]);
+                    else if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
+                    else umma_commit(&empty_a[sa]);
+                }
+                __syncwarp();
                 a_lo += a_step;
                 if (++sa == SA) { sa = 0; par_a ^= 1; a_lo = a_lo0; }
             }
-            if (PAIR) umma_commit_pair(tmem_full);
-            else umma_commit(tmem_full);
+            if (leader) {
+                if (PAIR) umma_commit_pair(tmem_full);
+                else umma_commit(tmem_full);
+            }
         }
     } else {
         const int q = warp & 3;
