@@ -436,16 +436,25 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 #endif
 #if VG_WGRAD_TRACE
 __device__ unsigned long long g_wgrad_trace[8];
-#define TR_BEGIN() long long tr_t = clock64()
-#define TR_ADD(i)                                               \
-    do {                                                        \
-        const long long tr_n = clock64();                       \
-        if (tr_on) g_wgrad_trace[i] += tr_n - tr_t;             \
-        tr_t = tr_n;                                            \
+// counters live in registers and are flushed once per role (a global read-modify-write per phase would time itself)
+#define TR_BEGIN()            \
+    long long tr_t = clock64(); \
+    long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TR_ADD(i)                         \
+    do {                                  \
+        const long long tr_n = clock64(); \
+        tr_acc[i] += tr_n - tr_t;         \
+        tr_t = tr_n;                      \
+    } while (0)
+#define TR_FLUSH()                                                          \
+    do {                                                                    \
+        if (tr_on)                                                          \
+            for (int tr_i = 0; tr_i < 8; ++tr_i) g_wgrad_trace[tr_i] += tr_acc[tr_i]; \
     } while (0)
 #else
 #define TR_BEGIN() (void)0
 #define TR_ADD(i) (void)0
+#define TR_FLUSH() (void)0
 #endif
 // PAIR = true: launched as clusters of two CTAs along grid.x holding consecutive M tiles of the same N tile; the pair
 // issues M = 256 UMMAs (cta_group::2).  Each CTA loads its own P tile and HALF of the Q atoms of every stage, so the
@@ -579,6 +588,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 if (++sa == SA) { sa = 0; par_a ^= 1; }
                 if (++tj == p.tiles_w) { tj = 0; if (++ti == p.tiles_h) { ti = 0; ++tb_i; } }
             }
+            TR_FLUSH();
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -658,6 +668,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 if (PAIR) umma_commit_pair(tmem_full);
                 else umma_commit(tmem_full);
             }
+            TR_FLUSH();
         }
     } else {
         const int q = warp & 3;
