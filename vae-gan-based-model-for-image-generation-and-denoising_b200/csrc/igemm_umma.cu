@@ -715,7 +715,9 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int n = min(n0 + c + j, p.n_valid - 1);
-                                old[j] = __ldcg(reinterpret_cast<const float4*>(dst + static_cast<long long>(n) * p.s_n));
+                                old[j] = (p.debug_flags & 16)
+                                             ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                             : __ldcg(reinterpret_cast<const float4*>(dst + static_cast<long long>(n) * p.s_n));
                             }
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {

@@ -98,7 +98,8 @@ struct alignas(64) WgradParams {
     // splits > 1: each CTA stores its fp32 partial tile to `partial` ([cta][tap_local][128 rows][n_tile], coalesced
     // vector stores) and wgrad_reduce_kernel sums the splits into dw.  No atomics either way.
     float* partial;
-    int debug_flags;       // bit0: skip the epilogue stores, bit1: skip TMA+MMA main loop (profiling experiments only)
+    int debug_flags;       // bit0: skip the epilogue stores, bit1: skip TMA+MMA main loop, bit2: no MMAs, bit3: no TMA loads,
+                           // bit4: epilogue stores without reading dw (profiling experiments only)
     int pair;              // launch CTA pairs (cta_group::2, M = 256): needs an even m_tiles, full 128-row M tiles, an
                            // even number of Q atoms per stage and taps_per_cta % merge == 0
     int vec4_taps;         // k*k and taps_per_cta multiples of 4, dw 16-byte aligned: dw[m][n][4 taps] moves as one float4
