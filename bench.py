@@ -39,8 +39,9 @@ def _peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
-def _cpu_step_rate(batch: int, timed: int, warm: int = 1):
-    """images/s of the oracle's reference_step (the reference loop on the reference's own torch CPU arithmetic)."""
+def _cpu_step_rate(batch: int, timed: int, warm: int = 1, budget_s: float = 150.0):
+    """images/s of the oracle's reference_step (the reference loop on the reference's own torch CPU arithmetic).
+    Stops early (at least one timed step) once `budget_s` of wall clock is spent, so a slow host cannot stall a run."""
     import torch
     from oracle import vaegan_oracle as vo
     cores = os.cpu_count() or 1
@@ -48,6 +49,7 @@ def _cpu_step_rate(batch: int, timed: int, warm: int = 1):
     nets = vo.build_nets(vo.NetConfig(hw=HW, nz=NZ))
     opts = vo.make_optimizers(*nets)
     times = []
+    t_begin = time.perf_counter()
     for it in range(warm + timed):
         real, eps, n_real, n_fake = vo.make_inputs(batch, HW, NZ, seed=42 + it)
         t0 = time.perf_counter()
@@ -55,7 +57,9 @@ def _cpu_step_rate(batch: int, timed: int, warm: int = 1):
         dt = time.perf_counter() - t0
         if it >= warm:
             times.append(dt)
-    return batch / statistics.median(times), statistics.median(times), cores
+            if time.perf_counter() - t_begin > budget_s:
+                break
+    return batch / statistics.median(times), statistics.median(times), cores, len(times)
 
 
 def run_reference_arm(args):
@@ -64,11 +68,12 @@ def run_reference_arm(args):
         return 0
     sample_batch = 64
     # each "step" is a bounded sample of the cfg-2 step: 64 of the 256 images of one GPU's batch, same nets, fp32
-    steps = max(1, min(args.steps, 8))
-    rate, sec, cores = _cpu_step_rate(sample_batch, timed=steps, warm=max(1, min(args.warmup, 2)))
+    # (about 0.3 s per step on the box's 16 host cores: exactly --steps timed steps after --warmup untimed ones)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    rate, sec, cores, steps = _cpu_step_rate(sample_batch, timed=steps, warm=warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate,
-        "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN (SURVEY A.1), latent 128",
@@ -250,7 +255,7 @@ def run_gpu_arm(args):
     kernels = _kernel_microbench(torch, vb, dev) if not args.no_micro else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = _cpu_step_rate(64, timed=3, warm=1)
+        rate, sec, cores, _ = _cpu_step_rate(64, timed=3, warm=1)
         cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "cfg1: 3 timed steps (median) of 64 images, fp32, same nets, oracle restatement of "
                          "vaegan_code.py:66-135 on torch CPU"}
