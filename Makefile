@@ -28,7 +28,13 @@ trace:
 	$(NVCC) $(ARCH) -shared -o build/trace/libvaegan_b200.so build/trace/*.o
 	$(NVCC) $(ARCH) -O2 -std=c++17 -DVG_WGRAD_TRACE=1 -o build/trace/igemm_harness tests/native/igemm_harness.cu -Lbuild/trace -lvaegan_b200 -Xlinker -rpath -Xlinker '$$ORIGIN'
 
+# stand-alone hardware probes (tcgen05 issue rates, cluster launch rules, halo-tile descriptors): build/<name>
+PROBES := umma_rate umma_rate2 umma_ring cluster_probe umma_halo
+probes:
+	@mkdir -p build
+	for n in $(PROBES); do $(NVCC) $(ARCH) -O2 -std=c++17 -o build/$$n tests/native/$$n.cu || exit 1; done
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all harness trace clean
+.PHONY: all harness trace probes clean
