@@ -34,7 +34,12 @@ probes:
 	@mkdir -p build
 	for n in $(PROBES); do $(NVCC) $(ARCH) -O2 -std=c++17 -o build/$$n tests/native/$$n.cu || exit 1; done
 
+# CPU-only check of the halo-tile plan (includes conv_api.cu, links the library's other objects; no CUDA call is made)
+halo_plan_test: $(LIB) tests/native/halo_plan_test.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O1 -std=c++17 -Iinclude -o build/halo_plan_test tests/native/halo_plan_test.cu $(filter-out build/obj/conv_api.o,$(OBJS))
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all harness trace probes clean
+.PHONY: all harness trace probes halo_plan_test clean

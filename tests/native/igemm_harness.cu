@@ -283,6 +283,10 @@ int main(int argc, char** argv) {
         {"k4s2p1 64x64 c16->64 B2 (padded)", geom(2, 64, 64, 16, 64, 4, 2, 1)},
         {"k3s1p1 32x32 c16<-64 B3 (padded)", geom(3, 32, 32, 16, 64, 3, 1, 1)},
         {"k4s2p1 16x16 c32->64 B4", geom(4, 16, 16, 32, 64, 4, 2, 1)},
+        // shapes the halo-tile path accepts (VG_HALO=1: 128-byte rows, output grid a multiple of 16 x 8)
+        {"k4s2p1 64x64 c64->64 B2 (halo)", geom(2, 64, 64, 64, 64, 4, 2, 1)},
+        {"k4s2p1 32x48 c128->64 B3 (halo, 2 chunks)", geom(3, 32, 48, 128, 64, 4, 2, 1)},
+        {"k3s1p1 32x16 c64<-64 B2 (halo 3x3)", geom(2, 32, 16, 64, 64, 3, 1, 1)},
     };
     bool all = true;
     for (const Case& c : cases) {

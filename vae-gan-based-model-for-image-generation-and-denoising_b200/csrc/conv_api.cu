@@ -183,6 +183,140 @@ static void fuse_fill(IgemmParams& p, const VgConvGeom* g, const VgEpilogue* ep)
     p.fuse_slope = ep->slope;
 }
 
+// ---------------------------------------------------------------------------------------------- tap lists
+// "down" (Conv2d forward / ConvTranspose2d dgrad): one phase, k*k taps in packed-weight order; tap (ky, kx) reads
+// the (row parity, column parity) view of the big tensor that contains input row  s*i + ky - pad.
+static void down_fill_taps(IgemmParams& p, int k, int s, int pad, int small_c) {
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+            IgemmTap& t = p.taps[ky * k + kx];
+            const int vy = floor_mod(ky - pad, s), vx = floor_mod(kx - pad, s);
+            t.view = static_cast<int16_t>(vy * s + vx);
+            t.dy = static_cast<int16_t>((ky - pad - vy) / s);
+            t.dx = static_cast<int16_t>((kx - pad - vx) / s);
+            t.tap_id = static_cast<int16_t>(ky * k + kx);
+            t.brow = (ky * k + kx) * small_c;
+        }
+}
+
+// "up" (ConvTranspose2d forward / Conv2d dgrad): s*s output phases (ay, ax); phase row parity ay takes the ky with
+// (ay + pad - ky) divisible by s, from small row i + (ay + pad - ky) / s.  Sets num_phases, taps_per_phase, ph_ay / ph_ax.
+// Returns 0, -1 (phases with different tap counts) or -2 (tap count not supported).
+static int up_fill_taps(IgemmParams& p, int k, int s, int pad, int big_c) {
+    p.num_phases = s * s;
+    int per_dim = -1;
+    for (int a = 0; a < s; ++a) {
+        int n = 0;
+        for (int ky = 0; ky < k; ++ky) n += floor_mod(a + pad - ky, s) == 0;
+        if (per_dim >= 0 && n != per_dim) return -1;
+        per_dim = n;
+    }
+    const int per_phase = per_dim * per_dim;
+    if (per_phase * s * s > 64 || per_phase == 0) return -2;
+    for (int ay = 0; ay < s; ++ay)
+        for (int ax = 0; ax < s; ++ax) {
+            p.ph_ay[ay * s + ax] = ay;
+            p.ph_ax[ay * s + ax] = ax;
+        }
+    p.taps_per_phase = per_phase;
+    for (int ay = 0; ay < s; ++ay)
+        for (int ax = 0; ax < s; ++ax) {
+            const int ph = ay * s + ax;
+            int n = 0;
+            for (int ky = 0; ky < k; ++ky) {
+                if (floor_mod(ay + pad - ky, s) != 0) continue;
+                for (int kx = 0; kx < k; ++kx) {
+                    if (floor_mod(ax + pad - kx, s) != 0) continue;
+                    IgemmTap& t = p.taps[ph * per_phase + n];
+                    t.view = 0;
+                    t.dy = static_cast<int16_t>((ay + pad - ky) / s);
+                    t.dx = static_cast<int16_t>((ax + pad - kx) / s);
+                    t.tap_id = static_cast<int16_t>(ky * k + kx);
+                    t.brow = (ky * k + kx) * big_c;
+                    ++n;
+                }
+            }
+        }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- halo tiles
+// Experiment switch VG_HALO=1 (off by default).  Regroups the taps of every phase by the view
+// they read; when all groups have the same size and their shifts span at most 2 pixels, a pipeline stage loads ONE
+// (16 + hy) x (8 + hx) activation tile per group and channel chunk and the group's taps read shifted windows of it.
+// Needs 128-byte rows (kchunk 64), 16 x 8 output tiles (tb = 1) and an output grid those tiles cover exactly.
+// Returns false and leaves `p` alone when the launch does not qualify; on success the caller rebuilds amap[] with
+// the (halo_w, halo_h, 1) box and re-derives the stage count.
+static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
+    static const bool wanted = getenv("VG_HALO") != nullptr;
+    if (!wanted || p.kchunk != 64 || grid_w % 8 != 0 || grid_h % 16 != 0) return false;
+    const int tpp = p.taps_per_phase;
+    if (tpp < 2 || p.num_phases * tpp > 64) return false;
+    IgemmTap ordered[64];
+    int16_t org_dy[16], org_dx[16];
+    int shift_y[64], shift_x[64];
+    int gt = -1, groups_total = 0, hy = 0, hx = 0;
+    for (int ph = 0; ph < p.num_phases; ++ph) {
+        const IgemmTap* src = &p.taps[ph * tpp];
+        int n_out = 0, groups_here = 0;
+        bool used[64] = {};
+        for (int first = 0; first < tpp; ++first) {
+            if (used[first]) continue;
+            // one group: every not-yet-placed tap of this phase reading the same view, in (dy, dx) order as listed
+            int lo_y = 1 << 20, lo_x = 1 << 20, hi_y = -(1 << 20), hi_x = -(1 << 20), n = 0;
+            for (int t = first; t < tpp; ++t)
+                if (!used[t] && src[t].view == src[first].view) {
+                    lo_y = std::min<int>(lo_y, src[t].dy); hi_y = std::max<int>(hi_y, src[t].dy);
+                    lo_x = std::min<int>(lo_x, src[t].dx); hi_x = std::max<int>(hi_x, src[t].dx);
+                    ++n;
+                }
+            if (gt < 0) gt = n;
+            if (n != gt || groups_total >= 16) return false;
+            for (int t = first; t < tpp; ++t)
+                if (!used[t] && src[t].view == src[first].view) {
+                    used[t] = true;
+                    const int o = ph * tpp + n_out++;
+                    ordered[o] = src[t];
+                    shift_y[o] = src[t].dy - lo_y;
+                    shift_x[o] = src[t].dx - lo_x;
+                }
+            org_dy[groups_total] = static_cast<int16_t>(lo_y);
+            org_dx[groups_total] = static_cast<int16_t>(lo_x);
+            hy = std::max(hy, hi_y - lo_y);
+            hx = std::max(hx, hi_x - lo_x);
+            ++groups_total;
+            ++groups_here;
+        }
+        if (groups_here * gt != tpp) return false;
+    }
+    // every phase must hold the same number of groups (group index = flat first-tap index / gt)
+    if (gt < 2 || gt > 16 || hy > 2 || hx > 2 || groups_total * gt != p.num_phases * tpp) return false;
+    const int halo_w = 8 + hx, halo_h = 16 + hy, row_bytes = p.kchunk * 2;
+    const int halo_bytes = halo_w * halo_h * row_bytes;
+    const int stage = (halo_bytes + 1023) / 1024 * 1024 + gt * p.n_tile * row_bytes;
+    if (2 * stage + 4096 + igemm_fuse_smem_bytes(p) > 220 * 1024) return false;
+    for (int i = 0; i < p.num_phases * tpp; ++i) {
+        p.taps[i] = ordered[i];
+        p.halo_shift16[i] = static_cast<uint16_t>((shift_y[i] * halo_w + shift_x[i]) * row_bytes / 16);
+    }
+    for (int g = 0; g < groups_total; ++g) { p.halo_dy[g] = org_dy[g]; p.halo_dx[g] = org_dx[g]; }
+    p.halo = 1;
+    p.halo_w = halo_w;
+    p.halo_h = halo_h;
+    p.halo_bytes = halo_bytes;
+    p.halo_stage_bytes = (halo_bytes + 1023) / 1024 * 1024;
+    p.tps = gt;
+    p.b_merged = 0;
+    p.tw = 8;
+    p.th = 16;
+    p.tb = 1;
+    p.tiles_w = grid_w / 8;
+    p.tiles_h = grid_h / 16;
+    p.tiles_b = batch;
+    p.stages = pick_stages(stage, p.n_tile, 1 << 30, igemm_fuse_smem_bytes(p));
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------- down
 static int pick_ksplit(int tiles, int iters) {
     // few output tiles and a long (tap, channel-chunk) loop: spread the reduction over ~one wave of CTAs
@@ -224,19 +358,23 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
         const int rc = make_tmap_bf16(&p.bmap, wd, 2, dims, strides, box, swz);
         if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(B) failed (%d)", rc);
     }
-    for (int ky = 0; ky < k; ++ky)
-        for (int kx = 0; kx < k; ++kx) {
-            IgemmTap& t = p.taps[ky * k + kx];
-            const int vy = floor_mod(ky - pad, s), vx = floor_mod(kx - pad, s);
-            t.view = static_cast<int16_t>(vy * s + vx);
-            t.dy = static_cast<int16_t>((ky - pad - vy) / s);
-            t.dx = static_cast<int16_t>((kx - pad - vx) / s);
-            t.tap_id = static_cast<int16_t>(ky * k + kx);
-            t.brow = (ky * k + kx) * g->small_c;
-        }
+    down_fill_taps(p, k, s, pad, g->small_c);
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
     p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
                            igemm_fuse_smem_bytes(p));
+    if (halo_plan(p, g->small_w, g->small_h, g->batch)) {
+        for (int v = 0; v < 4; ++v) {
+            const int vv = v < nviews ? v : 0;
+            const int rc = make_view(&p.amap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, p.kchunk,
+                                     p.halo_w, p.halo_h, 1, swz);
+            if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(A halo view %d) failed (%d)", v, rc);
+        }
+        const uint64_t dims[2] = {(uint64_t)g->big_c, (uint64_t)k * k * g->small_c};
+        const uint64_t strides[2] = {1, (uint64_t)g->big_c};
+        const uint32_t box[2] = {(uint32_t)p.kchunk, (uint32_t)p.n_tile};
+        const int rc = make_tmap_bf16(&p.bmap, wd, 2, dims, strides, box, swz);
+        if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(B) failed (%d)", rc);
+    }
     p.out = small;
     p.out_fp32 = out_f32;
     p.out_B = g->batch;
@@ -247,7 +385,7 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     p.bias = bias;
     const size_t acc_bytes = static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
     const int ks = pick_ksplit(p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles, p.taps_per_phase * p.c_chunks);
-    if (ks > 1 && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    if (ks > 1 && !p.halo && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
         p.ksplit = ks;
         p.splitk_acc = static_cast<float*>(ws);
     }
@@ -301,42 +439,9 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.out_C = n_total;
         p.osy = p.osx = 1;
     } else {
-        p.num_phases = s * s;
-        // taps per output parity: ky with (a + pad - ky) divisible by s; every phase must have the same count
-        int per_dim = -1;
-        for (int a = 0; a < s; ++a) {
-            int n = 0;
-            for (int ky = 0; ky < k; ++ky) n += floor_mod(a + pad - ky, s) == 0;
-            if (per_dim >= 0 && n != per_dim)
-                return fail(VG_ERR_SHAPE, "up: phases with different tap counts (k%d s%d)", k, s);
-            per_dim = n;
-        }
-        const int per_phase = per_dim * per_dim;
-        if (per_phase * s * s > 64 || per_phase == 0) return fail(VG_ERR_SHAPE, "up: unsupported tap count");
-        for (int ay = 0; ay < s; ++ay)
-            for (int ax = 0; ax < s; ++ax) {
-                p.ph_ay[ay * s + ax] = ay;
-                p.ph_ax[ay * s + ax] = ax;
-            }
-        p.taps_per_phase = per_phase;
-        for (int ay = 0; ay < s; ++ay)
-            for (int ax = 0; ax < s; ++ax) {
-                const int ph = ay * s + ax;
-                int n = 0;
-                for (int ky = 0; ky < k; ++ky) {
-                    if (floor_mod(ay + pad - ky, s) != 0) continue;
-                    for (int kx = 0; kx < k; ++kx) {
-                        if (floor_mod(ax + pad - kx, s) != 0) continue;
-                        IgemmTap& t = p.taps[ph * per_phase + n];
-                        t.view = 0;
-                        t.dy = static_cast<int16_t>((ay + pad - ky) / s);
-                        t.dx = static_cast<int16_t>((ax + pad - kx) / s);
-                        t.tap_id = static_cast<int16_t>(ky * k + kx);
-                        t.brow = (ky * k + kx) * g->big_c;
-                        ++n;
-                    }
-                }
-            }
+        const int trc = up_fill_taps(p, k, s, pad, g->big_c);
+        if (trc == -1) return fail(VG_ERR_SHAPE, "up: phases with different tap counts (k%d s%d)", k, s);
+        if (trc == -2) return fail(VG_ERR_SHAPE, "up: unsupported tap count");
         p.out_H = g->big_h;
         p.out_W = g->big_w;
         p.out_C = g->big_c;
@@ -345,6 +450,13 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
     p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
                            igemm_fuse_smem_bytes(p));
+    if (!dense && halo_plan(p, grid_w, grid_h, g->batch)) {
+        for (int v = 0; v < 4; ++v) {
+            const int rc = make_view(&p.amap[v], small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.kchunk,
+                                     p.halo_w, p.halo_h, 1, swz);
+            if (rc != 0) return fail(VG_ERR_CUDA, "up: cuTensorMapEncodeTiled(A halo) failed (%d)", rc);
+        }
+    }
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();

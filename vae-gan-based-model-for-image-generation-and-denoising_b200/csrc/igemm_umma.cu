@@ -54,9 +54,13 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 // ------------------------------------------------------------------------------------------------
 // fprop-type kernel: A = activation views (K-major), B = packed weights (K-major), D -> NHWC output
 // ------------------------------------------------------------------------------------------------
-template <int FMODE>
+template <int FMODE, bool HALO = false>
 __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
     // FMODE = IgemmParams::fuse_mode (compile-time: the plain kernel carries none of the fused-epilogue code).
+    // HALO  = IgemmParams::halo: the `tps` taps of a stage are the shifted windows of ONE (th+hy) x (tw+hx) halo tile
+    //         (tw = 8, tb = 1: window row m = pixel (m / 8, m % 8) = halo row shift + (m / 8) * halo_w + m % 8, i.e. an
+    //         8-row-group stride of halo_w rows - tests/native/umma_halo.cu shows the tensor core reads exactly those
+    //         rows when the descriptor's base-offset field is 0).  One activation load per stage instead of `tps`.
     // Persistent: each CTA walks work items (M tile, N tile, phase, K slice) with stride gridDim.x.  The smem ring
     // runs continuously across items and the accumulator is double-buffered in TMEM, so the epilogue of item i
     // overlaps the loads and MMAs of item i+1 and the per-CTA prologue (TMEM alloc, barrier init) is paid once.
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int row_bytes = p.kchunk * 2;
     const int tps = p.tps > 1 ? p.tps : 1;
     const int a_sub = 128 * row_bytes, b_sub = p.n_tile * row_bytes;   // one tap's operand tiles
-    const int a_stage = tps * a_sub;
+    const int a_stage = HALO ? p.halo_stage_bytes : tps * a_sub;
     const int b_stage = tps * b_sub;
     const int stages = p.stages;
     uint8_t* sA = smem;
@@ -156,10 +160,17 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty[s], par ^ 1);
-                    if (leader) mbar_expect_tx(&full[s], a_stage + b_stage);
+                    if (leader) mbar_expect_tx(&full[s], (HALO ? p.halo_bytes : a_stage) + b_stage);
+                    if (HALO) {
+                        // the group's halo tile: origin = the smallest shift of its taps (IgemmParams::halo_dy / dx)
+                        const int gi = (phase * p.taps_per_phase + tap_i) / tps;
+                        if (leader)
+                            tma_load_4d(sA + s * a_stage, &p.amap[taps[tap_i].view], &full[s], c * p.kchunk,
+                                        j0 + p.halo_dx[gi], i0 + p.halo_dy[gi], b0);
+                    }
                     for (int t = 0; t < tps; ++t) {
                         const IgemmTap tap = taps[tap_i + t];
-                        if (leader)
+                        if (!HALO && leader)
                             tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
                                         j0 + tap.dx, i0 + tap.dy, b0);
                         if (!p.b_merged && leader)
@@ -178,9 +189,10 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
             const uint32_t layout = p.kchunk == 64 ? 2u : (p.kchunk == 32 ? 4u : 6u);
             const uint32_t sbo = 8 * row_bytes;
+            const uint32_t sbo_a = HALO ? p.halo_w * row_bytes : sbo;       // halo: one 8-pixel image row per group
             const int ksteps = p.kchunk / 16;
             // descriptors of stage 0 / k-step 0; per instruction only the start-address field (lo word) moves
-            const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 0, sbo, layout);
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 0, sbo_a, layout);
             const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 0, sbo, layout);
             const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
             const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
@@ -196,12 +208,25 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 mbar_wait(&tmem_empty[acc], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+                // halo: the stage's taps differ in where their window starts inside the tile (halo_shift16, in
+                // 16-byte units), which follows the tap group -> track it like the producer does
+                int tap_i = HALO ? it_begin / p.c_chunks * tps : 0, hc = HALO ? it_begin % p.c_chunks : 0;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&full[s], par);
 #if VG_STAGE_FENCE
                     tc_fence_after();
 #endif
-                    if (leader) {
+                    if (HALO) {
+                        if (leader) {
+                            const uint16_t* sh = &p.halo_shift16[phase * p.taps_per_phase + tap_i];
+                            for (int t = 0; t < tps; ++t)
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16_lohi(d_tmem, a_lo + sh[t] + 2 * k, a_hi, b_lo + t * b_t + 2 * k, b_hi,
+                                                   idesc, (it | t | k) != 0);
+                            umma_commit(&empty[s]);
+                        }
+                        if (++hc == p.c_chunks) { hc = 0; tap_i += tps; }
+                    } else if (leader) {
                         if (ksteps == 4) {
                             umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
                             umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
@@ -839,7 +864,7 @@ static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_b
 // dynamic shared memory of an fprop-type launch: operand ring, barriers, fused-epilogue tables
 int igemm_total_smem(const IgemmParams& p) {
     const int tps = p.tps > 1 ? p.tps : 1;
-    const int stage = tps * (128 + p.n_tile) * p.kchunk * 2;
+    const int stage = p.halo ? p.halo_stage_bytes + tps * p.n_tile * p.kchunk * 2 : tps * (128 + p.n_tile) * p.kchunk * 2;
     return p.stages * stage + 1024 + kBarrierBytes + igemm_fuse_smem_bytes(p);
 }
 
@@ -848,7 +873,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         for (auto fn : {igemm_fprop_kernel<0>, igemm_fprop_kernel<1>, igemm_fprop_kernel<2>, igemm_fprop_kernel<3>,
-                        igemm_fprop_kernel<4>}) {
+                        igemm_fprop_kernel<4>, igemm_fprop_kernel<0, true>, igemm_fprop_kernel<1, true>,
+                        igemm_fprop_kernel<2, true>, igemm_fprop_kernel<3, true>, igemm_fprop_kernel<4, true>}) {
             const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) attr_err = e;
         }
@@ -864,6 +890,15 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
         cudaError_t e = cudaMemsetAsync(p.splitk_acc, 0, out_elems * sizeof(float), stream);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
+    if (p.halo) {
+        switch (p.fuse_mode) {
+            case 1: igemm_fprop_kernel<1, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+            case 2: igemm_fprop_kernel<2, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+            case 3: igemm_fprop_kernel<3, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+            case 4: igemm_fprop_kernel<4, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+            default: igemm_fprop_kernel<0, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        }
+    } else
     switch (p.fuse_mode) {
         case 1: igemm_fprop_kernel<1><<<grid, kIgemmThreads, smem, stream>>>(p); break;
         case 2: igemm_fprop_kernel<2><<<grid, kIgemmThreads, smem, stream>>>(p); break;

@@ -65,6 +65,16 @@ struct alignas(64) IgemmParams {
     const float* fuse_stats;   // [groups][4][fuse_c]: mean, rstd, scale, shift
     int fuse_act;
     float fuse_slope;
+    // Halo tiles (experiment switch VG_HALO=1; kchunk == 64, tw = 8, th = 16, tb = 1).  The taps of a phase are ordered
+    // in groups of `tps` taps that read the same view at shifts within [0, hy] x [0, hx]; a pipeline stage holds ONE
+    // activation tile of (th + hy) x (tw + hx) pixels and the group's `tps` weight slabs.  Group index
+    // gi = (phase * taps_per_phase + first tap of the group) / tps.
+    int halo;
+    int halo_w, halo_h;          // tw + hx, th + hy: the TMA box of amap[] in this mode
+    int halo_bytes;              // halo_w * halo_h * kchunk * 2: what one activation load delivers
+    int halo_stage_bytes;        // the same rounded up to the swizzle period (1024 B)
+    int16_t halo_dy[16], halo_dx[16];   // per group: origin of the halo tile relative to the output tile's (i0, j0)
+    uint16_t halo_shift16[64];   // per tap (index as taps[]): (sy * halo_w + sx) * row_bytes / 16, the window's start
 };
 
 // shared memory the fused epilogue adds to a CTA
