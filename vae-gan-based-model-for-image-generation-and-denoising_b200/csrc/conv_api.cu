@@ -248,8 +248,10 @@ static int up_fill_taps(IgemmParams& p, int k, int s, int pad, int big_c) {
 // Returns false and leaves `p` alone when the launch does not qualify; on success the caller rebuilds amap[] with
 // the (halo_w, halo_h, 1) box and re-derives the stage count.
 static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
-    static const bool wanted = getenv("VG_HALO") != nullptr;
-    if (!wanted || p.kchunk != 64 || grid_w % 8 != 0 || grid_h % 16 != 0) return false;
+    // VG_HALO=1: every eligible launch; VG_HALO=<n >= 16>: only launches whose N tile is at most n (e.g. 64)
+    static const int wanted = getenv("VG_HALO") ? std::max(1, atoi(getenv("VG_HALO"))) : 0;
+    if (wanted == 0 || (wanted >= 16 && p.n_tile > wanted)) return false;
+    if (p.kchunk != 64 || grid_w % 8 != 0 || grid_h % 16 != 0) return false;
     const int tpp = p.taps_per_phase;
     if (tpp < 2 || p.num_phases * tpp > 64) return false;
     IgemmTap ordered[64];
