@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the data-parallel host logic (sharding, bucket planning, bucketed all-reduce with the
+"""CPU, world_size 2 and 4, gloo: the data-parallel host logic (sharding, bucket planning, bucketed all-reduce with the
 1/world factor applied by the optimizer) reproduces "N reference replicas on disjoint shards, gradients averaged"
  - checked against the oracle run on the whole batch by hand-averaging."""
 import os
@@ -77,24 +77,27 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     want = sum(gathered)
-    ok = torch.allclose(flat, want, rtol=1e-6, atol=1e-7) and len(ar.buckets) > 1
+    # (with more than two ranks the collective's summation order differs from sum(gathered): fp32 round-off)
+    tol = dict(rtol=1e-6, atol=1e-7) if world == 2 else dict(rtol=1e-5, atol=1e-6 * float(want.abs().max()))
+    ok = torch.allclose(flat, want, **tol) and len(ar.buckets) > 1
     # averaged gradient == mean of the replicas' gradients (what Adam sees with grad_scale = 1/world)
-    ok = ok and torch.allclose(flat / world, sum(gathered) / world)
+    ok = ok and torch.allclose(flat / world, sum(gathered) / world, **tol)
     # a second round after reset must work too
     flat.copy_(local)
     for i in reversed(range(len(params))):
         ar.mark_ready(i)
     ar.finish()
-    ok = ok and torch.allclose(flat, want, rtol=1e-6, atol=1e-7)
+    ok = ok and torch.allclose(flat, want, **tol)
     out.put((rank, bool(ok), len(ar.buckets)))
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_world2_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_bucketed_allreduce_gloo(world):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     results = [out.get(timeout=240) for _ in procs]
