@@ -133,12 +133,20 @@ int vg_conv_down_ex(const VgConvGeom* g, VgDType dtype, const void* big, const v
                     const VgEpilogue* ep, void* stream);
 int vg_conv_up_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* w, void* big,
                   const VgEpilogue* ep, void* stream);
-/* dw (fp32, reference layout [small_c][big_c_valid][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient.
- * Optional scratch (ws may be NULL): with vg_conv_wgrad_workspace_bytes() the tensor-core path splits the pixel
- * reduction across SMs and combines the partial tiles in a second kernel (no atomics are used either way). */
+/* dw (fp32, reference layout [small_c][big_c_valid][k][k]) is ACCUMULATED into (+=); zero it for a fresh gradient
+ * (what autograd's `.grad +=` / loss.backward() after optimizer.zero_grad() of vaegan_code.py:103-104,131-133 does).
+ * Layers with few weight tiles and a long pixel reduction split the reduction across SMs; the splits add their
+ * tiles into dw with 16-byte vector reductions (fp32 atomics: the summation order, hence the last bits, vary from
+ * run to run).  vg_conv_wgrad_workspace_bytes() reports the scratch the non-atomic variant (partial tiles + a
+ * reduction kernel; experiment switch VG_WGRAD_ATOMIC=0) needs - 0 otherwise; ws may be NULL.
+ * vg_conv_wgrad_ex with VG_WGRAD_OVERWRITE: dw = gradient; dw need not be initialised (a tile's single owner skips
+ * the read-modify-write, split layers zero dw first). */
+#define VG_WGRAD_OVERWRITE 1
 size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dtype);
 int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* ws,
                   size_t ws_bytes, void* stream);
+int vg_conv_wgrad_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* ws,
+                     size_t ws_bytes, int flags, void* stream);
 
 
 /* ---- BatchNorm2d (training statistics), activations, layout edges ---------------------------------------------

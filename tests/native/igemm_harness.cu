@@ -184,6 +184,19 @@ static bool run_case(const Case& c, bool verbose_fail) {
         const bool o1 = report("down", nm.c_str(), e_d, m_d, tol_out);
         const bool o2 = report("up", nm.c_str(), e_u, m_u, tol_out);
         const bool o3 = report("wgrad", nm.c_str(), e_w, m_w, tol_w);
+        // VG_WGRAD_OVERWRITE: the destination starts as garbage (NaN pattern) and must come back as the plain gradient
+        CK(cudaMemset(d_dw, 0xFF, n_w * 4));
+        rc = vg_conv_wgrad_ex(&g, dt, d_small, d_big, d_dw, d_wws, wws_bytes, VG_WGRAD_OVERWRITE, nullptr);
+        if (rc != VG_OK) { printf("  wgrad(overwrite) failed (%d): %s\n", rc, vg_last_error()); ok = false; }
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h_dw.data(), d_dw, n_w * 4, cudaMemcpyDeviceToHost));
+        double e_o = 0;
+        for (size_t i = 0; i < n_w; ++i) {
+            const double err = fabs(h_dw[i] - r_wg[i]);
+            if (!(err <= e_o)) e_o = err;
+        }
+        const bool o4 = report("wgrad=", nm.c_str(), e_o, m_w, tol_w);
+        ok = ok && o4;
         if (verbose_fail) {
             if (!o1) printf("    down worst at %zu: got %g want %g\n", bad_d, get(h_small, bad_d), r_down[bad_d]);
             if (!o2) printf("    up worst at %zu: got %g want %g\n", bad_u, get(h_big, bad_u), r_up[bad_u]);
@@ -258,8 +271,172 @@ static void perf_case(const char* name, VgConvGeom g, int iters) {
     cudaFree(d_big); cudaFree(d_small); cudaFree(d_wd); cudaFree(d_wu); cudaFree(d_w); cudaFree(d_dw); cudaFree(d_wws);
 }
 
+// ---- timing of the fused-epilogue launches (modes 1-3) and of the weight gradient on RANDOM data (zero operands draw
+// less power and clock higher than a real step does)
+__global__ void fill_random_bf16(__nv_bfloat16* p, size_t n, uint32_t seed, float scale) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        p[i] = __float2bfloat16_rn(((h & 0xFFFF) / 32768.0f - 1.0f) * scale);
+    }
+}
+__global__ void fill_f32(float* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static int g_fused_only = -1, g_fused_idx = 0;      // `fused <n>`: run only the n-th fused case (for ncu)
+static void perf_fused(const char* name, VgConvGeom g, int up, int mode, int groups, int iters) {
+    if (g_fused_only >= 0 && g_fused_idx++ != g_fused_only) return;
+    const int kk = g.kernel * g.kernel;
+    const size_t n_big = (size_t)g.batch * g.big_h * g.big_w * g.big_c;
+    const size_t n_small = (size_t)g.batch * g.small_h * g.small_w * g.small_c;
+    const size_t n_w = (size_t)g.small_c * g.big_c * kk;
+    const size_t n_out = up ? n_big : n_small;
+    const int C = up ? g.big_c : g.small_c;
+    __nv_bfloat16 *d_big, *d_small, *d_wd, *d_wu, *d_x;
+    float *d_w, *d_sums, *d_stats, *d_dw;
+    CK(cudaMalloc(&d_big, n_big * 2));
+    CK(cudaMalloc(&d_small, n_small * 2));
+    CK(cudaMalloc(&d_x, n_out * 2));
+    CK(cudaMalloc(&d_wd, n_w * 2));
+    CK(cudaMalloc(&d_wu, n_w * 2));
+    CK(cudaMalloc(&d_w, n_w * 4));
+    CK(cudaMalloc(&d_dw, n_w * 4));
+    CK(cudaMalloc(&d_sums, (size_t)groups * 2 * C * 4));
+    CK(cudaMalloc(&d_stats, (size_t)groups * 4 * C * 4));
+    fill_random_bf16<<<1024, 256>>>(d_big, n_big, 1u, 1.f);
+    fill_random_bf16<<<1024, 256>>>(d_small, n_small, 2u, 1.f);
+    fill_random_bf16<<<1024, 256>>>(d_x, n_out, 3u, 1.f);
+    fill_random_bf16<<<1024, 256>>>(d_wd, n_w, 4u, 0.05f);
+    fill_random_bf16<<<1024, 256>>>(d_wu, n_w, 5u, 0.05f);
+    fill_f32<<<64, 256>>>(d_stats, (size_t)groups * 4 * C, 0.5f);
+    CK(cudaMemset(d_sums, 0, (size_t)groups * 2 * C * 4));
+    CK(cudaMemset(d_dw, 0, n_w * 4));
+    VgEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.mode = mode;
+    ep.groups = groups;
+    ep.channels = C;
+    ep.act = VG_ACT_LEAKY;
+    ep.slope = 0.2f;
+    ep.sums = d_sums;
+    ep.x = d_x;
+    ep.stats = d_stats;
+    const double flops = 2.0 * g.batch * g.small_h * g.small_w * (double)g.small_c * g.big_c * kk;
+    const double bytes = 2.0 * (n_big + n_small + n_w + (mode >= 2 ? n_out : 0));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    auto run = [&]() {
+        if (mode == 0) return up ? vg_conv_up(&g, VG_BF16, d_small, d_wu, d_big, nullptr)
+                                 : vg_conv_down(&g, VG_BF16, d_big, d_wd, nullptr, d_small, 0, nullptr, 0, nullptr);
+        return up ? vg_conv_up_ex(&g, VG_BF16, d_small, d_wu, d_big, &ep, nullptr)
+                  : vg_conv_down_ex(&g, VG_BF16, d_big, d_wd, nullptr, d_small, &ep, nullptr);
+    };
+    for (int i = 0; i < 3; ++i)
+        if (run() != VG_OK) { printf("  fused %s failed: %s\n", name, vg_last_error()); return; }
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f, sum = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; ++i) run();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= iters;
+        best = ms < best ? ms : best;
+        sum += ms;
+    }
+    printf("  fused %-30s %-4s mode %d  %8.1f us (mean %.1f)  %7.1f TFLOP/s  %6.0f GB/s algorithmic\n", name,
+           up ? "up" : "down", mode, best * 1e3, sum / 3 * 1e3, flops / (best * 1e-3) / 1e12, bytes / (best * 1e-3) / 1e9);
+    cudaFree(d_big); cudaFree(d_small); cudaFree(d_x); cudaFree(d_wd); cudaFree(d_wu); cudaFree(d_w); cudaFree(d_dw);
+    cudaFree(d_sums); cudaFree(d_stats);
+}
+
+static void perf_wgrad_random(const char* name, VgConvGeom g, int iters) {
+    const int kk = g.kernel * g.kernel;
+    const size_t n_big = (size_t)g.batch * g.big_h * g.big_w * g.big_c;
+    const size_t n_small = (size_t)g.batch * g.small_h * g.small_w * g.small_c;
+    const size_t n_w = (size_t)g.small_c * g.big_c * kk;
+    __nv_bfloat16 *d_big, *d_small;
+    float* d_dw;
+    CK(cudaMalloc(&d_big, n_big * 2));
+    CK(cudaMalloc(&d_small, n_small * 2));
+    CK(cudaMalloc(&d_dw, n_w * 4));
+    fill_random_bf16<<<1024, 256>>>(d_big, n_big, 1u, 1.f);
+    fill_random_bf16<<<1024, 256>>>(d_small, n_small, 2u, 1.f);
+    void* d_wws = nullptr;
+    const size_t wws_bytes = vg_conv_wgrad_workspace_bytes(&g, VG_BF16);
+    CK(cudaMalloc(&d_wws, wws_bytes + 16));
+    const double flops = 2.0 * g.batch * g.small_h * g.small_w * (double)g.small_c * g.big_c * kk;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int flags = 0; flags < 2; ++flags) {
+        auto run = [&]() { return vg_conv_wgrad_ex(&g, VG_BF16, d_small, d_big, d_dw, d_wws, wws_bytes, flags, nullptr); };
+        CK(cudaMemset(d_dw, 0, n_w * 4));
+        for (int i = 0; i < 3; ++i)
+            if (run() != VG_OK) { printf("  wgrad %s failed: %s\n", name, vg_last_error()); return; }
+        CK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < iters; ++i) run();
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ms /= iters;
+            best = ms < best ? ms : best;
+        }
+        printf("  wgrad %-30s %-9s %8.1f us  %7.1f TFLOP/s  (scratch %zu KB)\n", name, flags ? "overwrite" : "add",
+               best * 1e3, flops / (best * 1e-3) / 1e12, wws_bytes >> 10);
+    }
+    cudaFree(d_big); cudaFree(d_small); cudaFree(d_dw); cudaFree(d_wws);
+}
+
 int main(int argc, char** argv) {
     const bool perf = argc > 1 && strcmp(argv[1], "perf") == 0;
+    const bool fused = argc > 1 && strcmp(argv[1], "fused") == 0;
+    if (fused) {
+        if (argc > 2) g_fused_only = atoi(argv[2]);
+        if (vg_device_check() != VG_OK) { printf("device check failed: %s\n", vg_last_error()); return 1; }
+        printf("fused-epilogue launches, random data (cfg-2 shapes; D layers at the stacked batch 512)\n");
+        perf_fused("G last dgrad (s2d 64->64)", geom(256, 64, 64, 64, 64, 4, 2, 1), 1, 2, 1, 20);
+        perf_fused("G last dgrad (s2d 64->64)", geom(256, 64, 64, 64, 64, 4, 2, 1), 1, 0, 1, 20);
+        perf_fused("D 64->128 dgrad B512", geom(512, 32, 32, 64, 128, 4, 2, 1), 1, 3, 1, 20);
+        perf_fused("D 64->128 dgrad B512", geom(512, 32, 32, 64, 128, 4, 2, 1), 1, 0, 1, 20);
+        perf_fused("D 128->256 dgrad B512", geom(512, 16, 16, 128, 256, 4, 2, 1), 1, 2, 2, 20);
+        perf_fused("D 128->256 dgrad B512", geom(512, 16, 16, 128, 256, 4, 2, 1), 1, 0, 2, 20);
+        perf_fused("D 256->512 dgrad B512", geom(512, 8, 8, 256, 512, 4, 2, 1), 1, 2, 2, 20);
+        perf_fused("G 128->64 dgrad", geom(256, 64, 64, 64, 128, 4, 2, 1), 0, 2, 1, 20);
+        perf_fused("G 128->64 dgrad", geom(256, 64, 64, 64, 128, 4, 2, 1), 0, 0, 1, 20);
+        perf_fused("G 256->128 dgrad", geom(256, 32, 32, 128, 256, 4, 2, 1), 0, 2, 1, 20);
+        perf_fused("G 256->128 dgrad", geom(256, 32, 32, 128, 256, 4, 2, 1), 0, 0, 1, 20);
+        perf_fused("G 512->256 dgrad", geom(256, 16, 16, 256, 512, 4, 2, 1), 0, 2, 1, 20);
+        perf_fused("G 1024->512 dgrad", geom(256, 8, 8, 512, 1024, 4, 2, 1), 0, 2, 1, 20);
+        perf_fused("G 128->64 fwd", geom(256, 64, 64, 64, 128, 4, 2, 1), 1, 1, 1, 20);
+        perf_fused("G 128->64 fwd", geom(256, 64, 64, 64, 128, 4, 2, 1), 1, 0, 1, 20);
+        perf_fused("G 256->128 fwd", geom(256, 32, 32, 128, 256, 4, 2, 1), 1, 1, 1, 20);
+        perf_fused("G 512->256 fwd", geom(256, 16, 16, 256, 512, 4, 2, 1), 1, 1, 1, 20);
+        perf_fused("G 1024->512 fwd", geom(256, 8, 8, 512, 1024, 4, 2, 1), 1, 1, 1, 20);
+        perf_fused("D 64->128 fwd B512", geom(512, 32, 32, 64, 128, 4, 2, 1), 0, 1, 2, 20);
+        perf_fused("D 128->256 fwd B512", geom(512, 16, 16, 128, 256, 4, 2, 1), 0, 1, 2, 20);
+        perf_fused("D 256->512 fwd B512", geom(512, 8, 8, 256, 512, 4, 2, 1), 0, 1, 2, 20);
+        if (g_fused_only >= 0) return 0;
+        printf("weight gradients, random data\n");
+        perf_wgrad_random("G 1024->512", geom(256, 8, 8, 512, 1024, 4, 2, 1), 20);
+        perf_wgrad_random("G 512->256", geom(256, 16, 16, 256, 512, 4, 2, 1), 20);
+        perf_wgrad_random("G 256->128", geom(256, 32, 32, 128, 256, 4, 2, 1), 20);
+        perf_wgrad_random("G 128->64", geom(256, 64, 64, 64, 128, 4, 2, 1), 20);
+        perf_wgrad_random("G last (s2d 64->64)", geom(256, 64, 64, 64, 64, 4, 2, 1), 20);
+        perf_wgrad_random("D 64->128 B512", geom(512, 32, 32, 64, 128, 4, 2, 1), 20);
+        perf_wgrad_random("D 128->256 B512", geom(512, 16, 16, 128, 256, 4, 2, 1), 20);
+        perf_wgrad_random("D 256->512 B512", geom(512, 8, 8, 256, 512, 4, 2, 1), 20);
+        perf_wgrad_random("D first (s2d 64->64 k2) B512", geom(512, 33, 33, 64, 64, 2, 1, 0), 20);
+        return 0;
+    }
     int rc = vg_device_check();
     if (rc != VG_OK) {
         printf("device check failed: %s\n", vg_last_error());

@@ -34,6 +34,7 @@ class VgEpilogue(Structure):
                 ("sums", c_void_p), ("x", c_void_p), ("stats", c_void_p)]
 
 
+WGRAD_OVERWRITE = 1
 EPI_NONE, EPI_BN_STATS, EPI_BN_BWD, EPI_ACT_BWD, EPI_ACT_FWD = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
@@ -55,6 +56,7 @@ PROTOTYPES = {
     "vg_conv_up_ex": (c_int, [_G, c_int, _P, _P, _P, _E, _P]),
     "vg_conv_wgrad_workspace_bytes": (c_size_t, [_G, c_int]),
     "vg_conv_wgrad": (c_int, [_G, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "vg_conv_wgrad_ex": (c_int, [_G, c_int, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "vg_reduce_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "vg_bn_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int]),
     "vg_bn_train_fwd": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,

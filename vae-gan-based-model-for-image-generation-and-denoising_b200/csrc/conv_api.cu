@@ -13,6 +13,40 @@
 
 namespace vg {
 
+// Experiment switches (environment variables): read ONCE, at the first launch, never on the
+// launch path.  All unset in the product path.
+struct Switches {
+    int halo;            // VG_HALO: 0 off, 1 every eligible launch, n >= 16 only N tiles <= n
+    int wgrad_kpix;      // VG_WGRAD_KPIX: pixels per stage of the weight-gradient kernel (default 128)
+    int wgrad_sa;        // VG_WGRAD_SA: depth of its P ring (0 = default)
+    int wgrad_pair;      // VG_WGRAD2: CTA pairs
+    int wgrad_atomic;    // VG_WGRAD_ATOMIC: split layers reduce with vector atomics (1) or partial tiles + reduce (0)
+    int debug_wgrad;     // VG_DEBUG_WGRAD: only honoured by -DVG_DEBUG_WGRAD=1 builds
+    int tep;             // VG_TEP: 0 = per-lane global loads / stores in the epilogues instead of the TMA epilogue
+    int ew8;             // VG_EW8: 0 = four epilogue warps even for launches that own a whole SM
+    int wide_from;       // VG_WIDE_FROM: N tiles >= this own a whole SM (default 256; 128 measured 15-25 % slower on the N = 128 layers)
+    int xtma_wide;       // VG_XTMA_WIDE: N = 256 tiles of modes 2 / 3 also fetch the saved tensor by TMA
+};
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static const Switches& switches() {
+    static const Switches s = {
+        getenv("VG_HALO") ? std::max(1, atoi(getenv("VG_HALO"))) : 0,
+        env_int("VG_WGRAD_KPIX", 128),
+        env_int("VG_WGRAD_SA", 0),
+        getenv("VG_WGRAD2") != nullptr ? 1 : 0,
+        env_int("VG_WGRAD_ATOMIC", 1),
+        env_int("VG_DEBUG_WGRAD", 0),
+        env_int("VG_TEP", 1),
+        env_int("VG_EW8", 1),
+        env_int("VG_WIDE_FROM", 256),
+        env_int("VG_XTMA_WIDE", 0),
+    };
+    return s;
+}
+
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static int pow2_ceil(int v) {
     int p = 1;
@@ -45,11 +79,15 @@ static int pick_tps(int kchunk, int c_chunks, int taps) {
     return 1;
 }
 
+// N tiles below switches().wide_from run two CTAs per SM (two MMA-issuing threads, 4 + 4 epilogue warps); wider ones
+// own the SM (one issuer is enough at >= 64 tensor cycles per instruction) and get eight epilogue warps.
+static bool owns_sm(int n_tile) { return n_tile >= switches().wide_from; }
+
 static int pick_stages(int stage_bytes, int n_tile, int iters = 1 << 30, int extra_smem = 0) {
-    // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question:
-    // narrow accumulators leave room for two CTAs per SM (110 KB each), wide ones take the whole SM.
+    // The kernel is persistent (the ring runs across tiles), so the depth is purely a bandwidth / latency question.
+    // `extra_smem`: epilogue slabs + fused-epilogue tables (barriers and alignment slack are budgeted here).
     (void)iters;
-    const int budget = (n_tile <= 128 ? 110 : 220) * 1024 - 2048 - extra_smem;
+    const int budget = (owns_sm(n_tile) ? 225 : 112) * 1024 - 3072 - extra_smem;
     return std::max(2, std::min(8, budget / stage_bytes));
 }
 
@@ -183,6 +221,36 @@ static void fuse_fill(IgemmParams& p, const VgConvGeom* g, const VgEpilogue* ep)
     p.fuse_slope = ep->slope;
 }
 
+// TMA epilogue plan (IgemmParams::tep / ew8 / ep_slots + the output-side tensor maps).  `out` / `x`: the output tensor
+// and (modes 2 / 3) the saved tensor of the same NHWC shape [B][H][W][C]; strided phases (`up`, stride s) address
+// their (row, column) parity views.  Call after n_tile, the tile box, the phases and ksplit are settled.
+static void plan_epilogue_flags(IgemmParams& p, const void* out, int C, int out_f32) {
+    p.ew8 = owns_sm(p.n_tile) && switches().ew8 != 0 && (p.n_tile / 32) % 2 == 0 && p.n_tile % 32 == 0;
+    const bool mode23 = p.fuse_mode == VG_EPI_BN_BWD || p.fuse_mode == VG_EPI_ACT_BWD;
+    p.tep = switches().tep != 0 && !out_f32 && p.ksplit <= 1 && p.n_tile % 32 == 0 && C % 8 == 0 && aligned16(out) &&
+            (!mode23 || aligned16(p.fuse_x));
+    // slabs per epilogue warp: two for plain stores; four when the saved tensor arrives by TMA two chunks ahead.
+    // Launches that own the SM have eight epilogue warps and 48 KB stages: one slab each (the previous chunk's store
+    // has long read it when a warp comes back two chunks later) keeps the fourth stage; at N = 256 the saved tensor
+    // then comes per lane as before (VG_XTMA_WIDE=1: three slabs, TMA).
+    if (mode23) p.ep_slots = (p.n_tile > 128 && !switches().xtma_wide) ? 1 : (p.ew8 ? 3 : 4);
+    else p.ep_slots = p.ew8 ? 1 : 2;
+}
+static int plan_epilogue_maps(IgemmParams& p, const void* out, int B, int H, int W, int C) {
+    const bool mode23 = p.fuse_mode == VG_EPI_BN_BWD || p.fuse_mode == VG_EPI_ACT_BWD;
+    if (!p.tep) return 0;
+    // the 32 consecutive tile rows of one epilogue warp form a (bw, bh, bb) box of the (tw, th, tb) tile
+    const int bw = std::min(p.tw, 32), bh = std::min(p.th, 32 / bw), bb = 32 / (bw * bh);
+    for (int ph = 0; ph < p.num_phases; ++ph) {
+        int rc = make_view(&p.omap[ph], out, B, H, W, C, p.osy, p.ph_ay[ph], p.ph_ax[ph], 32, bw, bh, bb, 64);
+        if (rc == 0 && mode23)
+            rc = make_view(&p.xmap[ph], p.fuse_x, B, H, W, C, p.osy, p.ph_ay[ph], p.ph_ax[ph], 32, bw, bh, bb, 64);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+static int epilogue_extra_smem(const IgemmParams& p) { return igemm_epilogue_smem_bytes(p) + igemm_fuse_smem_bytes(p); }
+
 // ---------------------------------------------------------------------------------------------- tap lists
 // "down" (Conv2d forward / ConvTranspose2d dgrad): one phase, k*k taps in packed-weight order; tap (ky, kx) reads
 // the (row parity, column parity) view of the big tensor that contains input row  s*i + ky - pad.
@@ -249,7 +317,7 @@ static int up_fill_taps(IgemmParams& p, int k, int s, int pad, int big_c) {
 // the (halo_w, halo_h, 1) box and re-derives the stage count.
 static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
     // VG_HALO=1: every eligible launch; VG_HALO=<n >= 16>: only launches whose N tile is at most n (e.g. 64)
-    static const int wanted = getenv("VG_HALO") ? std::max(1, atoi(getenv("VG_HALO"))) : 0;
+    const int wanted = switches().halo;
     if (wanted == 0 || (wanted >= 16 && p.n_tile > wanted)) return false;
     if (p.kchunk != 64 || grid_w % 8 != 0 || grid_h % 16 != 0) return false;
     const int tpp = p.taps_per_phase;
@@ -296,7 +364,7 @@ static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
     const int halo_w = 8 + hx, halo_h = 16 + hy, row_bytes = p.kchunk * 2;
     const int halo_bytes = halo_w * halo_h * row_bytes;
     const int stage = (halo_bytes + 1023) / 1024 * 1024 + gt * p.n_tile * row_bytes;
-    if (2 * stage + 4096 + igemm_fuse_smem_bytes(p) > 220 * 1024) return false;
+    if (2 * stage + 4096 + epilogue_extra_smem(p) > 220 * 1024) return false;
     for (int i = 0; i < p.num_phases * tpp; ++i) {
         p.taps[i] = ordered[i];
         p.halo_shift16[i] = static_cast<uint16_t>((shift_y[i] * halo_w + shift_x[i]) * row_bytes / 16);
@@ -315,7 +383,9 @@ static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
     p.tiles_w = grid_w / 8;
     p.tiles_h = grid_h / 16;
     p.tiles_b = batch;
-    p.stages = pick_stages(stage, p.n_tile, 1 << 30, igemm_fuse_smem_bytes(p));
+    // (two CTAs per SM only if two stages + the epilogue tables fit into half an SM's shared memory)
+    const bool half_sm = !owns_sm(p.n_tile) && 2 * stage + 3072 + epilogue_extra_smem(p) <= 112 * 1024;
+    p.stages = pick_stages(stage, half_sm ? p.n_tile : 256, 1 << 30, epilogue_extra_smem(p));
     return true;
 }
 
@@ -362,9 +432,24 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
     }
     down_fill_taps(p, k, s, pad, g->small_c);
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
+    p.out = small;
+    p.out_fp32 = out_f32;
+    p.out_B = g->batch;
+    p.out_H = g->small_h;
+    p.out_W = g->small_w;
+    p.out_C = g->small_c;
+    p.osy = p.osx = 1;
+    p.bias = bias;
+    const size_t acc_bytes = static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
+    const int ks = pick_ksplit(p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles, p.taps_per_phase * p.c_chunks);
+    if (ks > 1 && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        p.ksplit = ks;
+        p.splitk_acc = static_cast<float*>(ws);
+    }
+    plan_epilogue_flags(p, small, g->small_c, out_f32);
     p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
-                           igemm_fuse_smem_bytes(p));
-    if (halo_plan(p, g->small_w, g->small_h, g->batch)) {
+                           epilogue_extra_smem(p));
+    if (p.ksplit <= 1 && halo_plan(p, g->small_w, g->small_h, g->batch)) {
         for (int v = 0; v < 4; ++v) {
             const int vv = v < nviews ? v : 0;
             const int rc = make_view(&p.amap[v], big, g->batch, g->big_h, g->big_w, g->big_c, s, vv / s, vv % s, p.kchunk,
@@ -377,20 +462,8 @@ static int down_umma(const VgConvGeom* g, const void* big, const void* wd, const
         const int rc = make_tmap_bf16(&p.bmap, wd, 2, dims, strides, box, swz);
         if (rc != 0) return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(B) failed (%d)", rc);
     }
-    p.out = small;
-    p.out_fp32 = out_f32;
-    p.out_B = g->batch;
-    p.out_H = g->small_h;
-    p.out_W = g->small_w;
-    p.out_C = g->small_c;
-    p.osy = p.osx = 1;
-    p.bias = bias;
-    const size_t acc_bytes = static_cast<size_t>(g->batch) * g->small_h * g->small_w * g->small_c * sizeof(float);
-    const int ks = pick_ksplit(p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles, p.taps_per_phase * p.c_chunks);
-    if (ks > 1 && !p.halo && p.fuse_mode == 0 && ws != nullptr && ws_bytes >= acc_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
-        p.ksplit = ks;
-        p.splitk_acc = static_cast<float*>(ws);
-    }
+    if (plan_epilogue_maps(p, small, g->batch, g->small_h, g->small_w, g->small_c) != 0)
+        return fail(VG_ERR_CUDA, "down: cuTensorMapEncodeTiled(output) failed");
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<down>");
     note_launch(p.ksplit > 1 ? 2 : 1);
@@ -450,8 +523,9 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
         p.osy = p.osx = s;
     }
     p.tps = pick_tps(p.kchunk, p.c_chunks, p.taps_per_phase);
+    plan_epilogue_flags(p, big, p.out_C, 0);
     p.stages = pick_stages(p.tps * (128 + p.n_tile) * p.kchunk * 2, p.n_tile, p.taps_per_phase / p.tps * p.c_chunks,
-                           igemm_fuse_smem_bytes(p));
+                           epilogue_extra_smem(p));
     if (!dense && halo_plan(p, grid_w, grid_h, g->batch)) {
         for (int v = 0; v < 4; ++v) {
             const int rc = make_view(&p.amap[v], small, g->batch, g->small_h, g->small_w, g->small_c, 1, 0, 0, p.kchunk,
@@ -459,6 +533,8 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
             if (rc != 0) return fail(VG_ERR_CUDA, "up: cuTensorMapEncodeTiled(A halo) failed (%d)", rc);
         }
     }
+    if (plan_epilogue_maps(p, big, g->batch, p.out_H, p.out_W, p.out_C) != 0)
+        return fail(VG_ERR_CUDA, "up: cuTensorMapEncodeTiled(output) failed");
     const int rc = launch_igemm(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_fprop_kernel<up>");
     note_launch();
@@ -467,7 +543,7 @@ static int up_umma(const VgConvGeom* g, const void* small, const void* wu, void*
 
 // ---------------------------------------------------------------------------------------------- wgrad
 static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, float* dw, void* ws, size_t ws_bytes,
-                      cudaStream_t stream, size_t* ws_needed = nullptr) {
+                      cudaStream_t stream, size_t* ws_needed = nullptr, int overwrite = 0) {
     if (ws_needed == nullptr && (!aligned16(big) || !aligned16(small)))
         return fail(VG_ERR_ALIGN, "wgrad: 16-byte alignment");
     WgradParams p;
@@ -477,8 +553,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     const int nt = wgrad_n_tile(g->big_c);
     const int tpc = std::min(std::min(k * k, 512 / nt), 16);
     const int merge = nt <= 64 ? std::max(1, std::min(tpc, 256 / nt)) : 1;   // wide tiles keep one tap per UMMA
-    const char* kp = getenv("VG_WGRAD_KPIX");
-    const int kpix = kp ? atoi(kp) : 128;
+    const int kpix = switches().wgrad_kpix;
     pick_box(kpix, g->small_w, g->small_h, &p.tw, &p.th, &p.tb);
     p.tiles_w = ceil_div(g->small_w, p.tw);
     p.tiles_h = ceil_div(g->small_h, p.th);
@@ -524,13 +599,11 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.splits = base_ctas >= 100 ? 1 : std::max(1, std::min(total_tiles, 148 / base_ctas));
     const int a_stage = kpix * 256, b_stage = p.merge * p.n_tile * kpix * 2;
     p.stages_a = kpix >= 128 ? 2 : 3;
-    if (const char* sa = getenv("VG_WGRAD_SA")) p.stages_a = std::max(2, atoi(sa));      // experiment switch
+    if (switches().wgrad_sa > 0) p.stages_a = std::max(2, switches().wgrad_sa);      // experiment switch
     p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;
-    {
-        const char* dbg = getenv("VG_DEBUG_WGRAD");
-        p.debug_flags = dbg ? atoi(dbg) : 0;
-    }
+    p.debug_flags = switches().debug_wgrad;
+    p.accumulate = overwrite ? 0 : 1;
     const int bcv = bc_valid(g);
     p.s_m = static_cast<long long>(bcv) * k * k;
     p.s_n = k * k;
@@ -542,7 +615,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
                   (p.s_m % 4) == 0;
     {
         // CTA pairs sharing the Q operand (experiment switch VG_WGRAD2=1)
-        static const bool want_pair = getenv("VG_WGRAD2") != nullptr;
+        const bool want_pair = switches().wgrad_pair != 0;
         const int n_atoms = p.n_tile / p.q_atom_c;
         p.pair = want_pair && p.m_tiles % 2 == 0 && p.m_atoms * p.p_atom_c == 128 && g->small_c % 128 == 0 &&
                  (p.merge * n_atoms) % 2 == 0 && p.taps_per_cta % p.merge == 0 && p.num_taps % p.taps_per_cta == 0;
@@ -552,7 +625,12 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
             p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage_b) / b_half));
         }
     }
-    if (p.splits > 1) {
+    // Split layers (few weight tiles, a long pixel reduction): every split adds its tile straight into dw with 16-byte
+    // vector reductions (red.global.add.v4.f32; dw is small and L2-resident) - no partial tiles, no second kernel.
+    p.atomic_split = p.splits > 1 && p.vec4_taps && switches().wgrad_atomic != 0;
+    if (p.atomic_split) {
+        if (ws_needed != nullptr) { *ws_needed = 0; return VG_OK; }
+    } else if (p.splits > 1) {
         const size_t need = wgrad_partial_bytes(p);
         if (ws_needed != nullptr) { *ws_needed = need; return VG_OK; }
         if (ws != nullptr && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) p.partial = static_cast<float*>(ws);
@@ -561,9 +639,14 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
         *ws_needed = 0;
         return VG_OK;
     }
+    if (p.splits > 1 && overwrite) {       // every split path accumulates: start from zero
+        const cudaError_t e = cudaMemsetAsync(dw, 0, static_cast<size_t>(g->small_c) * bcv * k * k * sizeof(float), stream);
+        if (e != cudaSuccess) return cuda_fail(e, "wgrad: memset");
+        p.accumulate = 1;
+    }
     const int rc = launch_wgrad(p, stream);
     if (rc != 0) return cuda_fail(static_cast<cudaError_t>(rc), "igemm_wgrad_kernel");
-    note_launch(p.splits > 1 ? 2 : 1);
+    note_launch((p.splits > 1 && !p.atomic_split) ? 2 : 1);
     return VG_OK;
 }
 
@@ -783,14 +866,31 @@ extern "C" size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dty
     return need;
 }
 
-extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
-                             void* ws, size_t ws_bytes, void* stream) {
+static int wgrad_dispatch(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* ws,
+                          size_t ws_bytes, int overwrite, void* stream) {
     int rc = check_geom(g);
     if (rc != VG_OK) return rc;
     if (big == nullptr || dw == nullptr || small == nullptr) return fail(VG_ERR_ARG, "wgrad: null pointer");
     rc = device_check();
     if (rc != VG_OK) return rc;
+    if (dtype == VG_BF16 && !is_gemv(g) && umma_wgrad_ok(g))
+        return wgrad_umma(g, small, big, dw, ws, ws_bytes, as_stream(stream), nullptr, overwrite);
+    if (overwrite) {     // the other paths accumulate: give them a zeroed destination
+        const size_t n = static_cast<size_t>(g->small_c) * bc_valid(g) * g->kernel * g->kernel;
+        const cudaError_t e = cudaMemsetAsync(dw, 0, n * sizeof(float), as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "wgrad: memset");
+    }
     if (is_gemv(g)) return gemv_wgrad(g, dtype, small, big, dw, as_stream(stream));
-    if (dtype == VG_BF16 && umma_wgrad_ok(g)) return wgrad_umma(g, small, big, dw, ws, ws_bytes, as_stream(stream));
     return simt_conv_wgrad(g, dtype, small, big, dw, as_stream(stream));
+}
+
+extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
+                             void* ws, size_t ws_bytes, void* stream) {
+    return wgrad_dispatch(g, dtype, small, big, dw, ws, ws_bytes, 0, stream);
+}
+
+extern "C" int vg_conv_wgrad_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
+                                void* ws, size_t ws_bytes, int flags, void* stream) {
+    if (flags & ~VG_WGRAD_OVERWRITE) return fail(VG_ERR_ARG, "wgrad: unknown flags 0x%x", flags);
+    return wgrad_dispatch(g, dtype, small, big, dw, ws, ws_bytes, (flags & VG_WGRAD_OVERWRITE) ? 1 : 0, stream);
 }

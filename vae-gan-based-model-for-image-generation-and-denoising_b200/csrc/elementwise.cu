@@ -734,13 +734,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
         // The fp32 sums carry ~1e-7 relative error already; a double-precision divide + square root per channel in every
         // thread's prologue was a multi-microsecond latency in front of each (short) apply pass.  fp32 with one
         // Newton step on rsqrt is within 2 ulp of the double result.
-        const float mf = sg[c] * static_cast<float>(inv_n);
-        const float var_f = fmaxf(fmaf(-mf, mf, sg[C + c] * static_cast<float>(inv_n)), 0.f);
+        // E[x^2] - mean^2 is formed in double (three fp64 operations per channel): in fp32 the subtraction itself
+        // loses log2(mean^2 / var) bits on layers whose |mean| >> std (biased encoder blocks); the fp32 sums are the
+        // remaining error source
+        const double m = static_cast<double>(sg[c]) * inv_n;
+        const float mf = static_cast<float>(m);
+        const float var_f = static_cast<float>(fmax(fma(-m, m, static_cast<double>(sg[C + c]) * inv_n), 0.0));
         float rstd = rsqrtf(var_f + eps);
         rstd = rstd * fmaf(-0.5f * (var_f + eps) * rstd, rstd, 1.5f);
-        const double m = static_cast<double>(mf);
-        const double var = static_cast<double>(var_f);
-        (void)var;
         const float g = gamma ? __ldg(gamma + c) : 1.f, bt = beta ? __ldg(beta + c) : 0.f;
         sc[j] = g * rstd;
         sh[j] = bt - mf * sc[j];

@@ -19,9 +19,11 @@ namespace vg {
 #ifndef VG_STAGE_FENCE
 #define VG_STAGE_FENCE 0
 #endif
-static constexpr int kIgemmThreads = 192;
+static constexpr int kIgemmThreads = 192;        // TMA warp, MMA warp, 4 epilogue warps
+static constexpr int kIgemmMaxThreads = 320;     // ... or 8 epilogue warps (IgemmParams::ew8)
 static constexpr int kMaxStages = 24;
-static constexpr int kBarrierBytes = (4 * kMaxStages + 4) * 8 + 16;
+static constexpr int kSlabBytes = 2048;          // one epilogue staging slab: 32 rows x 32 bf16 columns
+static constexpr int kBarrierBytes = (4 * kMaxStages + 4 + 32) * 8 + 16;
 
 // Column totals over the 32 lanes of a warp: v[j] is this lane's (= this output row's) value of column j.  A
 // transposing butterfly (16+8+4+2+1 = 31 shuffles instead of 32 x 5) leaves the total of column `lane` in the
@@ -55,7 +57,7 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 // fprop-type kernel: A = activation views (K-major), B = packed weights (K-major), D -> NHWC output
 // ------------------------------------------------------------------------------------------------
 template <int FMODE, bool HALO = false>
-__global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __grid_constant__ IgemmParams p) {
     // FMODE = IgemmParams::fuse_mode (compile-time: the plain kernel carries none of the fused-epilogue code).
     // HALO  = IgemmParams::halo: the `tps` taps of a stage are the shifted windows of ONE (th+hy) x (tw+hx) halo tile
     //         (tw = 8, tb = 1: window row m = pixel (m / 8, m % 8) = halo row shift + (m / 8) * halo_w + m % 8, i.e. an
@@ -78,20 +80,25 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     const int stages = p.stages;
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * a_stage;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage);
+    // epilogue staging slabs (TMA epilogue): [epilogue warp][slot][32 rows x 64 B], SWIZZLE_64B, 1024-byte aligned
+    uint8_t* sE = sB + stages * b_stage;
+    sE += (1024u - (smem_u32(sE) & 1023u)) & 1023u;
+    const int n_ewarps = p.ew8 ? 8 : 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sE + (p.tep ? n_ewarps * p.ep_slots * kSlabBytes : 0));
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* ebar = tmem_empty + 2;               // [8 epilogue warps][4 slots]: "saved-tensor box has landed"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ebar + 32);
     // fused-epilogue scratch: per-CTA channel sums [groups][2][C], then (mode 2) per-channel (mean, rstd, scale, shift)
     constexpr int fmode = FMODE;
     const int fC = p.fuse_c;
     float* s_sums = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarrierBytes);
     float4* s_prm = reinterpret_cast<float4*>(s_sums + p.fuse_groups * 2 * fC);
     if (fmode == 1 || fmode == 2) {
-        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += kIgemmThreads) s_sums[i] = 0.f;
+        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += blockDim.x) s_sums[i] = 0.f;
         if (fmode == 2) {
-            for (int i = threadIdx.x; i < p.fuse_groups * fC; i += kIgemmThreads) {
+            for (int i = threadIdx.x; i < p.fuse_groups * fC; i += blockDim.x) {
                 const int g = i / fC, c = i - g * fC;
                 const float* st = p.fuse_stats + static_cast<size_t>(g) * 4 * fC;
                 s_prm[i] = make_float4(__ldg(st + c), __ldg(st + fC + c), __ldg(st + 2 * fC + c), __ldg(st + 3 * fC + c));
@@ -108,14 +115,20 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.amap[v]);
         tma_prefetch_desc(&p.bmap);
+        if (p.tep)
+            for (int v = 0; v < p.num_phases; ++v) {
+                tma_prefetch_desc(&p.omap[v]);
+                if (fmode == 2 || fmode == 3) tma_prefetch_desc(&p.xmap[v]);
+            }
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);      // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], n_ewarps);      // one arrival per epilogue warp
         }
+        for (int i = 0; i < 32; ++i) mbar_init(&ebar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -250,7 +263,11 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             }
         }
     } else {
+        // Epilogue warps.  A warp may read only the TMEM lane quadrant (warp % 4); with p.ew8 (one CTA per SM, wide
+        // tiles) two warps share a quadrant and take alternate 32-column chunks.
+        const int ew = warp - 2;
         const int q = warp & 3;
+        const int c_begin = (ew >> 2) * 32, c_step = p.ew8 ? 64 : 32;
         const int row = q * 32 + lane;
         const int w_l = row % p.tw;
         const int h_l = (row / p.tw) % p.th;
@@ -258,6 +275,45 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
         const __nv_bfloat16* fx = static_cast<const __nv_bfloat16*>(p.fuse_x);
         // derivative of the fused layer's activation on the negative side (ReLU 0, LeakyReLU slope, identity 1)
         const float neg_slope = p.fuse_act == 1 ? 0.f : (p.fuse_act == 2 ? p.fuse_slope : 1.f);
+        constexpr bool mode23 = (FMODE == 2 || FMODE == 3);
+        // TMA epilogue (p.tep): the warp's 32 rows x 32 columns of a chunk go through a 2 KB shared-memory slab
+        // (64-byte rows, SWIZZLE_64B: conflict-free 16-byte accesses) and leave with ONE bulk tensor store; in modes
+        // 2 / 3 the same slab first receives the saved tensor's box by TMA, `ep_slots - 2` chunks ahead, and the
+        // result overwrites it in place.  Per-lane 16-byte global accesses at pixel stride cost 32 L1 wavefronts per
+        // instruction and made the LSU pipe the busiest unit of the narrow-tile launches (ncu, round 2).
+        const bool tep = p.tep != 0;
+        const int S = p.ep_slots;
+        const bool xtma = tep && mode23 && S >= 3;      // else (wide tiles, S = 1) the saved tensor comes per lane
+        const uint32_t slab0 = smem_u32(sE) + static_cast<uint32_t>(ew * S) * kSlabBytes;
+        const uint32_t lrow = slab0 + static_cast<uint32_t>(lane) * 64u;       // this lane's row inside slot 0
+        const uint32_t sw = (lane >> 1) & 3;                                   // SWIZZLE_64B: unit ^= (row >> 1) & 3
+        uint64_t* xbar = ebar + ew * 4;
+        const int r0 = q * 32;
+        const int sub_w = r0 % p.tw, sub_h = (r0 / p.tw) % p.th, sub_b = r0 / (p.tw * p.th);
+        int slot = 0;
+        uint32_t xpar = 0;
+        // prefetch cursor of the saved-tensor boxes (lane 0 only)
+        int pf_item = blockIdx.x, pf_c = c_begin, pf_slot = 0, pf_j = 0, pf_i = 0, pf_b = 0, pf_n0 = 0, pf_phase = 0;
+        auto pf_setup = [&]() {
+            if (pf_item >= total_items) return;
+            int i0, j0, b0, n0, phase, it_begin, iters;
+            decode(pf_item, i0, j0, b0, n0, phase, it_begin, iters);
+            pf_j = j0 + sub_w; pf_i = i0 + sub_h; pf_b = b0 + sub_b; pf_n0 = n0; pf_phase = phase;
+        };
+        auto pf_issue = [&]() {
+            if (pf_item >= total_items) return;
+            mbar_expect_tx(&xbar[pf_slot], kSlabBytes);
+            tma_load_4d(sE + (ew * S + pf_slot) * kSlabBytes, &p.xmap[pf_phase], &xbar[pf_slot], pf_n0 + pf_c, pf_j, pf_i,
+                        pf_b);
+            if (++pf_slot == S) pf_slot = 0;
+            pf_c += c_step;
+            if (pf_c >= p.n_tile) { pf_c = c_begin; pf_item += gridDim.x; pf_setup(); }
+        };
+        if (xtma && lane == 0) {
+            pf_setup();
+            for (int i = 0; i < S - 2; ++i) pf_issue();
+        }
+        __syncwarp();
         int li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
             int i0, j0, b0, n0, phase, it_begin, iters;
@@ -274,7 +330,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             float* gs0 = s_sums + grp * 2 * fC;
             float* gs1 = gs0 + fC;
 
-            // mode 2/3: this row's slice of the saved conv output, one 32-column chunk ahead of the accumulator
+            // mode 2/3 without the TMA epilogue: this row's slice of the saved conv output, one chunk ahead
             uint4 xq[4] = {};
             auto load_x = [&](int c) {
                 if (valid) {
@@ -287,12 +343,12 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     }
                 }
             };
-            if (fmode == 2 || fmode == 3) load_x(0);
+            if (mode23 && !xtma) load_x(c_begin);
 
             mbar_wait(&tmem_full[acc], (li >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_tile;
-            for (int c = 0; c < p.n_tile; c += 32) {
+            for (int c = c_begin; c < p.n_tile; c += c_step) {
                 uint32_t v[32];
                 const bool full_chunk = (p.n_tile - c) >= 32;       // else a 16-column tail
                 if (full_chunk) {
@@ -302,6 +358,21 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                     tmem_ld_32x16(taddr + c, h);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[j + 16] = 0; }
+                }
+                const uint32_t my = lrow + static_cast<uint32_t>(slot) * kSlabBytes;
+                if (tep) {
+                    // the slab this chunk uses was last read by the store issued two chunks ago (S = 2) / is about to
+                    // be re-filled for the chunk S - 2 ahead: at most the newest store may still be reading
+                    if (lane == 0) {
+                        if (S == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+                        if (xtma) pf_issue();
+                    }
+                    __syncwarp();
+                    if (xtma) {
+                        mbar_wait(&xbar[slot], xpar);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) xq[k] = ld_shared_v4(my + ((static_cast<uint32_t>(k) ^ sw) << 4));
+                    }
                 }
                 tmem_ld_wait();
                 float f[32];
@@ -342,7 +413,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 int ch0 = 0;
                 if (fmode == 1 || fmode == 2) ch0 = (n0 + c) % fC;
                 float xv[32];
-                if (fmode == 2 || fmode == 3) {
+                if (mode23) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t w4[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
@@ -352,7 +423,7 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                             xv[8 * j + 2 * i + 1] = __uint_as_float(w4[i] & 0xFFFF0000u);
                         }
                     }
-                    if (c + 32 < p.n_tile) load_x(c + 32);
+                    if (!xtma && c + c_step < p.n_tile) load_x(c + c_step);
                     if (fmode == 2) {
                         const float4* pr_base = s_prm + grp * fC + ch0;
 #pragma unroll
@@ -384,7 +455,21 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                if (valid) {
+                if (tep) {
+                    // (rows / columns outside the tensor are dropped by the bulk store itself)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        st_shared_v4(my + ((static_cast<uint32_t>(k) ^ sw) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2],
+                                     pk[4 * k + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&p.omap[phase], sE + (ew * S + slot) * kSlabBytes, n0 + c, j0 + sub_w, i0 + sub_h,
+                                     b0 + sub_b);
+                        bulk_commit();
+                    }
+                    if (++slot == S) { slot = 0; xpar ^= 1; }
+                } else if (valid) {
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + c);
                     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -420,13 +505,14 @@ __global__ void __launch_bounds__(kIgemmThreads) igemm_fprop_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (tep && lane == 0) bulk_wait<0>();      // the slabs must outlive the stores that read them
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
     if (fmode == 1 || fmode == 2) {
         // one flush per CTA; a persistent CTA touches one or two N tiles, the rest of its table is still zero
-        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += kIgemmThreads) {
+        for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += blockDim.x) {
             const float t = s_sums[i];
             if (t != 0.f) atomicAdd(p.fuse_sums + i, t);
         }
@@ -458,6 +544,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 //   [4] issuer: wait full_b      [5] issuer: UMMA issue                  [6] issuer: commit + ring    [7] wait full_a
 #ifndef VG_WGRAD_TRACE
 #define VG_WGRAD_TRACE 0
+#endif
+// -DVG_DEBUG_WGRAD=1 (make debug-wgrad): WgradParams::debug_flags is honoured (profiling experiments that skip the
+// epilogue / main loop / MMAs / TMA loads; results are wrong).  The default build carries none of those branches.
+#ifndef VG_DEBUG_WGRAD
+#define VG_DEBUG_WGRAD 0
+#endif
+#if VG_DEBUG_WGRAD
+#define WGRAD_DBG(p, bit) (((p).debug_flags & (bit)) != 0)
+#else
+#define WGRAD_DBG(p, bit) false
 #endif
 #if VG_WGRAD_TRACE
 __device__ unsigned long long g_wgrad_trace[8];
@@ -523,7 +619,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pt_begin = static_cast<int>(static_cast<long long>(total_tiles) * split / p.splits);
     int pt_end = static_cast<int>(static_cast<long long>(total_tiles) * (split + 1) / p.splits);
-    if (p.debug_flags & 2) pt_end = pt_begin;
+    if (WGRAD_DBG(p, 2)) pt_end = pt_begin;
     const uint32_t ncols = tmem_cols_for(p.taps_per_cta * p.n_tile);
 
     if (warp == 0 && lane == 0) {
@@ -567,7 +663,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                         if (leader)
                             tma_load_4d_pair(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa],
                                              m0 + a * p.p_atom_c, j0, i0, b0);
-                } else if (p.debug_flags & 8) {
+                } else if (WGRAD_DBG(p, 8)) {
                     if (leader) mbar_arrive(&full_a[sa]);
                 } else {
                     if (leader) mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
@@ -594,7 +690,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                                 tma_load_4d_pair(sB + sb * b_stage + h * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
                                                  n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
                         }
-                    } else if (p.debug_flags & 8) {
+                    } else if (WGRAD_DBG(p, 8)) {
                         if (leader) mbar_arrive(&full_b[sb]);
                     } else {
                         if (leader) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
@@ -654,7 +750,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
                         umma_commit_pair(&empty_b[sb]);
-                    } else if (p.debug_flags & 4) {
+                    } else if (WGRAD_DBG(p, 4)) {
                         mbar_arrive(&empty_b[sb]);
                     } else {
                         if (ksteps == 8) {
@@ -682,7 +778,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 }
                 if (leader) {
                     if (PAIR) umma_commit_pair(&empty_a[sa]);
-                    else if (p.debug_flags & 4) mbar_arrive(&empty_a[sa]);
+                    else if (WGRAD_DBG(p, 4)) mbar_arrive(&empty_a[sa]);
                     else umma_commit(&empty_a[sa]);
                 }
                 __syncwarp();
@@ -700,11 +796,33 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
         const int row = q * 32 + lane;
         const int m = m0 + row;
         const bool valid = (row < p.m_atoms * p.p_atom_c) && (m < p.m_valid);
-        const bool has_work = (pt_end > pt_begin) && !(p.debug_flags & 1);
+        const bool has_work = (pt_end > pt_begin) && !WGRAD_DBG(p, 1);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        if (p.splits > 1) {
+        if (p.atomic_split) {
+            // split layers: dw[m][n][4 taps] += this split's tile, one 16-byte reduction per (m, n, 4 taps)
+            for (int g4 = 0; g4 < ntap; g4 += 4) {
+                float* dst = p.dw + static_cast<long long>(m) * p.s_m + (tap0 + g4);
+                for (int c = 0; c < p.n_tile; c += 16) {
+                    uint32_t v0[16], v1[16], v2[16], v3[16];
+                    tmem_ld_32x16(taddr + (g4 + 0) * p.n_tile + c, v0);
+                    tmem_ld_32x16(taddr + (g4 + 1) * p.n_tile + c, v1);
+                    tmem_ld_32x16(taddr + (g4 + 2) * p.n_tile + c, v2);
+                    tmem_ld_32x16(taddr + (g4 + 3) * p.n_tile + c, v3);
+                    tmem_ld_wait();
+                    if (valid && has_work) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.n_valid)
+                                red_add_v4(dst + static_cast<long long>(n) * p.s_n, __uint_as_float(v0[j]),
+                                           __uint_as_float(v1[j]), __uint_as_float(v2[j]), __uint_as_float(v3[j]));
+                        }
+                    }
+                }
+            }
+        } else if (p.splits > 1) {
             // partial tile -> workspace: [cta][tap_local][row][n_tile]; each thread writes its row contiguously
             const long long y_canon = static_cast<long long>(m_tile) * p.n_tiles + n_tile_idx;
             const long long cta = (static_cast<long long>(blockIdx.z) * (p.m_tiles * p.n_tiles) + y_canon) * p.splits + split;
@@ -740,7 +858,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int n = min(n0 + c + j, p.n_valid - 1);
-                                old[j] = (p.debug_flags & 16)
+                                old[j] = (WGRAD_DBG(p, 16) || !p.accumulate)
                                              ? make_float4(0.f, 0.f, 0.f, 0.f)
                                              : __ldcg(reinterpret_cast<const float4*>(dst + static_cast<long long>(n) * p.s_n));
                             }
@@ -771,7 +889,10 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int n = n0 + c + j;
-                                if (n < p.n_valid) dst[static_cast<long long>(n) * p.s_n] += __uint_as_float(v[j]);
+                                if (n < p.n_valid) {
+                                    float* q = dst + static_cast<long long>(n) * p.s_n;
+                                    *q = (p.accumulate ? *q : 0.f) + __uint_as_float(v[j]);
+                                }
                             }
                         }
                     }
@@ -836,11 +957,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) 
 #pragma unroll
             for (int v = 0; v < VEC; ++v) atomicAdd(dst + v, acc[v]);
         } else if (VEC == 4) {
-            float4 o = *reinterpret_cast<float4*>(dst);
+            float4 o = p.accumulate ? *reinterpret_cast<float4*>(dst) : make_float4(0.f, 0.f, 0.f, 0.f);
             o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
             *reinterpret_cast<float4*>(dst) = o;
         } else {
-            dst[0] += acc[0];
+            dst[0] = (p.accumulate ? dst[0] : 0.f) + acc[0];
         }
     }
 }
@@ -865,7 +986,7 @@ static int smem_bytes_for(int stages, int stage_bytes) { return stages * stage_b
 int igemm_total_smem(const IgemmParams& p) {
     const int tps = p.tps > 1 ? p.tps : 1;
     const int stage = p.halo ? p.halo_stage_bytes + tps * p.n_tile * p.kchunk * 2 : tps * (128 + p.n_tile) * p.kchunk * 2;
-    return p.stages * stage + 1024 + kBarrierBytes + igemm_fuse_smem_bytes(p);
+    return p.stages * stage + 1024 + igemm_epilogue_smem_bytes(p) + kBarrierBytes + igemm_fuse_smem_bytes(p);
 }
 
 int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
@@ -883,7 +1004,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     const int smem = igemm_total_smem(p);
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const long long items = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * p.n_tiles * p.num_phases * ksplit;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const int threads = p.ew8 ? kIgemmMaxThreads : kIgemmThreads;
     dim3 grid(static_cast<unsigned>(std::min<long long>(items, 148LL * per_sm)));
     const size_t out_elems = static_cast<size_t>(p.out_B) * p.out_H * p.out_W * p.out_C;
     if (ksplit > 1) {
@@ -892,19 +1014,19 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     }
     if (p.halo) {
         switch (p.fuse_mode) {
-            case 1: igemm_fprop_kernel<1, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-            case 2: igemm_fprop_kernel<2, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-            case 3: igemm_fprop_kernel<3, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-            case 4: igemm_fprop_kernel<4, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-            default: igemm_fprop_kernel<0, true><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+            case 1: igemm_fprop_kernel<1, true><<<grid, threads, smem, stream>>>(p); break;
+            case 2: igemm_fprop_kernel<2, true><<<grid, threads, smem, stream>>>(p); break;
+            case 3: igemm_fprop_kernel<3, true><<<grid, threads, smem, stream>>>(p); break;
+            case 4: igemm_fprop_kernel<4, true><<<grid, threads, smem, stream>>>(p); break;
+            default: igemm_fprop_kernel<0, true><<<grid, threads, smem, stream>>>(p); break;
         }
     } else
     switch (p.fuse_mode) {
-        case 1: igemm_fprop_kernel<1><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-        case 2: igemm_fprop_kernel<2><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-        case 3: igemm_fprop_kernel<3><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-        case 4: igemm_fprop_kernel<4><<<grid, kIgemmThreads, smem, stream>>>(p); break;
-        default: igemm_fprop_kernel<0><<<grid, kIgemmThreads, smem, stream>>>(p); break;
+        case 1: igemm_fprop_kernel<1><<<grid, threads, smem, stream>>>(p); break;
+        case 2: igemm_fprop_kernel<2><<<grid, threads, smem, stream>>>(p); break;
+        case 3: igemm_fprop_kernel<3><<<grid, threads, smem, stream>>>(p); break;
+        case 4: igemm_fprop_kernel<4><<<grid, threads, smem, stream>>>(p); break;
+        default: igemm_fprop_kernel<0><<<grid, threads, smem, stream>>>(p); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -940,7 +1062,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
         igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
         e = cudaGetLastError();
     }
-    if (e != cudaSuccess || p.splits <= 1) return static_cast<int>(e);
+    if (e != cudaSuccess || p.splits <= 1 || p.atomic_split) return static_cast<int>(e);
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * p.num_taps / (p.vec4_taps ? 4 : 1);
     const bool chunked = p.splits >= 16 && total <= 32768;   // few outputs, many splits
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));

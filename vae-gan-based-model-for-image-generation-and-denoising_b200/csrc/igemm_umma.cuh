@@ -65,6 +65,16 @@ struct alignas(64) IgemmParams {
     const float* fuse_stats;   // [groups][4][fuse_c]: mean, rstd, scale, shift
     int fuse_act;
     float fuse_slope;
+    // TMA epilogue (bf16 output, no split-K, n_tile % 32 == 0): every epilogue warp moves its 32 rows x 32 columns
+    // of a chunk through a 2 KB shared-memory slab - one bulk tensor store per chunk (omap[phase]: the output, or its
+    // (row, column) parity view for the strided phases of an `up` contraction) and, in modes 2 / 3, one bulk tensor
+    // load of the saved tensor's box (xmap[phase], same geometry) `ep_slots - 2` chunks ahead.
+    CUtensorMap omap[4];
+    CUtensorMap xmap[4];
+    int tep;
+    int ep_slots;              // slabs per epilogue warp: 2 (store double-buffer) or 3..4 (modes 2 / 3: + prefetch depth)
+    int ew8;                   // 8 epilogue warps (320 threads): two per TMEM lane quadrant taking alternate chunks;
+                               // for launches that own a whole SM (wide tiles), where 4 warps cannot keep up
     // Halo tiles (experiment switch VG_HALO=1; kchunk == 64, tw = 8, th = 16, tb = 1).  The taps of a phase are ordered
     // in groups of `tps` taps that read the same view at shifts within [0, hy] x [0, hx]; a pipeline stage holds ONE
     // activation tile of (th + hy) x (tw + hx) pixels and the group's `tps` weight slabs.  Group index
@@ -82,6 +92,10 @@ inline int igemm_fuse_smem_bytes(const IgemmParams& p) {
     if (p.fuse_mode == 1) return p.fuse_groups * 2 * p.fuse_c * 4;
     if (p.fuse_mode == 2) return p.fuse_groups * p.fuse_c * (2 * 4 + 16);
     return 0;
+}
+// shared memory of the TMA epilogue's staging slabs (+ the padding that aligns them to 1024 B)
+inline int igemm_epilogue_smem_bytes(const IgemmParams& p) {
+    return 1024 + (p.tep ? (p.ew8 ? 8 : 4) * p.ep_slots * 2048 : 0);
 }
 
 struct alignas(64) WgradParams {
@@ -113,6 +127,9 @@ struct alignas(64) WgradParams {
     int pair;              // launch CTA pairs (cta_group::2, M = 256): needs an even m_tiles, full 128-row M tiles, an
                            // even number of Q atoms per stage and taps_per_cta % merge == 0
     int vec4_taps;         // k*k and taps_per_cta multiples of 4, dw 16-byte aligned: dw[m][n][4 taps] moves as one float4
+    int accumulate;        // 1: dw += result (default); 0: dw = result (the owner of a tile skips reading dw; split paths
+                           // start from a zeroed dw / store in the reduction kernel)
+    int atomic_split;      // splits > 1: every CTA adds its tile into dw with red.global.add.v4.f32 (needs vec4_taps)
 };
 
 // Host-side launchers (return cudaError_t as int).

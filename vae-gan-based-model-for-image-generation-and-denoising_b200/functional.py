@@ -151,14 +151,18 @@ def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[Vg
     return big
 
 
-def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dw[small_c, big_c, k, k] (+)= wgrad; a fresh zeroed buffer is created when `dw` is None."""
+def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None,
+               overwrite: bool = False) -> torch.Tensor:
+    """dw[small_c, big_c, k, k] += wgrad, or, with `overwrite` / a fresh buffer (`dw` None), dw = wgrad
+    (VG_WGRAD_OVERWRITE: the buffer need not be initialised)."""
     if dw is None:
-        dw = torch.zeros((g.small_c, g.big_c_valid or g.big_c, g.kernel, g.kernel), dtype=torch.float32,
+        dw = torch.empty((g.small_c, g.big_c_valid or g.big_c, g.kernel, g.kernel), dtype=torch.float32,
                          device=small.device)
+        overwrite = True
     nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
     ws = _ws(nbytes, small.device) if nbytes else None
-    call("vg_conv_wgrad", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes, _stream(),
+    call("vg_conv_wgrad_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes,
+         _lib.WGRAD_OVERWRITE if overwrite else 0, _stream(),
          flops=conv_flops(g), tag=_conv_tag(g, "wgrad"), nbytes=conv_bytes(g))
     if ws is not None and WgradOverlap.streams:
         WgradOverlap.keepalive.append(ws)
@@ -210,17 +214,38 @@ def bn_act_train_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, act
 
 class SumsArena:
     """Zero-initialised fp32 scratch for the channel sums of the fused convolution epilogues.  Slices are handed
-    out sequentially from one buffer per device; `reset()` (called by the fused step at the start of every step, so
-    that a captured CUDA graph always sees the same addresses) re-zeroes it with one memset.  When the buffer runs out
-    a fresh zero buffer replaces it - the old one stays alive through the slices still referencing it."""
+    out sequentially.  A fused step OWNS its arena (`activate(buffer)` at the start of every step, after zeroing
+    the part it used: the addresses are baked into its CUDA graph, so the buffer lives exactly as long as the step
+    object and nothing else ever hands out or replaces it).  Module calls outside a step draw from a per-device
+    default buffer; when that runs out a fresh zero buffer replaces it - the old one stays alive through the slices
+    still referencing it."""
     FLOATS = 1 << 20
     _buf = {}
     _off = {}
+    _owned = None          # [buffer, offset, high-water mark] of the step currently running
+
+    @classmethod
+    def activate(cls, buf: torch.Tensor) -> None:
+        cls._owned = [buf, 0, 0]
+
+    @classmethod
+    def deactivate(cls) -> int:
+        """-> floats the owner handed out (its high-water mark: what it has to re-zero next time)."""
+        used = cls._owned[2] if cls._owned is not None else 0
+        cls._owned = None
+        return used
 
     @classmethod
     def take(cls, n: int, device) -> torch.Tensor:
-        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
         n = (n + 31) // 32 * 32
+        if cls._owned is not None:
+            buf, off, _ = cls._owned
+            if off + n > buf.numel():
+                raise _lib.VaeganB200Error(f"fused-epilogue sums arena exhausted ({buf.numel()} floats)")
+            cls._owned[1] = off + n
+            cls._owned[2] = max(cls._owned[2], off + n)
+            return buf[off:off + n]
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
         buf = cls._buf.get(key)
         if buf is None or cls._off[key] + n > buf.numel():
             buf = torch.zeros(max(cls.FLOATS, n), dtype=torch.float32, device=device)
@@ -463,9 +488,10 @@ class S2DWeightMap:
         call("vg_gather_f32", _p(t["weq"]), _p(_contig(master)), _p(t["fwd"]), t["weq"].numel(), 1, 0, _stream())
         return t["weq"]
 
-    def grad_buffer(self, device) -> torch.Tensor:
+    def grad_buffer(self, device, zero: bool = True) -> torch.Tensor:
         t = self._tensors(device)
-        t["dweq"].zero_()
+        if zero:
+            t["dweq"].zero_()
         return t["dweq"]
 
     def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
@@ -508,9 +534,10 @@ class LinearGemmMap:
         call("vg_linear_permute", _p(_contig(master)), _p(t["weq"]), self.n, self.n_pad, self.C, self.kk, 0, _stream())
         return t["weq"]
 
-    def grad_buffer(self, device) -> torch.Tensor:
+    def grad_buffer(self, device, zero: bool = True) -> torch.Tensor:
         t = self._tensors(device)
-        t["dweq"].zero_()
+        if zero:
+            t["dweq"].zero_()
         return t["dweq"]
 
     def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
@@ -550,9 +577,10 @@ class PadRowsMap:
         call("vg_linear_permute", _p(_contig(master)), _p(t["weq"]), self.n, self.n_pad, self.row, 1, 0, _stream())
         return t["weq"]
 
-    def grad_buffer(self, device) -> torch.Tensor:
+    def grad_buffer(self, device, zero: bool = True) -> torch.Tensor:
         t = self._tensors(device)
-        t["dweq"].zero_()
+        if zero:
+            t["dweq"].zero_()
         return t["dweq"]
 
     def scatter(self, dweq: torch.Tensor, target: torch.Tensor) -> None:
@@ -588,7 +616,12 @@ class PackedWeights:
         key = (w.data_ptr(), g.small_c, g.big_c, g.kernel)
         if self.version != w._version or self.key != key:
             src = wmap.materialize(w.detach()) if wmap is not None else w.detach()
-            self.wd, self.wu = pack_weights(src, g)
+            kk = g.kernel * g.kernel
+            if self.wd is not None and self.wd.shape == (kk, g.small_c, g.big_c) and self.wd.device == w.device:
+                # refresh IN PLACE: a captured CUDA graph (fused step) may hold these addresses
+                call("vg_pack_weights_bf16", ctypes.byref(g), _p(src), _p(self.wd), _p(self.wu), _stream())
+            else:
+                self.wd, self.wu = pack_weights(src, g)
             self.version, self.key = w._version, key
         return self.wd, self.wu
 
@@ -812,9 +845,12 @@ class ConvLayerFn(torch.autograd.Function):
                 if bias_with_wgrad:
                     bias_sum(d_raw, dbias)
                 if wmap is None:
-                    return conv_wgrad(small, big, g, main_grad)
+                    # (a flat-buffer owner that zeroes before every backward pass and runs each layer once per pass
+                    # marks its gradients `first_touch`: the kernel then stores instead of read-add-write)
+                    return conv_wgrad(small, big, g, main_grad,
+                                      overwrite=main_grad is not None and getattr(weight, "grad_first_touch", False))
                 # space-to-depth layer: gradient of the equivalent weights, folded back into the master layout
-                dweq = conv_wgrad(small, big, g, wmap.grad_buffer(small.device))
+                dweq = conv_wgrad(small, big, g, wmap.grad_buffer(small.device, zero=False), overwrite=True)
                 target = main_grad if main_grad is not None else torch.zeros(weight.shape, dtype=torch.float32,
                                                                              device=small.device)
                 wmap.scatter(dweq, target)

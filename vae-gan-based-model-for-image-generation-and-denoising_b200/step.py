@@ -32,6 +32,7 @@ class _FlatAdam:
 
     def __init__(self, net: nn.Module, lr, betas, eps):
         params = [p for p in net.parameters()]
+        self.names = [k for k, _ in net.named_parameters()]
         dev = params[0].device
         offs, total = [], 0
         for p in params:
@@ -49,11 +50,18 @@ class _FlatAdam:
             view.copy_(p.detach())
             p.data = view
             p.main_grad = self.grads[o:o + p.numel()].view_as(p)
+            # the step zeroes `grads` before every backward pass and each layer runs once per pass: the weight-gradient
+            # kernel may store instead of read-add-write (functional.ConvLayerFn.backward)
+            p.grad_first_touch = True
             p.grad = None
         self.lr, self.betas, self.eps = lr, betas, eps
 
     def zero_grad(self):
         self.grads.zero_()      # cudaMemsetAsync
+
+    def named_views(self, flat: torch.Tensor):
+        """{parameter name: view of `flat` shaped like the parameter} for a flat buffer laid out like `self.grads`."""
+        return {k: flat[o:o + n].view(shape) for k, o, n, shape in zip(self.names, self.offsets, self.sizes, self.shapes)}
 
     def state_dict(self):
         """Per-parameter moments in `net.parameters()` order and the step count - the content of
@@ -130,7 +138,8 @@ class VAEGANStep:
     def __init__(self, encoder, decoder, discriminator, *, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  alpha_kl: float = 0.1, alpha_adv: float = 0.1, kl_warmup_epochs: int = 50, sigma_inst: float = 0.05,
                  denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
-                 process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True):
+                 process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True,
+                 capture_grads: bool = False):
         self.E, self.G, self.D = encoder, decoder, discriminator
         self.dtype = encoder._dtype()
         self.dev = next(encoder.parameters()).device
@@ -140,14 +149,31 @@ class VAEGANStep:
         self.sigma_inst, self.denoise_sigma, self.n_dis = sigma_inst, denoise_sigma, n_dis
         self.real_label, self.fake_label = real_label, fake_label
         self.pg = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
         self.opt_E = _FlatAdam(encoder, lr, betas, eps)
         self.opt_G = _FlatAdam(decoder, lr, betas, eps)
         self.opt_D = _FlatAdam(discriminator, lr, betas, eps)
+        if self.world > 1:
+            # replicas must start from the same state (DDP's constructor does the same): rank 0's parameters and
+            # BatchNorm buffers go to everyone
+            dist = torch.distributed
+            src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+            for opt in (self.opt_E, self.opt_G, self.opt_D):
+                dist.broadcast(opt.params, src, group=process_group)
+            for net in (encoder, decoder, discriminator):
+                for b in net.buffers():
+                    dist.broadcast(b, src, group=process_group)
+        # channel-sum scratch of the fused convolution epilogues: owned by this step (its graph bakes the addresses in)
+        self._sums = torch.zeros(F_.SumsArena.FLOATS, dtype=torch.float32, device=self.dev)
+        self._sums_used = self._sums.numel()
         self.use_graph = use_cuda_graph
         self.seed = seed
+        # parity tests: keep a copy of the discriminator's gradient of EVERY update (the flat buffer is re-used)
+        self.capture_grads = capture_grads
+        self._d_grad_copies = [torch.zeros_like(self.opt_D.grads) for _ in range(n_dis)] if capture_grads else []
         # side streams (parallel branches of the captured graph): weight gradients round-robin, plus the start-of-step
         # weight packing and noise generation that the encoder's forward pass does not wait for
         self.wgrad_streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)] if overlap_wgrad else []
@@ -177,8 +203,9 @@ class VAEGANStep:
         return s
 
     def _randn_into(self, t: torch.Tensor, stream_id: int):
+        # (Philox stream = 16 * rank + tensor id: data-parallel replicas draw different noise from the same seed)
         call("vg_randn", _p(t), t.numel(), ctypes.c_ulonglong(self.seed), _p(self._static["rng_offset"]),
-             ctypes.c_ulonglong(stream_id), _stream())
+             ctypes.c_ulonglong(16 * self.rank + stream_id), _stream())
 
     def _allreduce(self, opt: _FlatAdam):
         if self.world > 1:
@@ -188,9 +215,12 @@ class VAEGANStep:
     def _run(self, gen_noise: bool):
         if self.wgrad_streams:
             F_.WgradOverlap.enable(self.wgrad_streams)
+        self._sums[:self._sums_used].zero_()          # one memset per step (only what the previous run handed out)
+        F_.SumsArena.activate(self._sums)
         try:
             self._run_body(gen_noise)
         finally:
+            self._sums_used = max(32, F_.SumsArena.deactivate())
             F_.WgradOverlap.disable()
 
     def _run_body(self, gen_noise: bool):
@@ -198,7 +228,6 @@ class VAEGANStep:
         E, G, D = self.E, self.G, self.D
         real, loss = s["real"], s["losses"]
         B = real.shape[0]
-        F_.SumsArena.reset(self.dev)   # channel-sum scratch of the fused conv epilogues: one memset per step
         # every replay starts from freshly packed bf16 weights (one launch per net): the encoder's are needed at once,
         # the generator's and the discriminator's are packed on the second stream under the encoder's forward pass
         E.repack_weights()
@@ -264,6 +293,8 @@ class VAEGANStep:
             call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
             torch.autograd.backward([p_pair], [dp])
             F_.WgradOverlap.join()
+            if self.capture_grads:
+                self._d_grad_copies[it].copy_(self.opt_D.grads)
             self._allreduce(self.opt_D)
             self.opt_D.step(1.0 / self.world)
             D.repack_weights()
@@ -374,6 +405,12 @@ class VAEGANStep:
                 self._restore_state(self._snapshot)
                 self._snapshot = None
             self._graph[1].replay()
+        # The encoder's and the generator's masters were updated by the fused Adam at the end of the step, behind
+        # autograd's version counters; their bf16 copies are re-packed at the start of the NEXT step.  Anything that
+        # uses the modules in between (validation, generation: vaegan_code.py:147-171, main_vae.py:348-374) must not
+        # see the stale copies: mark them so that the next module call re-packs (in place).
+        self.E.invalidate_packed_weights()
+        self.G.invalidate_packed_weights()
         return {k: s["losses"][i] for i, k in enumerate(LOSS_KEYS)}
 
     # state save / restore so that warm-up + capture do not advance training
@@ -406,10 +443,19 @@ class VAEGANStep:
         self.opt_E.load_state_dict(sd["opt_E"])
         self.opt_G.load_state_dict(sd["opt_G"])
         self.opt_D.load_state_dict(sd["opt_D"])
-        self.seed = sd.get("seed", self.seed)
+        if sd.get("seed", self.seed) != self.seed:
+            self.seed = sd["seed"]
+            self._graph = None          # the seed is a launch argument baked into the captured graph
         self._pending_rng = int(sd.get("rng_offset", 0))
         if self._static is not None:
             self._static["rng_offset"].fill_(self._pending_rng)
+
+    def gradients(self):
+        """Gradients of the most recent step as {name: tensor} per network: "E" / "G" (what their Adam consumed, i.e.
+        after the all-reduce, before the 1/world scale) and "D" = a list with one dict per discriminator update (all of
+        them with `capture_grads=True`, else only the last).  Views of the flat buffers: clone to keep."""
+        d = [self.opt_D.named_views(c) for c in self._d_grad_copies] or [self.opt_D.named_views(self.opt_D.grads)]
+        return {"E": self.opt_E.named_views(self.opt_E.grads), "G": self.opt_G.named_views(self.opt_G.grads), "D": d}
 
     def last_outputs(self):
         """mu, logvar, recon of the most recent step (device tensors; static under CUDA-graph replay)."""
