@@ -139,9 +139,12 @@ int vg_conv_up_ex(const VgConvGeom* g, VgDType dtype, const void* small, const v
  * tiles into dw with 16-byte vector reductions (fp32 atomics: the summation order, hence the last bits, vary from
  * run to run).  vg_conv_wgrad_workspace_bytes() reports the scratch the non-atomic variant (partial tiles + a
  * reduction kernel; experiment switch VG_WGRAD_ATOMIC=0) needs - 0 otherwise; ws may be NULL.
- * vg_conv_wgrad_ex with VG_WGRAD_OVERWRITE: dw = gradient; dw need not be initialised (a tile's single owner skips
- * the read-modify-write, split layers zero dw first). */
+ * vg_conv_wgrad_ex flags: VG_WGRAD_OVERWRITE - dw = gradient; dw need not be initialised (a tile's single owner skips
+ * the read-modify-write, split layers zero dw first).  VG_WGRAD_DST_ZERO - the caller guarantees dw is all zeros
+ * (first gradient after optimizer.zero_grad()): same result as accumulating, without reading dw where one CTA owns
+ * a tile and without the extra memset of the split layers. */
 #define VG_WGRAD_OVERWRITE 1
+#define VG_WGRAD_DST_ZERO 2
 size_t vg_conv_wgrad_workspace_bytes(const VgConvGeom* g, VgDType dtype);
 int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw, void* ws,
                   size_t ws_bytes, void* stream);

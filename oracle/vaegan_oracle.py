@@ -212,8 +212,8 @@ def reference_step(enc, gen, dis, opt_e, opt_g, opt_d, real, epoch: int, eps, n_
     z = z.unsqueeze(-1).unsqueeze(-1)                    # :78
     recon = gen(z)                                       # :83
 
-    real_labels = torch.full((batch,), 0.9, device=real.device)   # :88
-    fake_labels = torch.full((batch,), 0.1, device=real.device)   # :89
+    real_labels = torch.full((batch,), 0.9, device=real.device, dtype=real.dtype)   # :88 (dtype: float64 twins)
+    fake_labels = torch.full((batch,), 0.1, device=real.device, dtype=real.dtype)   # :89
     real_noisy = real + sigma_inst * n_real              # :91
     recon_noisy = recon + sigma_inst * n_fake            # :92
 
@@ -250,7 +250,7 @@ def reference_step(enc, gen, dis, opt_e, opt_g, opt_d, real, epoch: int, eps, n_
 
 # --------------------------------------------------------------------------------------------- bf16 emulation
 def _round_bf16(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).to(torch.float32)
+    return t.to(torch.bfloat16).to(t.dtype)       # (dtype-preserving: the emulation also runs on float64 twins)
 
 
 class _RoundSTE(torch.autograd.Function):

@@ -34,7 +34,7 @@ class VgEpilogue(Structure):
                 ("sums", c_void_p), ("x", c_void_p), ("stats", c_void_p)]
 
 
-WGRAD_OVERWRITE = 1
+WGRAD_OVERWRITE, WGRAD_DST_ZERO = 1, 2
 EPI_NONE, EPI_BN_STATS, EPI_BN_BWD, EPI_ACT_BWD, EPI_ACT_FWD = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one

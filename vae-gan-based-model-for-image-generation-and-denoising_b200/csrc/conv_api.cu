@@ -603,7 +603,7 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
     p.stages_b = std::max(2, std::min(20, (200 * 1024 - p.stages_a * a_stage) / b_stage));
     p.dw = dw;
     p.debug_flags = switches().debug_wgrad;
-    p.accumulate = overwrite ? 0 : 1;
+    p.accumulate = overwrite ? 0 : 1;      // (overwrite: 1 = unknown content, 2 = the caller says dw is zero)
     const int bcv = bc_valid(g);
     p.s_m = static_cast<long long>(bcv) * k * k;
     p.s_n = k * k;
@@ -640,8 +640,11 @@ static int wgrad_umma(const VgConvGeom* g, const void* small, const void* big, f
         return VG_OK;
     }
     if (p.splits > 1 && overwrite) {       // every split path accumulates: start from zero
-        const cudaError_t e = cudaMemsetAsync(dw, 0, static_cast<size_t>(g->small_c) * bcv * k * k * sizeof(float), stream);
-        if (e != cudaSuccess) return cuda_fail(e, "wgrad: memset");
+        if (overwrite == 1) {
+            const cudaError_t e =
+                cudaMemsetAsync(dw, 0, static_cast<size_t>(g->small_c) * bcv * k * k * sizeof(float), stream);
+            if (e != cudaSuccess) return cuda_fail(e, "wgrad: memset");
+        }
         p.accumulate = 1;
     }
     const int rc = launch_wgrad(p, stream);
@@ -875,7 +878,7 @@ static int wgrad_dispatch(const VgConvGeom* g, VgDType dtype, const void* small,
     if (rc != VG_OK) return rc;
     if (dtype == VG_BF16 && !is_gemv(g) && umma_wgrad_ok(g))
         return wgrad_umma(g, small, big, dw, ws, ws_bytes, as_stream(stream), nullptr, overwrite);
-    if (overwrite) {     // the other paths accumulate: give them a zeroed destination
+    if (overwrite == 1) {     // the other paths accumulate: give them a zeroed destination
         const size_t n = static_cast<size_t>(g->small_c) * bc_valid(g) * g->kernel * g->kernel;
         const cudaError_t e = cudaMemsetAsync(dw, 0, n * sizeof(float), as_stream(stream));
         if (e != cudaSuccess) return cuda_fail(e, "wgrad: memset");
@@ -891,6 +894,7 @@ extern "C" int vg_conv_wgrad(const VgConvGeom* g, VgDType dtype, const void* sma
 
 extern "C" int vg_conv_wgrad_ex(const VgConvGeom* g, VgDType dtype, const void* small, const void* big, float* dw,
                                 void* ws, size_t ws_bytes, int flags, void* stream) {
-    if (flags & ~VG_WGRAD_OVERWRITE) return fail(VG_ERR_ARG, "wgrad: unknown flags 0x%x", flags);
-    return wgrad_dispatch(g, dtype, small, big, dw, ws, ws_bytes, (flags & VG_WGRAD_OVERWRITE) ? 1 : 0, stream);
+    if (flags & ~(VG_WGRAD_OVERWRITE | VG_WGRAD_DST_ZERO)) return fail(VG_ERR_ARG, "wgrad: unknown flags 0x%x", flags);
+    return wgrad_dispatch(g, dtype, small, big, dw, ws, ws_bytes,
+                          (flags & VG_WGRAD_OVERWRITE) ? 1 : ((flags & VG_WGRAD_DST_ZERO) ? 2 : 0), stream);
 }

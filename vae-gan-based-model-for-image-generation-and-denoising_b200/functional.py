@@ -152,9 +152,10 @@ def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[Vg
 
 
 def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Optional[torch.Tensor] = None,
-               overwrite: bool = False) -> torch.Tensor:
+               overwrite: bool = False, dst_zero: bool = False) -> torch.Tensor:
     """dw[small_c, big_c, k, k] += wgrad, or, with `overwrite` / a fresh buffer (`dw` None), dw = wgrad
-    (VG_WGRAD_OVERWRITE: the buffer need not be initialised)."""
+    (VG_WGRAD_OVERWRITE: the buffer need not be initialised).  `dst_zero`: the caller knows dw is all zeros
+    (VG_WGRAD_DST_ZERO)."""
     if dw is None:
         dw = torch.empty((g.small_c, g.big_c_valid or g.big_c, g.kernel, g.kernel), dtype=torch.float32,
                          device=small.device)
@@ -162,7 +163,7 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, g: VgConvGeom, dw: Option
     nbytes = _lib.load().vg_conv_wgrad_workspace_bytes(ctypes.byref(g), _DT[small.dtype])
     ws = _ws(nbytes, small.device) if nbytes else None
     call("vg_conv_wgrad_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(big), _p(dw), _p(ws), nbytes,
-         _lib.WGRAD_OVERWRITE if overwrite else 0, _stream(),
+         _lib.WGRAD_OVERWRITE if overwrite else (_lib.WGRAD_DST_ZERO if dst_zero else 0), _stream(),
          flops=conv_flops(g), tag=_conv_tag(g, "wgrad"), nbytes=conv_bytes(g))
     if ws is not None and WgradOverlap.streams:
         WgradOverlap.keepalive.append(ws)
@@ -846,9 +847,9 @@ class ConvLayerFn(torch.autograd.Function):
                     bias_sum(d_raw, dbias)
                 if wmap is None:
                     # (a flat-buffer owner that zeroes before every backward pass and runs each layer once per pass
-                    # marks its gradients `first_touch`: the kernel then stores instead of read-add-write)
+                    # marks its gradients `first_touch`: the kernel then skips reading the (zero) destination)
                     return conv_wgrad(small, big, g, main_grad,
-                                      overwrite=main_grad is not None and getattr(weight, "grad_first_touch", False))
+                                      dst_zero=main_grad is not None and getattr(weight, "grad_first_touch", False))
                 # space-to-depth layer: gradient of the equivalent weights, folded back into the master layout
                 dweq = conv_wgrad(small, big, g, wmap.grad_buffer(small.device, zero=False), overwrite=True)
                 target = main_grad if main_grad is not None else torch.zeros(weight.shape, dtype=torch.float32,
