@@ -66,11 +66,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_batch = 64
-    # each "step" is a bounded sample of the cfg-2 step: 64 of the 256 images of one GPU's batch, same nets, fp32
-    # (about 0.3 s per step on the box's 16 host cores: exactly --steps timed steps after --warmup untimed ones)
+    sample_batch = BATCH_PER_GPU
+    # each "step" is one full cfg-2 step of ONE GPU's batch (256 images, same nets, fp32) on all host cores: about
+    # 1.3 s per step on the box's 16 cores - exactly --steps timed steps after --warmup untimed ones (a wall-clock
+    # guard of 240 s ends the loop early on a slow host; `steps` then reports what was timed)
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    rate, sec, cores, steps = _cpu_step_rate(sample_batch, timed=steps, warm=warm)
+    rate, sec, cores, steps = _cpu_step_rate(sample_batch, timed=steps, warm=warm, budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate,
         "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
@@ -78,11 +79,11 @@ def run_reference_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN (SURVEY A.1), latent 128",
                    "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * args.gpus,
-                   "parallelism": f"dp{args.gpus}",
-                   "note": "reference CPU arithmetic (torch CPU/oneDNN) on the oracle's line-by-line restatement of "
+                   "parallelism": f"dp{args.gpus}", "measured_batch": sample_batch,
+                   "note": "one process on the host cores steps one GPU's batch; reference CPU arithmetic (torch CPU/oneDNN) on the oracle's line-by-line restatement of "
                            "vaegan_code.py:66-135"},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} timed steps of {sample_batch} images (a quarter of one GPU's cfg-2 batch)"},
+                         "sample": f"{steps} timed steps of {sample_batch} images (one GPU's full cfg-2 batch per step)"},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -246,6 +247,12 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_u8_value = world * B * args.steps / float(t)
 
+    extra = None
+    if not args.no_extra:
+        del step
+        torch.cuda.empty_cache()
+        extra = _extra_configs(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, min(args.steps, 10))
+
     if rank != 0:
         _finish(world)
         return 0
@@ -255,10 +262,10 @@ def run_gpu_arm(args):
     kernels = _kernel_microbench(torch, vb, dev) if not args.no_micro else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores, _ = _cpu_step_rate(64, timed=3, warm=1)
+        rate, sec, cores, n_timed = _cpu_step_rate(BATCH_PER_GPU, timed=3, warm=1, budget_s=60.0)
         cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "cfg1: 3 timed steps (median) of 64 images, fp32, same nets, oracle restatement of "
-                         "vaegan_code.py:66-135 on torch CPU"}
+               "sample": f"{n_timed} timed steps (median) of {BATCH_PER_GPU} images (the cfg-2 batch), fp32, same nets, "
+                         "oracle restatement of vaegan_code.py:66-135 on torch CPU"}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -295,11 +302,124 @@ def run_gpu_arm(args):
                                     "what": "6.245 GFLOP/image x batch / step time"},
                      "kernels": kernels},
         "cpu_baseline": cpu,
+        "other_configs": extra,
         "final_total_loss": final_total,
     }
     print(json.dumps(line), flush=True)
     _finish(world)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------ configs 3, 4, 5
+CFG4_GFLOP_PER_IMAGE = 33.49          # 128x128 nets, double width, latent 256
+
+
+def _time_step(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, *, hw, nz, width, batch, sigma, steps):
+    """ms/step (max over ranks) of the graph-replayed bf16 step for one net / batch configuration, inputs resident."""
+    torch.manual_seed(42)
+    enc = vb.Encoder([3, hw, hw], nz, width=width, precision="bf16")
+    gen = vb.Generator(nz=nz, ngf=64 * width, hw=hw, precision="bf16")
+    dis = vb.Discriminator(ndf=64 * width, hw=hw, precision="bf16")
+    gen.apply(vb.weights_init)
+    dis.apply(vb.weights_init)
+    for m in (enc, gen, dis):
+        m.to(dev)
+    step = VAEGANStep(enc, gen, dis, use_cuda_graph=True, seed=4321 + rank, denoise_sigma=sigma)
+    g = torch.Generator(device="cpu").manual_seed(2000 + rank)
+    pool = [(torch.rand(batch, 3, hw, hw, generator=g) * 2 - 1).to(dev) for _ in range(2)]
+    for i in range(3):
+        step.step(pool[i % 2], 50)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses = step.step(pool[i % 2], 50)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total = float(losses["total"])
+    del step, enc, gen, dis, pool
+    torch.cuda.empty_cache()
+    return float(t) / steps, total
+
+
+def _generation_sweep(torch, vb, dev):
+    """cfg 5: decoder-only generation (main_vae.py:360-366: eval-mode decoder under no_grad on z ~ N(0, I)) through
+    vaegan_b200.GraphedGenerator (one CUDA graph per batch size), batch 1 ... 4096, latency and images/s per batch;
+    the reference decoder on the host cores beside it at three batch sizes (oracle port, bounded)."""
+    peaks = _peaks()
+    torch.manual_seed(42)
+    gen = vb.Generator(nz=NZ, hw=HW, precision="bf16")
+    gen.apply(vb.weights_init)
+    gen.to(dev).eval()
+    gg = vb.GraphedGenerator(gen)
+    rows = []
+    gflop_per_image = 2 * 0.41805        # forward MACs of the 64x64 generator (SURVEY.md A.2): 0.836 GFLOP / image
+    for b in (1, 4, 16, 64, 256, 1024, 4096):
+        z = torch.randn(b, NZ, 1, 1, device=dev)
+        for _ in range(3):
+            gg(z)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            n = 50 if b <= 256 else 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                out = gg(z)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            best = ms if best is None else min(best, ms)
+        rows.append({"batch": b, "ms": best, "images_per_s": b / (best * 1e-3),
+                     "tflops": gflop_per_image * b / best, "frac_of_bf16_peak": gflop_per_image * b / best / peaks["sustained"]})
+    cpu = []
+    try:
+        from oracle import vaegan_oracle as vo
+        torch.set_num_threads(os.cpu_count() or 1)
+        g_ref = vo.make_generator(nz=NZ, ngf=64, hw=HW).eval()
+        for b in (1, 64, 1024):
+            z = torch.randn(b, NZ, 1, 1)
+            vo.generate(g_ref, z)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                vo.generate(g_ref, z)
+            dt = (time.perf_counter() - t0) / reps
+            cpu.append({"batch": b, "ms": dt * 1e3, "images_per_s": b / dt})
+    except Exception as e:      # the CPU leg is a reported baseline, never a reason to lose the GPU numbers
+        cpu = [{"error": repr(e)}]
+    return {"workload": "cfg5", "what": "eval-mode generator forward z -> 64x64 image (fp32 NCHW out), bf16 tensor-core "
+            "path, one CUDA graph per batch size, z resident, best of 3 x n replays", "sweep": rows,
+            "cpu_reference_decoder": {"cores": os.cpu_count() or 1, "kind": "port", "rows": cpu}}
+
+
+def _extra_configs(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, steps):
+    """BASELINE.json configs 3, 4 and 5 next to the headline cfg-2 line (same timing rules: warm-up 3, CUDA events,
+    max over ranks, inputs resident and far larger than L2)."""
+    peaks = _peaks()
+    out = {}
+    ms, total = _time_step(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, hw=HW, nz=NZ, width=1,
+                           batch=BATCH_PER_GPU, sigma=0.1, steps=steps)
+    out["cfg3"] = {"workload": "cfg3", "what": "denoising mode: encoder input = clamp(real + 0.1 * noise, -1, 1), drawn "
+                   "on the device every step; reconstruction target stays real", "batch_per_gpu": BATCH_PER_GPU,
+                   "global_batch": BATCH_PER_GPU * world, "n_gpus": world, "ms_per_step": ms, "steps": steps,
+                   "images_per_s": world * BATCH_PER_GPU / (ms * 1e-3), "final_total_loss": total,
+                   "whole_step_frac_of_bf16_peak": STEP_GFLOP_PER_IMAGE * BATCH_PER_GPU / ms / peaks["sustained"]}
+    # cfg 4: global batch 512 over 2 / 4 / 8 GPUs; a single GPU runs the 8-GPU shard (64 images)
+    b4 = 512 // world if world >= 2 else 64
+    ms, total = _time_step(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, hw=128, nz=256, width=2, batch=b4,
+                           sigma=0.0, steps=steps)
+    out["cfg4"] = {"workload": "cfg4", "what": "128x128 nets, 2x channel width, latent 256" +
+                   ("" if world >= 2 else "; ONE GPU running the per-GPU shard of the 8-GPU case (64 images)"),
+                   "batch_per_gpu": b4, "global_batch": b4 * world, "n_gpus": world, "ms_per_step": ms, "steps": steps,
+                   "images_per_s": world * b4 / (ms * 1e-3), "final_total_loss": total,
+                   "whole_step_frac_of_bf16_peak": CFG4_GFLOP_PER_IMAGE * b4 / ms / peaks["sustained"]}
+    if rank == 0 and world == 1:
+        out["cfg5"] = _generation_sweep(torch, vb, dev)
+    return out
 
 
 def _finish(world: int):
@@ -358,17 +478,21 @@ def _kernel_microbench(torch, vb, dev):
     out = []
     B = BATCH_PER_GPU
 
-    def timeit(f, iters=10):
+    def timeit(f, iters=20, repeats=3):
         for _ in range(3):
             f()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            f()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+        best = None
+        for _ in range(repeats):           # min of 3 x 20: one slow repeat (clock ramp, a stray host stall) does not stick
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                f()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            best = ms if best is None else min(best, ms)
+        return best
 
     shapes = [("G ConvT 512->256 8^2->16^2", fn.ConvSpec("up", 512, 256, 4, 2, 1), 8),
               ("G ConvT 256->128 16^2->32^2", fn.ConvSpec("up", 256, 128, 4, 2, 1), 16),
@@ -416,6 +540,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel micro-benchmarks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg 3 / 4 / 5 measurements (other_configs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -27,9 +27,11 @@ def test_reference_arm_json_line():
     assert line["unit"] == "images/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 1
     assert line["config"]["workload"] == "cfg2" and "model" not in line["config"]
-    assert line["value"] > 0 and abs(line["ms_per_step"] * 1e-3 * line["value"] - 64) < 1e-6 * 64     # 64-image sample
+    # every timed step is one GPU's FULL cfg-2 batch (256 images): the label and the measurement are the same config
+    assert line["config"]["batch_per_gpu"] == 256 and line["config"]["measured_batch"] == 256
+    assert line["value"] > 0 and abs(line["ms_per_step"] * 1e-3 * line["value"] - 256) < 1e-6 * 256
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "64 images" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "256 images" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

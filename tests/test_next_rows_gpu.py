@@ -139,3 +139,39 @@ def test_uint8_nhwc_input_path():
     for k in la:      # d_loss_1 / adv / total follow discriminator Adam steps whose near-zero gradients carry sign noise
         tol = 1e-5 if k in ("d_loss_0", "recon", "kl") else 1e-3
         assert abs(float(la[k]) - float(lb[k])) <= tol * abs(float(lb[k])) + 1e-7, k
+
+
+@pytest.mark.parametrize("batch", [1, 16, 256])
+def test_cfg5_graphed_generator(batch):
+    """vaegan_b200.GraphedGenerator: the eval-mode generator replayed from one CUDA graph per batch size gives the
+    eager module's output bit for bit, tracks weight updates made between replays (no re-capture), and agrees with
+    the oracle's generate() (main_vae.py:361-366) within the bf16 tolerance."""
+    import vaegan_b200 as vb
+    from oracle import vaegan_oracle as vo
+    o_nets, nets = make_pair(64, 128, "bf16")
+    g_ref, g = o_nets[1], nets[1]
+    g.eval()
+    gg = vb.GraphedGenerator(g)
+    z = torch.randn(batch, 128, 1, 1, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        eager = g(z.cuda()).clone()
+    out = gg(z.cuda(), clone=True)
+    again = gg(z, clone=True)                       # host z: copied into the graph's static buffer
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager) and torch.equal(again, eager)
+    assert float((out.cpu() - vo.generate(g_ref, z)).abs().max()) < 3e-2
+    # an optimizer step between two replays: the graph must read the new weights
+    with torch.no_grad():
+        for p_mine, p_ref in zip(g.parameters(), g_ref.parameters()):
+            delta = 0.01 * torch.randn(p_ref.shape, generator=torch.Generator().manual_seed(12))
+            p_ref.add_(delta)
+            p_mine.add_(delta.cuda())               # (in-place: bumps the version counter like optimizer.step())
+    out2 = gg(z.cuda(), clone=True)
+    with torch.no_grad():
+        eager2 = g(z.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out2, eager2) and not torch.equal(out2, out)
+    assert float((out2.cpu() - vo.generate(g_ref, z)).abs().max()) < 3e-2
+    g.train()
+    with pytest.raises(RuntimeError):
+        gg(z.cuda())

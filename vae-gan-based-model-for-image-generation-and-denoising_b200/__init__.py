@@ -5,6 +5,7 @@ Import as `vaegan_b200` (the repo-root shim maps that name onto this directory).
 from ._lib import LIB_PATH, VaeganB200Error, load as load_library  # noqa: F401
 from .modules import (ConvBlock, Decoder, Discriminator, Encoder, Generator, set_default_precision,  # noqa: F401
                       weights_init)
+from .generate import GraphedGenerator  # noqa: F401
 
 __all__ = ["ConvBlock", "Encoder", "Generator", "Decoder", "Discriminator", "weights_init", "set_default_precision",
-           "load_library", "VaeganB200Error", "LIB_PATH"]
+           "GraphedGenerator", "load_library", "VaeganB200Error", "LIB_PATH"]

@@ -309,9 +309,13 @@ static int up_fill_taps(IgemmParams& p, int k, int s, int pad, int big_c) {
 }
 
 // ---------------------------------------------------------------------------------------------- halo tiles
-// Experiment switch VG_HALO=1 (off by default).  Regroups the taps of every phase by the view
-// they read; when all groups have the same size and their shifts span at most 2 pixels, a pipeline stage loads ONE
-// (16 + hy) x (8 + hx) activation tile per group and channel chunk and the group's taps read shifted windows of it.
+// Experiment switch VG_HALO (off by default).  Regroups the taps of every phase by (view, column
+// shift): the taps of a group differ only in their ROW shift, so a pipeline stage loads ONE (16 + hy) x 8 activation tile
+// per group and channel chunk and the group's taps read row-shifted windows of it.  A window starts sy * 8 rows = sy
+// KB into the tile, i.e. on a 1024-byte swizzle-atom boundary: the operand descriptors stay completely standard.
+// (The first variant also shared the tile across COLUMN shifts - windows starting at any 128-byte row, 8-row groups
+// a non-1024 stride apart.  It computes correctly but ran 1.45-1.5x SLOWER on every layer (r2b_fused_VG_HALO_64.log):
+// the tensor core fetches an 8-row group that straddles two swizzle atoms twice.)
 // Needs 128-byte rows (kchunk 64), 16 x 8 output tiles (tb = 1) and an output grid those tiles cover exactly.
 // Returns false and leaves `p` alone when the launch does not qualify; on success the caller rebuilds amap[] with
 // the (halo_w, halo_h, 1) box and re-derives the stage count.
@@ -323,58 +327,57 @@ static bool halo_plan(IgemmParams& p, int grid_w, int grid_h, int batch) {
     const int tpp = p.taps_per_phase;
     if (tpp < 2 || p.num_phases * tpp > 64) return false;
     IgemmTap ordered[64];
-    int16_t org_dy[16], org_dx[16];
-    int shift_y[64], shift_x[64];
-    int gt = -1, groups_total = 0, hy = 0, hx = 0;
+    int16_t org_dy[32], org_dx[32];
+    int shift_y[64];
+    int gt = -1, groups_total = 0, hy = 0;
     for (int ph = 0; ph < p.num_phases; ++ph) {
         const IgemmTap* src = &p.taps[ph * tpp];
         int n_out = 0, groups_here = 0;
         bool used[64] = {};
         for (int first = 0; first < tpp; ++first) {
             if (used[first]) continue;
-            // one group: every not-yet-placed tap of this phase reading the same view, in (dy, dx) order as listed
-            int lo_y = 1 << 20, lo_x = 1 << 20, hi_y = -(1 << 20), hi_x = -(1 << 20), n = 0;
+            // one group: every not-yet-placed tap of this phase reading the same view at the same column shift
+            auto same = [&](int t) { return !used[t] && src[t].view == src[first].view && src[t].dx == src[first].dx; };
+            int lo_y = 1 << 20, hi_y = -(1 << 20), n = 0;
             for (int t = first; t < tpp; ++t)
-                if (!used[t] && src[t].view == src[first].view) {
+                if (same(t)) {
                     lo_y = std::min<int>(lo_y, src[t].dy); hi_y = std::max<int>(hi_y, src[t].dy);
-                    lo_x = std::min<int>(lo_x, src[t].dx); hi_x = std::max<int>(hi_x, src[t].dx);
                     ++n;
                 }
             if (gt < 0) gt = n;
-            if (n != gt || groups_total >= 16) return false;
+            if (n != gt || groups_total >= 32) return false;
+            const int16_t gdx = src[first].dx;
             for (int t = first; t < tpp; ++t)
-                if (!used[t] && src[t].view == src[first].view) {
-                    used[t] = true;
+                if (same(t)) {
                     const int o = ph * tpp + n_out++;
                     ordered[o] = src[t];
                     shift_y[o] = src[t].dy - lo_y;
-                    shift_x[o] = src[t].dx - lo_x;
+                    used[t] = true;
                 }
             org_dy[groups_total] = static_cast<int16_t>(lo_y);
-            org_dx[groups_total] = static_cast<int16_t>(lo_x);
+            org_dx[groups_total] = gdx;
             hy = std::max(hy, hi_y - lo_y);
-            hx = std::max(hx, hi_x - lo_x);
             ++groups_total;
             ++groups_here;
         }
         if (groups_here * gt != tpp) return false;
     }
     // every phase must hold the same number of groups (group index = flat first-tap index / gt)
-    if (gt < 2 || gt > 16 || hy > 2 || hx > 2 || groups_total * gt != p.num_phases * tpp) return false;
-    const int halo_w = 8 + hx, halo_h = 16 + hy, row_bytes = p.kchunk * 2;
-    const int halo_bytes = halo_w * halo_h * row_bytes;
-    const int stage = (halo_bytes + 1023) / 1024 * 1024 + gt * p.n_tile * row_bytes;
+    if (gt < 2 || gt > 16 || hy > 3 || groups_total * gt != p.num_phases * tpp) return false;
+    const int halo_w = 8, halo_h = 16 + hy, row_bytes = p.kchunk * 2;
+    const int halo_bytes = halo_w * halo_h * row_bytes;            // (a multiple of 1024)
+    const int stage = halo_bytes + gt * p.n_tile * row_bytes;
     if (2 * stage + 4096 + epilogue_extra_smem(p) > 220 * 1024) return false;
     for (int i = 0; i < p.num_phases * tpp; ++i) {
         p.taps[i] = ordered[i];
-        p.halo_shift16[i] = static_cast<uint16_t>((shift_y[i] * halo_w + shift_x[i]) * row_bytes / 16);
+        p.halo_shift16[i] = static_cast<uint16_t>(shift_y[i] * halo_w * row_bytes / 16);
     }
     for (int g = 0; g < groups_total; ++g) { p.halo_dy[g] = org_dy[g]; p.halo_dx[g] = org_dx[g]; }
     p.halo = 1;
     p.halo_w = halo_w;
     p.halo_h = halo_h;
     p.halo_bytes = halo_bytes;
-    p.halo_stage_bytes = (halo_bytes + 1023) / 1024 * 1024;
+    p.halo_stage_bytes = halo_bytes;
     p.tps = gt;
     p.b_merged = 0;
     p.tw = 8;

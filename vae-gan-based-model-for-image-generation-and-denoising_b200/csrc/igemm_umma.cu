@@ -173,24 +173,27 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                 int tap_i = it_begin / p.c_chunks * tps, c = it_begin % p.c_chunks;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty[s], par ^ 1);
-                    if (leader) mbar_expect_tx(&full[s], (HALO ? p.halo_bytes : a_stage) + b_stage);
-                    if (HALO) {
-                        // the group's halo tile: origin = the smallest shift of its taps (IgemmParams::halo_dy / dx)
-                        const int gi = (phase * p.taps_per_phase + tap_i) / tps;
-                        if (leader)
+                    // (elect.sync, not `lane == 0`: ptxas then knows exactly one thread runs the block and emits the
+                    // TMA / tcgen05 instructions straight-line instead of one ELECT + BRA.U.ANY loop per instruction)
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s], (HALO ? p.halo_bytes : a_stage) + b_stage);
+                        if (HALO) {
+                            // the group's halo tile: origin = the smallest shift of its taps (IgemmParams::halo_dy / dx)
+                            const int gi = (phase * p.taps_per_phase + tap_i) / tps;
                             tma_load_4d(sA + s * a_stage, &p.amap[taps[tap_i].view], &full[s], c * p.kchunk,
                                         j0 + p.halo_dx[gi], i0 + p.halo_dy[gi], b0);
+                        }
+                        for (int t = 0; t < tps; ++t) {
+                            const IgemmTap tap = taps[tap_i + t];
+                            if (!HALO)
+                                tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
+                                            j0 + tap.dx, i0 + tap.dy, b0);
+                            if (!p.b_merged)
+                                tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
+                        }
+                        if (p.b_merged)
+                            tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, taps[tap_i].brow + n0);
                     }
-                    for (int t = 0; t < tps; ++t) {
-                        const IgemmTap tap = taps[tap_i + t];
-                        if (!HALO && leader)
-                            tma_load_4d(sA + s * a_stage + t * a_sub, &p.amap[tap.view], &full[s], c * p.kchunk,
-                                        j0 + tap.dx, i0 + tap.dy, b0);
-                        if (!p.b_merged && leader)
-                            tma_load_2d(sB + s * b_stage + t * b_sub, &p.bmap, &full[s], c * p.kchunk, tap.brow + n0);
-                    }
-                    if (p.b_merged && leader)
-                        tma_load_2d(sB + s * b_stage, &p.bmap, &full[s], c * p.kchunk, taps[tap_i].brow + n0);
                     __syncwarp();
                     if (++c == p.c_chunks) { c = 0; tap_i += tps; }
                     if (++s == stages) { s = 0; par ^= 1; }
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
             const uint32_t layout = p.kchunk == 64 ? 2u : (p.kchunk == 32 ? 4u : 6u);
             const uint32_t sbo = 8 * row_bytes;
-            const uint32_t sbo_a = HALO ? p.halo_w * row_bytes : sbo;       // halo: one 8-pixel image row per group
+            const uint32_t sbo_a = sbo;     // (halo windows start on swizzle-atom boundaries: standard descriptors)
             const int ksteps = p.kchunk / 16;
             // descriptors of stage 0 / k-step 0; per instruction only the start-address field (lo word) moves
             const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 0, sbo_a, layout);
@@ -229,8 +232,9 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
 #if VG_STAGE_FENCE
                     tc_fence_after();
 #endif
+                    const bool issuer = elect_one();     // (elect.sync: ptxas then KNOWS one thread runs the block)
                     if (HALO) {
-                        if (leader) {
+                        if (issuer) {
                             const uint16_t* sh = &p.halo_shift16[phase * p.taps_per_phase + tap_i];
                             for (int t = 0; t < tps; ++t)
                                 for (int k = 0; k < ksteps; ++k)
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                             umma_commit(&empty[s]);
                         }
                         if (++hc == p.c_chunks) { hc = 0; tap_i += tps; }
-                    } else if (leader) {
+                    } else if (issuer) {
                         if (ksteps == 4) {
                             umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, it != 0);
                             umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                     b_lo += b_step;
                     if (++s == stages) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
                 }
-                if (leader) umma_commit(&tmem_full[acc]);   // (with zero iterations this arrives immediately)
+                if (elect_one()) umma_commit(&tmem_full[acc]);   // (with zero iterations this arrives immediately)
                 __syncwarp();
             }
         }
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
         const int sub_w = r0 % p.tw, sub_h = (r0 / p.tw) % p.th, sub_b = r0 / (p.tw * p.th);
         int slot = 0;
         uint32_t xpar = 0;
-        // prefetch cursor of the saved-tensor boxes (lane 0 only)
+        // prefetch cursor of the saved-tensor boxes (warp-uniform: every lane tracks it, one elected lane issues)
         int pf_item = blockIdx.x, pf_c = c_begin, pf_slot = 0, pf_j = 0, pf_i = 0, pf_b = 0, pf_n0 = 0, pf_phase = 0;
         auto pf_setup = [&]() {
             if (pf_item >= total_items) return;
@@ -302,14 +306,16 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
         };
         auto pf_issue = [&]() {
             if (pf_item >= total_items) return;
-            mbar_expect_tx(&xbar[pf_slot], kSlabBytes);
-            tma_load_4d(sE + (ew * S + pf_slot) * kSlabBytes, &p.xmap[pf_phase], &xbar[pf_slot], pf_n0 + pf_c, pf_j, pf_i,
-                        pf_b);
+            if (elect_one()) {
+                mbar_expect_tx(&xbar[pf_slot], kSlabBytes);
+                tma_load_4d(sE + (ew * S + pf_slot) * kSlabBytes, &p.xmap[pf_phase], &xbar[pf_slot], pf_n0 + pf_c, pf_j,
+                            pf_i, pf_b);
+            }
             if (++pf_slot == S) pf_slot = 0;
             pf_c += c_step;
             if (pf_c >= p.n_tile) { pf_c = c_begin; pf_item += gridDim.x; pf_setup(); }
         };
-        if (xtma && lane == 0) {
+        if (xtma) {
             pf_setup();
             for (int i = 0; i < S - 2; ++i) pf_issue();
         }
@@ -363,11 +369,12 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                 if (tep) {
                     // the slab this chunk uses was last read by the store issued two chunks ago (S = 2) / is about to
                     // be re-filled for the chunk S - 2 ahead: at most the newest store may still be reading
+                    // (bulk async-groups belong to the thread that committed them: lane 0 stores, lane 0 waits)
                     if (lane == 0) {
                         if (S == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
-                        if (xtma) pf_issue();
                     }
                     __syncwarp();
+                    if (xtma) pf_issue();
                     if (xtma) {
                         mbar_wait(&xbar[slot], xpar);
 #pragma unroll
@@ -656,21 +663,21 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 const int j0 = tj * p.tw, i0 = ti * p.th, b0 = tb_i * p.tb;
                 WGRAD_WAIT(&empty_a[sa], par_a ^ 1);
                 TR_ADD(2);
-                if (PAIR) {
-                    // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
-                    if (rank == 0 && leader) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
-                    for (int a = 0; a < p.m_atoms; ++a)
-                        if (leader)
+                if (elect_one()) {     // (elect.sync: straight-line TMA issue, see igemm_fprop_kernel)
+                    if (PAIR) {
+                        // CTA 0's barrier counts the bytes of both CTAs; each CTA's data lands in its own shared memory
+                        if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * p.m_atoms * p_atom_bytes);
+                        for (int a = 0; a < p.m_atoms; ++a)
                             tma_load_4d_pair(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa],
                                              m0 + a * p.p_atom_c, j0, i0, b0);
-                } else if (WGRAD_DBG(p, 8)) {
-                    if (leader) mbar_arrive(&full_a[sa]);
-                } else {
-                    if (leader) mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
-                    for (int a = 0; a < p.m_atoms; ++a)
-                        if (leader)
+                    } else if (WGRAD_DBG(p, 8)) {
+                        mbar_arrive(&full_a[sa]);
+                    } else {
+                        mbar_expect_tx(&full_a[sa], p.m_atoms * p_atom_bytes);
+                        for (int a = 0; a < p.m_atoms; ++a)
                             tma_load_4d(sA + sa * a_stage + a * p_atom_bytes, &p.pmap, &full_a[sa], m0 + a * p.p_atom_c,
                                         j0, i0, b0);
+                    }
                 }
                 __syncwarp();
                 TR_ADD(3);
@@ -678,28 +685,28 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                     const int cnt = min(merge, ntap - tl);
                     WGRAD_WAIT(&empty_b[sb], par_b ^ 1);
                     TR_ADD(0);
-                    if (PAIR) {
-                        // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
-                        const int half = cnt * n_atoms / 2;
-                        if (rank == 0 && leader) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
-                        for (int h = 0; h < half; ++h) {
-                            const int idx = static_cast<int>(rank) * half + h;
-                            const int j = idx / n_atoms, a = idx - j * n_atoms;
-                            const IgemmTap tap = p.taps[tap0 + tl + j];
-                            if (leader)
+                    if (elect_one()) {
+                        if (PAIR) {
+                            // this CTA's half of the stage's Q atoms (atom index = tap_local * n_atoms + atom)
+                            const int half = cnt * n_atoms / 2;
+                            if (rank == 0) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                            for (int h = 0; h < half; ++h) {
+                                const int idx = static_cast<int>(rank) * half + h;
+                                const int j = idx / n_atoms, a = idx - j * n_atoms;
+                                const IgemmTap tap = p.taps[tap0 + tl + j];
                                 tma_load_4d_pair(sB + sb * b_stage + h * q_atom_bytes, &p.qmap[tap.view], &full_b[sb],
                                                  n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
-                        }
-                    } else if (WGRAD_DBG(p, 8)) {
-                        if (leader) mbar_arrive(&full_b[sb]);
-                    } else {
-                        if (leader) mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
-                        for (int j = 0; j < cnt; ++j) {
-                            const IgemmTap tap = p.taps[tap0 + tl + j];
-                            for (int a = 0; a < n_atoms; ++a)
-                                if (leader)
+                            }
+                        } else if (WGRAD_DBG(p, 8)) {
+                            mbar_arrive(&full_b[sb]);
+                        } else {
+                            mbar_expect_tx(&full_b[sb], cnt * tap_bytes);
+                            for (int j = 0; j < cnt; ++j) {
+                                const IgemmTap tap = p.taps[tap0 + tl + j];
+                                for (int a = 0; a < n_atoms; ++a)
                                     tma_load_4d(sB + sb * b_stage + j * tap_bytes + a * q_atom_bytes, &p.qmap[tap.view],
                                                 &full_b[sb], n0 + a * p.q_atom_c, j0 + tap.dx, i0 + tap.dy, b0);
+                            }
                         }
                     }
                     __syncwarp();
@@ -744,8 +751,8 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                     tc_fence_after();
 #endif
                     TR_ADD(4);
-                    if (!leader) {
-                        // (only lane 0 issues; the other lanes follow the ring with it)
+                    if (!elect_one()) {
+                        // (one elected lane issues; the other lanes follow the ring with it)
                     } else if (PAIR) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_pair_bf16_lohi(d_tmem, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, acc | (k != 0));
@@ -776,7 +783,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                     if (++sb == SB) { sb = 0; par_b ^= 1; b_lo = b_lo0; }
                     TR_ADD(6);
                 }
-                if (leader) {
+                if (elect_one()) {
                     if (PAIR) umma_commit_pair(&empty_a[sa]);
                     else if (WGRAD_DBG(p, 4)) mbar_arrive(&empty_a[sa]);
                     else umma_commit(&empty_a[sa]);
@@ -785,7 +792,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
                 a_lo += a_step;
                 if (++sa == SA) { sa = 0; par_a ^= 1; a_lo = a_lo0; }
             }
-            if (leader) {
+            if (elect_one()) {
                 if (PAIR) umma_commit_pair(tmem_full);
                 else umma_commit(tmem_full);
             }

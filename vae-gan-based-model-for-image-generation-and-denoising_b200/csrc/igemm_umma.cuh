@@ -83,7 +83,7 @@ struct alignas(64) IgemmParams {
     int halo_w, halo_h;          // tw + hx, th + hy: the TMA box of amap[] in this mode
     int halo_bytes;              // halo_w * halo_h * kchunk * 2: what one activation load delivers
     int halo_stage_bytes;        // the same rounded up to the swizzle period (1024 B)
-    int16_t halo_dy[16], halo_dx[16];   // per group: origin of the halo tile relative to the output tile's (i0, j0)
+    int16_t halo_dy[32], halo_dx[32];   // per group: origin of the halo tile relative to the output tile's (i0, j0)
     uint16_t halo_shift16[64];   // per tap (index as taps[]): (sy * halo_w + sx) * row_bytes / 16, the window's start
 };
 
