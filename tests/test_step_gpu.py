@@ -144,3 +144,41 @@ def test_graph_replay_equals_eager_and_device_noise_runs():
     l2 = {k: float(v) for k, v in sb.step(real, 50).items()}
     assert all(np.isfinite(v) for v in l1.values()) and all(np.isfinite(v) for v in l2.values())
     assert l1["total"] != l2["total"]
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_prefetched_host_batch_is_the_same_step(u8):
+    """VAEGANStep.prefetch(): the next batch's host -> device copy runs on a copy stream under the current step; the
+    step that consumes it sees exactly the data a plain step(host_tensor) would have copied itself - including when
+    the staged buffer is refilled for the following batch right after the launch."""
+    from oracle import vaegan_oracle as vo
+    hw, nz, batch = 64, 128, 8
+    _, nets_a = make_pair(hw, nz, "fp32")
+    _, nets_b = make_pair(hw, nz, "fp32")
+    sa, sb = _step_cls()(*nets_a, use_cuda_graph=True), _step_cls()(*nets_b, use_cuda_graph=True)
+    gen = torch.Generator().manual_seed(77)
+    if u8:
+        batches = [torch.randint(0, 256, (batch, hw, hw, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(3)]
+    else:
+        batches = [(torch.rand(batch, 3, hw, hw, generator=gen) * 2 - 1).pin_memory() for _ in range(3)]
+    noise = [tuple(t.cuda() for t in vo.make_inputs(batch, hw, nz, seed=60 + i)[1:]) for i in range(3)]
+    sa.prefetch(batches[0])
+    for i in range(3):
+        la = sa.step(batches[i], 50, *noise[i])
+        if i + 1 < 3:
+            sa.prefetch(batches[i + 1])                 # refills the staging buffer while step i runs
+        lb = sb.step(batches[i], 50, *noise[i])
+        torch.cuda.synchronize()
+        assert torch.equal(sa._static["real"], sb._static["real"]), i
+        # (the input data above is compared bit for bit; the losses of later steps follow Adam updates whose first
+        # moves are ~lr * sign(g) with fp32-atomic noise in g - two runs of the SAME step drift apart by ~1e-4)
+        tol = 1e-5 if i == 0 else 2e-3
+        for k in ("d_loss_0", "recon", "kl"):
+            assert abs(float(la[k]) - float(lb[k])) <= tol * abs(float(lb[k])) + 1e-7, (i, k)
+    # a different tensor than the prefetched one falls back to the direct copy
+    other = batches[0].clone().pin_memory()
+    sa.prefetch(batches[1])
+    sa.step(other, 50, *noise[0])
+    sb.step(other, 50, *noise[0])
+    torch.cuda.synchronize()
+    assert torch.equal(sa._static["real"], sb._static["real"])

@@ -65,8 +65,12 @@ class BucketedAllReduce:
     """
 
     def __init__(self, flat: torch.Tensor, offsets: Sequence[int], sizes: Sequence[int], group=None,
-                 bucket_bytes: int = 8 << 20, comm_stream: Optional["torch.cuda.Stream"] = None):
+                 bucket_bytes: int = 8 << 20, comm_stream: Optional["torch.cuda.Stream"] = None,
+                 producer_streams: Sequence["torch.cuda.Stream"] = ()):
+        """`producer_streams`: side streams that also write gradients into `flat` (the fused step issues its weight
+        gradients there); a bucket's all-reduce waits for them as well as for the current stream."""
         self.flat = flat
+        self.producer_streams = list(producer_streams)
         self.group = group
         self.buckets = plan_buckets(offsets, sizes, bucket_bytes, flat.element_size())
         self.owner = {}
@@ -91,6 +95,8 @@ class BucketedAllReduce:
         view = self.flat[b.lo:b.hi]
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())     # gradients of this bucket are complete
+            for st in self.producer_streams:
+                self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, group=self.group)
         else:
@@ -98,6 +104,8 @@ class BucketedAllReduce:
 
     def mark_ready(self, param_index: int):
         b_idx = self.owner[param_index]
+        if self.launched[b_idx]:
+            return
         self.pending[b_idx] -= 1
         if self.pending[b_idx] == 0 and not self.launched[b_idx]:
             self._launch(b_idx)

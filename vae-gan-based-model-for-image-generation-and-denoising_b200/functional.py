@@ -408,6 +408,32 @@ class WgradOverlap:
         cls.streams = []
 
 
+class GradReady:
+    """Data parallelism hook: the fused step registers, per parameter, a callable that is invoked once the kernels
+    producing that parameter's gradient have all been ISSUED (end of its layer's backward; weight gradients may still
+    be running on a WgradOverlap side stream - the callee waits for those streams).  dp.BucketedAllReduce.mark_ready
+    is what gets registered: a bucket's all-reduce starts under the rest of the backward pass."""
+    handlers: dict = {}
+
+    @classmethod
+    def set(cls, handlers: dict):
+        cls.handlers = handlers
+
+    @classmethod
+    def clear(cls):
+        cls.handlers = {}
+
+    @classmethod
+    def notify(cls, *params):
+        if not cls.handlers:
+            return
+        for p in params:
+            if p is not None:
+                h = cls.handlers.get(id(p))
+                if h is not None:
+                    h()
+
+
 # --------------------------------------------------------------------------------------------- space-to-depth layers
 def is_image_s2d(t: torch.Tensor, true_channels: int) -> bool:
     """An image-side activation (true_channels < 16) is either channel-padded to 16 or in space-to-depth form (64)."""
@@ -886,6 +912,7 @@ class ConvLayerFn(torch.autograd.Function):
             dx = conv_up(d_raw, w_bwd, g, ep=ep) if spec.kind == "down" else conv_down(d_raw, w_bwd, g, ep=ep)
             if ep is not None:
                 link_in.sums, link_in.fused = sums, True
+        GradReady.notify(weight, bias, gamma, beta)
         return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
                 _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
                 None, None, None, None, None, None, None, None, None, None, None)

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
+from .dp import BucketedAllReduce
 from ._lib import ACT_TANH, call
 from .functional import _p, _stream
 
@@ -40,6 +41,7 @@ class _FlatAdam:
             total += (p.numel() + 3) // 4 * 4        # keep every view 16-byte aligned
         self.n = total
         self.offsets, self.sizes, self.shapes = offs, [p.numel() for p in params], [tuple(p.shape) for p in params]
+        self.param_ids = [id(p) for p in params]
         self.params = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -96,14 +98,8 @@ class _ReparamFn(torch.autograd.Function):
         ctx.save_for_backward(mu, logvar, eps, kl_weight_dev)
         return z
 
-    # called (once) when the gradient w.r.t. z arrives, i.e. when the generator's backward pass has been issued
-    on_generator_done = None
-
     @staticmethod
     def backward(ctx, dz):
-        cb, _ReparamFn.on_generator_done = _ReparamFn.on_generator_done, None
-        if cb is not None:
-            cb()
         mu, logvar, eps, klw = ctx.saved_tensors
         B, nz = mu.shape
         dmu, dlv = torch.empty_like(mu), torch.empty_like(logvar)
@@ -139,7 +135,7 @@ class VAEGANStep:
                  alpha_kl: float = 0.1, alpha_adv: float = 0.1, kl_warmup_epochs: int = 50, sigma_inst: float = 0.05,
                  denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
                  process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True,
-                 capture_grads: bool = False):
+                 capture_grads: bool = False, bucket_bytes: Optional[Dict[str, int]] = None):
         self.E, self.G, self.D = encoder, decoder, discriminator
         self.dtype = encoder._dtype()
         self.dev = next(encoder.parameters()).device
@@ -177,12 +173,24 @@ class VAEGANStep:
         # side streams (parallel branches of the captured graph): weight gradients round-robin, plus the start-of-step
         # weight packing and noise generation that the encoder's forward pass does not wait for
         self.wgrad_streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)] if overlap_wgrad else []
-        # data parallel: the generator's gradient all-reduce (the largest message) starts as soon as its backward has
-        # been issued and runs under the encoder's backward pass on its own stream
-        self.comm_stream = torch.cuda.Stream(device=self.dev) if (overlap_wgrad and self.world > 1) else None
-        self._g_reduced = False
+        # data parallel (world > 1): bucketed gradient all-reduce on a communication stream, launched from INSIDE the
+        # backward passes - a bucket goes out as soon as the kernels producing its gradients have been issued
+        # (functional.GradReady, reverse parameter order) and runs under the rest of the backward pass.  The
+        # discriminator's 256->512 weight (76 % of its bytes) is ready first and travels under its remaining
+        # dgrad / wgrad launches; the generator's 53 MB leave in three buckets under its own and the encoder's backward.
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        bb = dict(E=2 << 20, G=8 << 20, D=4 << 20)
+        bb.update(bucket_bytes or {})
+        self.buckets = {}
+        if self.world > 1:
+            for key, opt in (("E", self.opt_E), ("G", self.opt_G), ("D", self.opt_D)):
+                padded = [(n + 3) // 4 * 4 for n in opt.sizes]
+                self.buckets[key] = BucketedAllReduce(opt.grads, opt.offsets, padded, process_group, bb[key],
+                                                      self.comm_stream, self.wgrad_streams)
         self._graph = None
         self._static = None
+        self._copy_stream = None            # prefetch(): host -> device copies of the next batch
+        self._prefetched = None
         self.launches_per_step = None
         for net in (encoder, decoder, discriminator):
             net.train()
@@ -206,10 +214,6 @@ class VAEGANStep:
         # (Philox stream = 16 * rank + tensor id: data-parallel replicas draw different noise from the same seed)
         call("vg_randn", _p(t), t.numel(), ctypes.c_ulonglong(self.seed), _p(self._static["rng_offset"]),
              ctypes.c_ulonglong(16 * self.rank + stream_id), _stream())
-
-    def _allreduce(self, opt: _FlatAdam):
-        if self.world > 1:
-            torch.distributed.all_reduce(opt.grads, group=self.pg)
 
     # ------------------------------------------------------------------------------------------ the schedule
     def _run(self, gen_noise: bool):
@@ -291,11 +295,17 @@ class VAEGANStep:
             slot = loss[it:it + 1] if it < 2 else None
             call("vg_bce", _p(p_pair[:B]), B, self.real_label, 1.0, _p(slot), 0, _p(dp[:B]), _stream())
             call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
-            torch.autograd.backward([p_pair], [dp])
+            self._arm_buckets("D")
+            try:
+                torch.autograd.backward([p_pair], [dp])
+            finally:
+                F_.GradReady.clear()
             F_.WgradOverlap.join()
-            if self.capture_grads:
+            if self.capture_grads and self.world == 1:
                 self._d_grad_copies[it].copy_(self.opt_D.grads)
-            self._allreduce(self.opt_D)
+            self._finish_buckets("D")
+            if self.capture_grads and self.world > 1:
+                self._d_grad_copies[it].copy_(self.opt_D.grads)
             self.opt_D.step(1.0 / self.world)
             D.repack_weights()
 
@@ -305,41 +315,42 @@ class VAEGANStep:
         d_params = list(D.parameters())
         for p in d_params:             # weight gradients of D are never used in this phase (reference discards them)
             p.requires_grad_(False)
-        self._g_reduced = False
-        if self.comm_stream is not None:
-            _ReparamFn.on_generator_done = self._reduce_generator_early
+        self._arm_buckets("E", "G")
         try:
             p_fake = D.forward_nhwc(recon_noisy)
             call("vg_bce", _p(p_fake), B, self.real_label, self.alpha_adv, _p(loss[4:5]), 0, _p(s["dp_a"]), _stream())
             torch.autograd.backward([p_fake], [s["dp_a"]])
         finally:
-            _ReparamFn.on_generator_done = None
+            F_.GradReady.clear()
             for p in d_params:
                 p.requires_grad_(True)
         call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
              _p(loss[5:6]), _stream())
         F_.WgradOverlap.join()
-        self._allreduce(self.opt_E)
-        if self._g_reduced:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        else:
-            self._allreduce(self.opt_G)
+        self._finish_buckets("G", "E")
         self.opt_E.step(1.0 / self.world)
         self.opt_G.step(1.0 / self.world)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
 
-    def _reduce_generator_early(self):
-        """Runs inside the backward pass when dL/dz reaches the reparameterisation: every generator kernel (dgrad
-        chain on this stream, weight gradients on the side streams) has been issued and the encoder's backward is
-        still to come - the generator's gradient all-reduce goes to its own stream behind all of those.  (Its Adam
-        stays at the end of the step: launched here it saturates HBM and delays the encoder's chain of small kernels.)"""
-        comm, cur = self.comm_stream, torch.cuda.current_stream()
-        comm.wait_stream(cur)
-        for st in self.wgrad_streams:
-            comm.wait_stream(st)
-        with torch.cuda.stream(comm):
-            self._allreduce(self.opt_G)
-        self._g_reduced = True
+    def _arm_buckets(self, *keys):
+        """Register dp.BucketedAllReduce.mark_ready for every parameter of the named networks: the layer backward
+        that has just issued a parameter's gradient kernels calls it (functional.GradReady)."""
+        if self.world == 1:
+            return
+        handlers = {}
+        for key in keys:
+            opt, bk = {"E": self.opt_E, "G": self.opt_G, "D": self.opt_D}[key], self.buckets[key]
+            bk.reset()
+            for i, pid in enumerate(opt.param_ids):
+                handlers[pid] = (lambda bk=bk, i=i: bk.mark_ready(i))
+        F_.GradReady.set(handlers)
+
+    def _finish_buckets(self, *keys):
+        """Launch what the backward pass did not trigger and make the current stream wait for the communication."""
+        if self.world == 1:
+            return
+        for key in keys:
+            self.buckets[key].finish()
 
     # ------------------------------------------------------------------------------------------ public API
     def step(self, real: torch.Tensor, epoch: int, eps: Optional[torch.Tensor] = None,
@@ -364,13 +375,19 @@ class VAEGANStep:
             self._static["rng_offset"].fill_(old_rng)
             self._graph = None
         s = self._static
+        staged = self._take_prefetched(real)
         if u8:
-            if s.get("real_u8") is None or s["real_u8"].shape != real.shape:
-                s["real_u8"] = torch.empty(real.shape, dtype=torch.uint8, device=self.dev)
-            s["real_u8"].copy_(real, non_blocking=True)
-            call("vg_u8_nhwc_to_nchw", _p(s["real_u8"]), _p(s["real"]), batch, 3, hw, hw, 0.5, 0.5, _stream())
+            src = staged
+            if src is None:
+                if s.get("real_u8") is None or s["real_u8"].shape != real.shape:
+                    s["real_u8"] = torch.empty(real.shape, dtype=torch.uint8, device=self.dev)
+                s["real_u8"].copy_(real, non_blocking=True)
+                src = s["real_u8"]
+            call("vg_u8_nhwc_to_nchw", _p(src), _p(s["real"]), batch, 3, hw, hw, 0.5, 0.5, _stream())
         else:
-            s["real"].copy_(real, non_blocking=True)
+            s["real"].copy_(real if staged is None else staged, non_blocking=True)
+        if staged is not None:
+            self._prefetched[3].record(torch.cuda.current_stream())    # the staging buffer may be refilled after this
         s["kl_w"].fill_(self.alpha_kl * min(1.0, epoch / self.kl_warmup) if self.kl_warmup > 0 else self.alpha_kl)
         if injected:
             s["eps"].copy_(eps, non_blocking=True)
@@ -412,6 +429,38 @@ class VAEGANStep:
         self.E.invalidate_packed_weights()
         self.G.invalidate_packed_weights()
         return {k: s["losses"][i] for i, k in enumerate(LOSS_KEYS)}
+
+    # ------------------------------------------------------------------------------------------ input prefetch
+    def prefetch(self, real: torch.Tensor) -> None:
+        """Start the host -> device copy of the NEXT step's batch (pinned host tensor) on a copy stream, so that it
+        runs under the step that is executing now; the next `step(real)` called with this same tensor picks the
+        staged copy up (a device-to-device move of ~12 MB) instead of copying from the host on the compute stream.
+        The data loader's double buffering (DataLoader(pin_memory=True) + non_blocking copies, main_vae.py:204-209)."""
+        if real.device.type != "cpu":
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        prev = self._prefetched
+        if prev is not None and prev[1].shape == real.shape and prev[1].dtype == real.dtype:
+            stage, ready, consumed = prev[1], prev[2], prev[3]
+        else:
+            stage = torch.empty(real.shape, dtype=real.dtype, device=self.dev)
+            ready, consumed = torch.cuda.Event(), torch.cuda.Event()
+            consumed.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(consumed)          # the previous consumer of the staging buffer has read it
+        with torch.cuda.stream(self._copy_stream):
+            stage.copy_(real, non_blocking=True)
+            ready.record(self._copy_stream)
+        self._prefetched = ((real.data_ptr(), tuple(real.shape), real.dtype, real._version), stage, ready, consumed)
+
+    def _take_prefetched(self, real: torch.Tensor):
+        pf = self._prefetched
+        if pf is None or real.device.type != "cpu":
+            return None
+        if pf[0] != (real.data_ptr(), tuple(real.shape), real.dtype, real._version):
+            return None
+        torch.cuda.current_stream().wait_event(pf[2])
+        return pf[1]
 
     # state save / restore so that warm-up + capture do not advance training
     def _save_state(self):
