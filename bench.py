@@ -256,9 +256,9 @@ def run_gpu_arm(args):
     e2e_u8_value = world * B * args.steps / float(t)
 
     extra = None
+    del step, losses
+    torch.cuda.empty_cache()
     if not args.no_extra:
-        del step
-        torch.cuda.empty_cache()
         extra = _extra_configs(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, min(args.steps, 10))
 
     if rank != 0:
@@ -431,12 +431,28 @@ def _extra_configs(torch, dist, vb, VAEGANStep, dev, rank, world, barrier, steps
 
 
 def _finish(world: int):
-    """Leave without tearing the NCCL communicator down: destroy_process_group() after NCCL collectives were captured
-    into a CUDA graph was observed to hang on this stack; the processes are about to exit anyway."""
-    if world > 1:
-        sys.stdout.flush()
+    """Tear the NCCL communicator down.  destroy_process_group() hangs while a CUDA graph that holds captured NCCL
+    kernels is alive (scripts/nccl_teardown_probe.py: > 30 s with the graph, 0.7 s once it is released), so every
+    VAEGANStep - and with it its graph - is dropped first.  A watchdog still ends the process if teardown stalls."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+
+    def bail():
+        time.sleep(60)
+        sys.stderr.write("bench.py: NCCL teardown stalled for 60 s, exiting without it\n")
         sys.stderr.flush()
         os._exit(0)
+
+    threading.Thread(target=bail, daemon=True).start()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
 
 
 def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):

@@ -255,6 +255,18 @@ int vg_bce(const float* p, int n, float target, float weight, float* loss_out, i
 size_t vg_mse_workspace_bytes(void);
 int vg_mse(const float* a, const float* b, long long n, float weight, const float* grad_in, float* grad_out,
            float* loss_out, void* ws, size_t ws_bytes, void* stream);
+/* One launch per discriminator update (vaegan_code.py:99-101): p[2n] holds D(real) then D(fake);
+ * loss_out = BCE(p[:n], target_real) + BCE(p[n:], target_fake), dp[2n] = weight * d(loss)/dp (may be NULL). */
+int vg_bce_pair(const float* p, int n, float target_real, float target_fake, float weight, float* loss_out, float* dp,
+                void* stream);
+/* One launch for vaegan_code.py:113 + :117: loss_out = weight * MSE(a, b) (fp32 NCHW pixels, or bf16 NHWC discriminator
+ * features for the Dis_l reconstruction term of README.md:11-14), grad_out = weight*2(a-b)/n (+ grad_in) in the
+ * element type, and - written by the block that finishes last - total_out = loss + *w_kl_dev * *kl + w_adv * *adv
+ * (NULL pointers contribute 0; total_out may be NULL).  ws: vg_mse_workspace_bytes() bytes, zeroed once by the caller;
+ * the kernel re-arms it. */
+int vg_mse_total(const void* a, const void* b, VgDType dt, long long n, float weight, const void* grad_in,
+                 void* grad_out, float* loss_out, const float* kl, const float* adv, const float* w_kl_dev, float w_adv,
+                 float* total_out, void* ws, size_t ws_bytes, void* stream);
 /* total = recon + w_kl*kl + w_adv*adv  (vaegan_code.py:117); w_kl read from the device if w_kl_dev != NULL. */
 int vg_total_loss(const float* recon, const float* kl, const float* adv, const float* w_kl_dev, float w_kl,
                   float w_adv, float* total, void* stream);

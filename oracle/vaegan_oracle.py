@@ -132,6 +132,13 @@ def make_discriminator(ndf: int = 64, nc: int = 3, hw: int = 256) -> nn.Module:
     return _Seq(layers, flatten_out=True)
 
 
+def conv_group_end(main: nn.Sequential, group: int) -> int:
+    """Index into `main` just past conv group `group` (conv [+ BatchNorm] + activation); negative = from the end."""
+    starts = [i for i, m in enumerate(main) if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))]
+    group = group % len(starts)
+    return starts[group + 1] if group + 1 < len(starts) else len(main)
+
+
 def weights_init(m: nn.Module) -> None:
     """gan_code.py:91-97."""
     name = m.__class__.__name__
@@ -191,8 +198,14 @@ class StepResult:
 
 def reference_step(enc, gen, dis, opt_e, opt_g, opt_d, real, epoch: int, eps, n_real, n_fake, *, n_dis: int = 2,
                    alpha_kl: float = 0.1, alpha_adv: float = 0.1, sigma_inst: float = 0.05,
-                   denoise_sigma: float = 0.0, n_denoise=None, keep_grads: bool = True) -> StepResult:
+                   denoise_sigma: float = 0.0, n_denoise=None, keep_grads: bool = True,
+                   recon_mode: str = "pixel", dis_layer: int = -2) -> StepResult:
     """One iteration of the hot loop, vaegan_code.py:66-135.  Line numbers refer to that file.
+
+    `recon_mode="dis_l"` replaces the pixel MSE of :113 by the feature-matching term the reference's README.md:11-14
+    (eq. 2, Larsen et al.) describes but vaegan_code.py does not implement: MSE between the discriminator's
+    `dis_layer`-th conv-group activations of recon_noisy and (detached) of real_noisy.  PARITY UNPINNED: there is no
+    reference code for this mode, the restatement below is the definition both sides of the test share.
 
     `denoise_sigma` > 0 is BASELINE.json config 3: the encoder sees clamp(real + sigma*n_denoise, -1, 1)
     (pattern of main_vae.py:104-105 / vaegan_code.py:153-154); the reconstruction target stays `real`.
@@ -228,8 +241,16 @@ def reference_step(enc, gen, dis, opt_e, opt_g, opt_d, real, epoch: int, eps, n_
         opt_d.step()                                     # :105
         res.losses[f"d_loss_{it}"] = float(d_loss.item())
 
-    fake_out = dis(recon_noisy)                          # :110
-    recon_loss = mse(recon, real)                        # :113
+    if recon_mode == "dis_l":
+        cut = conv_group_end(dis.main, dis_layer)
+        with torch.no_grad():
+            feat_real = dis.main[:cut](real_noisy)       # Dis_l(x): train-mode call, its own BatchNorm statistics
+        feat_fake = dis.main[:cut](recon_noisy)          # Dis_l(x~)
+        fake_out = dis.main[cut:](feat_fake).view(-1)    # :110 continues from the tapped features
+        recon_loss = mse(feat_fake, feat_real)           # README.md eq. (2)
+    else:
+        fake_out = dis(recon_noisy)                      # :110
+        recon_loss = mse(recon, real)                    # :113
     kl_loss = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp()) / batch   # :114
     g_adv = bce(fake_out, real_labels)                   # :115
     total = recon_loss + alpha_kl * min(1.0, epoch / 50) * kl_loss + alpha_adv * g_adv   # :117

@@ -420,6 +420,36 @@ def test_reparam_kl_bce_mse_against_torch():
     assert abs(float(loss) - float(l_ref)) < 1e-6 * abs(float(l_ref))
     assert rel_err(go, ar.grad + gi) < 1e-6
 
+    # one launch per discriminator update: BCE(real) + BCE(fake) of the stacked vector, both gradient seeds
+    pp = torch.cat([p, p.flip(0)])
+    pr = pp.clone().requires_grad_(True)
+    l_ref = F.binary_cross_entropy(pr[:B], torch.full((B,), 0.9)) + F.binary_cross_entropy(pr[B:], torch.full((B,), 0.1))
+    l_ref.backward()
+    loss, dp = torch.zeros((), device="cuda"), torch.empty(2 * B, device="cuda")
+    assert lib.vg_bce_pair(P(pp.cuda()), B, 0.9, 0.1, 1.0, P(loss), P(dp), None) == 0
+    assert abs(float(loss) - float(l_ref)) < 1e-5 * abs(float(l_ref))
+    ok = torch.ones(2 * B, dtype=torch.bool)
+    ok[[0, 1, 2 * B - 1, 2 * B - 2]] = False             # p = 0 / 1: the clamped logs have no finite torch gradient
+    assert rel_err(dp.cpu()[ok], pr.grad[ok]) < 1e-5
+
+    # MSE + gradient + the step's total in one launch (vaegan_code.py:113 + :117), fp32 pixels and bf16 features;
+    # called twice on the same workspace: the kernel re-arms it
+    ws = torch.zeros(lib.vg_mse_workspace_bytes() // 4, device="cuda")
+    kl, adv, wkl = (torch.tensor(v, device="cuda") for v in (15.5, 2.25, 0.07))
+    for dt, code in ((torch.float32, 0), (torch.bfloat16, 1)):
+        a2, b2, g2 = (torch.randn(4, 3, 16, 24, generator=gen).to(dt) for _ in range(3))
+        ar = a2.float().requires_grad_(True)
+        l_ref = F.mse_loss(ar, b2.float())
+        l_ref.backward()
+        for _ in range(2):
+            loss, tot = torch.zeros((), device="cuda"), torch.zeros((), device="cuda")
+            go = torch.empty(a2.shape, device="cuda", dtype=dt)
+            assert lib.vg_mse_total(P(a2.cuda()), P(b2.cuda()), code, a2.numel(), 1.0, P(g2.cuda()), P(go), P(loss), P(kl),
+                                    P(adv), P(wkl), 0.1, P(tot), P(ws), ws.numel() * 4, None) == 0
+            assert abs(float(loss) - float(l_ref)) < 1e-6 * abs(float(l_ref))
+            assert abs(float(tot) - (float(l_ref) + 0.07 * 15.5 + 0.1 * 2.25)) < 1e-6 * float(tot)
+            assert rel_err(go, ar.grad + g2.float()) < (1e-6 if dt == torch.float32 else 8e-3)
+
 
 def test_adam_matches_torch_optim():
     lib = __import__("vaegan_b200").load_library()

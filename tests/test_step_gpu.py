@@ -94,6 +94,31 @@ def test_fused_step_fp32_matches_reference_golden(name):
                 assert int(v) == int(fx[f"bn/{n}.{k}"])
 
 
+@pytest.mark.parametrize("precision,layer", [("fp32", -2), ("fp32", 1), ("bf16", -2)])
+def test_fused_step_dis_l_feature_matching(precision, layer):
+    """Dis_l reconstruction term (README.md eq. 2; no reference code - PARITY UNPINNED): the fused step against the
+    oracle's restatement.  fp32 1e-4 on the losses, bf16 the north-star 2e-2 (5e-2 after the discriminator's Adam
+    steps, as in the pixel mode); the encoder / generator gradients flow only through the tap, so they are checked."""
+    from oracle import vaegan_oracle as vo
+    from tests.util import cosine
+    hw, nz, batch, epoch = 64, 128, 16, 50
+    o_nets, nets = make_pair(hw, nz, precision)
+    real, eps, n_real, n_fake = vo.make_inputs(batch, hw, nz)
+    res_o = vo.reference_step(*o_nets, *vo.make_optimizers(*o_nets), real, epoch, eps, n_real, n_fake,
+                              recon_mode="dis_l", dis_layer=layer)
+    step = _step_cls()(*nets, use_cuda_graph=(precision == "bf16"), recon_mode="dis_l", dis_layer=layer)
+    losses = step.step(real.cuda(), epoch, eps.cuda(), n_real.cuda(), n_fake.cuda())
+    torch.cuda.synchronize()
+    for k, v in res_o.losses.items():
+        tol = 1e-4 if precision == "fp32" else (2e-2 if k in ("d_loss_0", "kl") else 5e-2)
+        assert abs(float(losses[k]) - v) <= tol * abs(v) + 1e-6, (k, float(losses[k]), v)
+    grads = step.gradients()
+    for name, want in (("G", res_o.g_grads), ("E", res_o.e_grads)):
+        flat_g = torch.cat([grads[name][k].flatten().cpu() for k in want])
+        flat_o = torch.cat([want[k].flatten() for k in want])
+        assert cosine(flat_g, flat_o) > (0.9999 if precision == "fp32" else 0.99), (name, cosine(flat_g, flat_o))
+
+
 def test_fused_step_bf16_losses_and_trajectory():
     """bf16 tensor-core mode: losses of a step from IDENTICAL state within 2e-2 relative of the fp32 oracle
     (north_star tolerance); the following steps start from states that already differ by bf16 rounding (and by Adam's

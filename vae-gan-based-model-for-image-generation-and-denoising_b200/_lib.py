@@ -85,6 +85,8 @@ PROTOTYPES = {
     "vg_bce": (c_int, [_P, c_int, c_float, c_float, _P, c_int, _P, _P]),
     "vg_mse_workspace_bytes": (c_size_t, []),
     "vg_mse": (c_int, [_P, _P, c_longlong, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "vg_bce_pair": (c_int, [_P, c_int, c_float, c_float, c_float, _P, _P, _P]),
+    "vg_mse_total": (c_int, [_P, _P, c_int, c_longlong, c_float, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, _P]),
     "vg_total_loss": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P]),
     "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_double, c_double, c_double, c_double, _P, c_float, _P]),
     "vg_randn": (c_int, [_P, c_longlong, c_ulonglong, _P, c_ulonglong, _P]),

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "vec.cuh"
 
 namespace vg {
 namespace {
@@ -153,6 +154,84 @@ __global__ void mse_finalize_kernel(const double* partial, int blocks, long long
     if (threadIdx.x == 0) *loss_out = static_cast<float>(tot / static_cast<double>(n));
 }
 
+// ---- one launch per discriminator update: BCE(D(real), real_label) + BCE(D(fake), fake_label) of the stacked
+// probability vector p[2n] (real half first), both gradient seeds, the summed loss (vaegan_code.py:99-101)
+__global__ void __launch_bounds__(1024) bce_pair_kernel(const float* __restrict__ p, int n, float t_real, float t_fake,
+                                                       float weight, float* __restrict__ loss_out,
+                                                       float* __restrict__ dp) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        const float target = i < n ? t_real : t_fake;
+        const float pi = p[i];
+        const float l1 = fmaxf(logf(pi), -100.f), l0 = fmaxf(log1pf(-pi), -100.f);
+        acc += static_cast<double>(-(target * l1 + (1.f - target) * l0));
+        if (dp != nullptr) dp[i] = weight / n * (pi - target) / fmaxf((1.f - pi) * pi, 1e-12f);
+    }
+    const double tot = block_sum(acc, red);      // (each half is a mean over n: the sum of both means = tot / n)
+    if (threadIdx.x == 0 && loss_out != nullptr) *loss_out = static_cast<float>(tot / n);
+}
+
+// ---- MSE(a, b) (mean) with its gradient and, from the last block to finish, the step's total loss - one launch for
+// vaegan_code.py:113 + :117 (no finalize / total kernels).  T = float (pixel MSE of the fp32 NCHW reconstruction) or
+// bf16 (Dis_l feature matching on NHWC discriminator features, README.md:11-14); the gradient is written in T.
+struct MseAcc {
+    double acc;
+    unsigned int ticket;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) mse_total_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                            long long n, float weight, const T* __restrict__ grad_in,
+                                                            T* __restrict__ grad_out, float* __restrict__ loss_out,
+                                                            const float* __restrict__ kl, const float* __restrict__ adv,
+                                                            const float* __restrict__ w_kl_ptr, float w_adv,
+                                                            float* __restrict__ total_out, MseAcc* __restrict__ ws) {
+    constexpr int V = Vec<T>::N;
+    __shared__ double red[32];
+    double acc = 0.0;
+    const float gs = 2.f * weight / static_cast<float>(n);
+    const long long nvec = n / V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float av[V], bv[V], gv[V];
+        Vec<T>::load(a + i * V, av);
+        Vec<T>::load(b + i * V, bv);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float d = av[j] - bv[j];
+            part = fmaf(d, d, part);
+            gv[j] = gs * d;
+        }
+        acc += static_cast<double>(part);
+        if (grad_out != nullptr) {
+            if (grad_in != nullptr) {
+                float gi[V];
+                Vec<T>::load(grad_in + i * V, gi);
+#pragma unroll
+                for (int j = 0; j < V; ++j) gv[j] += gi[j];
+            }
+            Vec<T>::store(grad_out + i * V, gv);
+        }
+    }
+    const double part = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&ws->acc, part);
+        __threadfence();
+        if (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const double tot = atomicAdd(&ws->acc, 0.0);
+            const float recon = static_cast<float>(weight * tot / static_cast<double>(n));
+            if (loss_out != nullptr) *loss_out = recon;
+            if (total_out != nullptr)
+                *total_out = recon + (w_kl_ptr ? *w_kl_ptr : 0.f) * (kl ? *kl : 0.f) + w_adv * (adv ? *adv : 0.f);
+            ws->acc = 0.0;          // re-armed for the next launch on this workspace
+            ws->ticket = 0;
+        }
+    }
+}
+
 // total = recon + w_kl * kl + w_adv * adv   (vaegan_code.py:117), all scalars on the device
 __global__ void total_loss_kernel(const float* recon, const float* kl, const float* adv, const float* w_kl_ptr,
                                   float w_kl, float w_adv, float* total) {
@@ -293,6 +372,42 @@ extern "C" int vg_bce(const float* p, int n, float target, float weight, float* 
     if (rc != VG_OK) return rc;
     if (p == nullptr) return fail(VG_ERR_ARG, "bce: null pointer");
     bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(p, n, target, weight, loss_out, accumulate, dp);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_bce_pair(const float* p, int n, float target_real, float target_fake, float weight, float* loss_out,
+                           float* dp, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (p == nullptr) return fail(VG_ERR_ARG, "bce_pair: null pointer");
+    bce_pair_kernel<<<1, 1024, 0, as_stream(stream)>>>(p, n, target_real, target_fake, weight, loss_out, dp);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+extern "C" int vg_mse_total(const void* a, const void* b, VgDType dt, long long n, float weight, const void* grad_in,
+                            void* grad_out, float* loss_out, const float* kl, const float* adv, const float* w_kl_dev,
+                            float w_adv, float* total_out, void* ws, size_t ws_bytes, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (a == nullptr || b == nullptr) return fail(VG_ERR_ARG, "mse_total: null pointer");
+    if (ws == nullptr || ws_bytes < sizeof(MseAcc)) return fail(VG_ERR_WORKSPACE, "mse_total: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(grad_in) |
+         reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(ws)) & 15)
+        return fail(VG_ERR_ALIGN, "mse_total: 16-byte alignment");
+    const int V = dt == VG_BF16 ? 8 : 4;
+    if (n % V != 0) return fail(VG_ERR_SHAPE, "mse_total: element count must be a multiple of %d", V);
+    const int blocks = grid_for(n / V);
+    if (dt == VG_BF16)
+        mse_total_kernel<__nv_bfloat16><<<blocks, kThreads, 0, as_stream(stream)>>>(
+            static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), n, weight,
+            static_cast<const __nv_bfloat16*>(grad_in), static_cast<__nv_bfloat16*>(grad_out), loss_out, kl, adv,
+            w_kl_dev, w_adv, total_out, static_cast<MseAcc*>(ws));
+    else
+        mse_total_kernel<float><<<blocks, kThreads, 0, as_stream(stream)>>>(
+            static_cast<const float*>(a), static_cast<const float*>(b), n, weight, static_cast<const float*>(grad_in),
+            static_cast<float*>(grad_out), loss_out, kl, adv, w_kl_dev, w_adv, total_out, static_cast<MseAcc*>(ws));
     VG_LAUNCHED();
     return VG_OK;
 }

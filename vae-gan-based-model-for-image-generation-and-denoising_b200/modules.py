@@ -332,14 +332,30 @@ class Discriminator(_KernelModule):
     def input_s2d_origin(self, h: int, w: int):
         return self._layers()[0].input_s2d_origin(self._dtype(), h, w)
 
-    def forward_nhwc(self, h, groups: int = 1):
+    def forward_nhwc(self, h, groups: int = 1, tap=None):
         """`groups` independent sub-batches stacked along the batch axis share every convolution launch while
-        BatchNorm treats them separately (the fused step runs D(real) and D(fake) of vaegan_code.py:96-97 this way)."""
+        BatchNorm treats them separately (the fused step runs D(real) and D(fake) of vaegan_code.py:96-97 this way).
+        `tap = (l, fn)`: the activation of conv group `l` (Dis_l of README.md eq. 2) is passed through `fn` before the
+        next layer reads it; the fused backward chain is cut there so that `fn` sees (and may add to) its gradient."""
         layers = self._layers()
-        h, link = _run_chain(layers[:-1], h, self.training, groups=groups)
+        if tap is None:
+            h, link = _run_chain(layers[:-1], h, self.training, groups=groups)
+        else:
+            cut = tap[0] % len(layers)
+            if cut >= len(layers) - 1:
+                raise ValueError("the tapped layer must be a hidden layer of the discriminator")
+            h = tap[1](self.features_nhwc(h, cut, groups=groups))
+            h, link = _run_chain(layers[cut + 1:-1], h, self.training, groups=groups)
         last = layers[-1]
         logits = last(h, self.training, out_f32=True, fuse_act=False, link_in=link)     # [B, 1, 1, 1] fp32
         return F_.PointwiseActFn.apply(logits, last.act, last.slope).view(-1)
+
+    def features_nhwc(self, h, layer: int, groups: int = 1):
+        """Activation (NHWC, internal dtype) after conv group `layer` - Dis_l(x)."""
+        layers = self._layers()
+        cut = layer % len(layers)
+        h, link = _run_chain(layers[:cut], h, self.training, groups=groups)
+        return layers[cut](h, self.training, groups=groups, link_in=link)
 
 
 def weights_init(m):

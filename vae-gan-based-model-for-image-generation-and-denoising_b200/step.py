@@ -111,23 +111,56 @@ class _ReparamFn(torch.autograd.Function):
 
 class _ReconHubFn(torch.autograd.Function):
     """recon (fp32 NCHW) -> recon + sigma*n_fake as the discriminator's NHWC input (vaegan_code.py:92).
-    Backward folds in the pixel-MSE term of :113: d_recon = d(adv path) + 2 (recon - real) / N, and writes the
-    reconstruction loss."""
+    Backward folds in the pixel-MSE term of :113, d_recon = d(adv path) + 2 (recon - real) / N, and the same launch
+    writes the reconstruction loss and the step's total (:117; KL and the adversarial term are already on the device
+    when the backward pass gets here).  `terms` = None in Dis_l mode (the feature tap owns the reconstruction term)."""
 
     @staticmethod
-    def forward(ctx, recon, real, n_fake, sigma, dtype, recon_loss_out, mse_ws, s2d_origin=None):
-        ctx.save_for_backward(recon, real, recon_loss_out, mse_ws)
-        ctx.s2d_origin = s2d_origin
+    def forward(ctx, recon, real, n_fake, sigma, dtype, terms, s2d_origin=None):
+        ctx.save_for_backward(recon, real)
+        ctx.s2d_origin, ctx.terms = s2d_origin, terms
         return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma, s2d_origin=s2d_origin)
 
     @staticmethod
     def backward(ctx, dy):
-        recon, real, loss_out, ws = ctx.saved_tensors
+        recon, real = ctx.saved_tensors
         d_adv = F_.nhwc_to_nchw(dy.contiguous(), channels=recon.shape[1], s2d_origin=ctx.s2d_origin)
+        if ctx.terms is None:
+            return d_adv, None, None, None, None, None, None
         d_total = torch.empty_like(recon)
-        call("vg_mse", _p(recon), _p(real), recon.numel(), 1.0, _p(d_adv), _p(d_total), _p(loss_out), _p(ws),
-             ws.numel() * 4, _stream())
-        return d_total, None, None, None, None, None, None, None
+        ctx.terms.mse_total(recon, real, d_adv, d_total)
+        return d_total, None, None, None, None, None, None
+
+
+class _FeatureMatchFn(torch.autograd.Function):
+    """Dis_l reconstruction term (README.md:11-14, eq. 2): identity on the tapped discriminator features of the
+    reconstruction; backward adds 2 (f - f_real) / N to their gradient and writes the loss and the step's total."""
+
+    @staticmethod
+    def forward(ctx, feat, feat_real, terms):
+        ctx.save_for_backward(feat, feat_real)
+        ctx.terms = terms
+        return feat.view_as(feat)
+
+    @staticmethod
+    def backward(ctx, dy):
+        feat, feat_real = ctx.saved_tensors
+        g = torch.empty_like(feat)
+        ctx.terms.mse_total(feat, feat_real, dy.contiguous(), g)
+        return g, None, None
+
+
+class _LossTerms:
+    """Device scalars the fused MSE + total launch reads / writes (slots of VAEGANStep's loss vector)."""
+
+    def __init__(self, losses, kl_w, alpha_adv, ws):
+        self.losses, self.kl_w, self.alpha_adv, self.ws = losses, kl_w, alpha_adv, ws
+
+    def mse_total(self, a, b, grad_in, grad_out):
+        L = self.losses
+        call("vg_mse_total", _p(a), _p(b), F_._DT[a.dtype], a.numel(), 1.0, _p(grad_in), _p(grad_out), _p(L[2:3]),
+             _p(L[3:4]), _p(L[4:5]), _p(self.kl_w), float(self.alpha_adv), _p(L[5:6]), _p(self.ws),
+             self.ws.numel() * 4, _stream())
 
 
 class VAEGANStep:
@@ -135,7 +168,8 @@ class VAEGANStep:
                  alpha_kl: float = 0.1, alpha_adv: float = 0.1, kl_warmup_epochs: int = 50, sigma_inst: float = 0.05,
                  denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
                  process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True,
-                 capture_grads: bool = False, bucket_bytes: Optional[Dict[str, int]] = None):
+                 capture_grads: bool = False, bucket_bytes: Optional[Dict[str, int]] = None,
+                 recon_mode: str = "pixel", dis_layer: int = -2):
         self.E, self.G, self.D = encoder, decoder, discriminator
         self.dtype = encoder._dtype()
         self.dev = next(encoder.parameters()).device
@@ -144,6 +178,12 @@ class VAEGANStep:
         self.alpha_kl, self.alpha_adv, self.kl_warmup = alpha_kl, alpha_adv, kl_warmup_epochs
         self.sigma_inst, self.denoise_sigma, self.n_dis = sigma_inst, denoise_sigma, n_dis
         self.real_label, self.fake_label = real_label, fake_label
+        # reconstruction term: "pixel" = MSE(recon, real) as vaegan_code.py:113 has it; "dis_l" = the feature-matching
+        # form of README.md:11-14 (eq. 2) on the discriminator's conv group `dis_layer` (no reference code: parity
+        # is pinned against the oracle's restatement only)
+        if recon_mode not in ("pixel", "dis_l"):
+            raise ValueError("recon_mode must be 'pixel' or 'dis_l'")
+        self.recon_mode, self.dis_layer = recon_mode, dis_layer
         self.pg = process_group
         self.world, self.rank = 1, 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -205,7 +245,7 @@ class VAEGANStep:
             "n_den": torch.zeros((batch, 3, hw, hw), **f32) if self.denoise_sigma > 0 else None,
             "kl_w": torch.zeros((), **f32), "losses": torch.zeros((len(LOSS_KEYS),), **f32),
             "rng_offset": torch.zeros((), dtype=torch.int64, device=dev),
-            "mse_ws": torch.empty((F_._lib.load().vg_mse_workspace_bytes() // 4,), **f32),
+            "mse_ws": torch.zeros((F_._lib.load().vg_mse_workspace_bytes() // 4,), **f32),
             "dp_a": torch.empty((batch,), **f32), "dp_pair": torch.empty((2 * batch,), **f32),
         }
         return s
@@ -279,8 +319,10 @@ class VAEGANStep:
         recon = F_.ToNCHWActFn.apply(G.forward_nhwc(z), ACT_TANH, 3)
 
         # ---- instance noise                                                           (:88-92)
-        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype, loss[2:3], s["mse_ws"],
-                                        d_fmt)
+        terms = _LossTerms(loss, s["kl_w"], self.alpha_adv, s["mse_ws"])
+        dis_l = self.recon_mode == "dis_l"
+        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype,
+                                        None if dis_l else terms, d_fmt)
         # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
         # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2)
         pair = torch.empty((2 * B,) + tuple(recon_noisy.shape[1:]), dtype=self.dtype, device=self.dev)
@@ -293,8 +335,7 @@ class VAEGANStep:
             self.opt_D.zero_grad()
             p_pair = D.forward_nhwc(pair, groups=2)
             slot = loss[it:it + 1] if it < 2 else None
-            call("vg_bce", _p(p_pair[:B]), B, self.real_label, 1.0, _p(slot), 0, _p(dp[:B]), _stream())
-            call("vg_bce", _p(p_pair[B:]), B, self.fake_label, 1.0, _p(slot), 1, _p(dp[B:]), _stream())
+            call("vg_bce_pair", _p(p_pair), B, self.real_label, self.fake_label, 1.0, _p(slot), _p(dp), _stream())
             self._arm_buckets("D")
             try:
                 torch.autograd.backward([p_pair], [dp])
@@ -317,15 +358,18 @@ class VAEGANStep:
             p.requires_grad_(False)
         self._arm_buckets("E", "G")
         try:
-            p_fake = D.forward_nhwc(recon_noisy)
+            tap = None
+            if dis_l:
+                with torch.no_grad():                   # Dis_l(x): its own train-mode call, like the oracle's
+                    feat_real = D.features_nhwc(pair[:B], self.dis_layer)
+                tap = (self.dis_layer, lambda f: _FeatureMatchFn.apply(f, feat_real, terms))
+            p_fake = D.forward_nhwc(recon_noisy, tap=tap)
             call("vg_bce", _p(p_fake), B, self.real_label, self.alpha_adv, _p(loss[4:5]), 0, _p(s["dp_a"]), _stream())
-            torch.autograd.backward([p_fake], [s["dp_a"]])
+            torch.autograd.backward([p_fake], [s["dp_a"]])      # (the MSE launch inside also writes recon and total)
         finally:
             F_.GradReady.clear()
             for p in d_params:
                 p.requires_grad_(True)
-        call("vg_total_loss", _p(loss[2:3]), _p(loss[3:4]), _p(loss[4:5]), _p(s["kl_w"]), 0.0, self.alpha_adv,
-             _p(loss[5:6]), _stream())
         F_.WgradOverlap.join()
         self._finish_buckets("G", "E")
         self.opt_E.step(1.0 / self.world)
