@@ -1,6 +1,8 @@
 #include "common.cuh"
+#include "pdl.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace vg {
@@ -13,6 +15,14 @@ char* last_error_buffer() {
 static std::atomic<long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("VG_PDL");
+        return v == nullptr || v[0] != '0';
+    }();
+    return on;
+}
 
 int device_check() {
     static std::mutex mu;

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "conv_simt.cuh"
 #include "gemv.cuh"
 #include "igemm_umma.cuh"
@@ -669,6 +670,7 @@ struct PackBatch {
 constexpr int kPackT = 32, kPackK = 16, kPackRow = kPackT + 2, kPackPlane = kPackT * kPackRow + 2;
 
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackBatch b) {
+    pdl_enter();
     __shared__ __nv_bfloat16 tile[kPackK * kPackPlane];
     const VgPackItem it = b.item[blockIdx.y];
     const int sc = it.small_c, bc = it.big_c, bcv = it.big_c_valid > 0 ? it.big_c_valid : it.big_c, kk = it.kk;
@@ -773,7 +775,7 @@ extern "C" int vg_pack_weights_multi(const VgPackItem* items, int n_items, void*
             biggest = std::max(biggest, pack_work(b.item[i]));
         }
         const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(biggest, 148 * 6)));
-        pack_weights_multi_kernel<<<dim3(blocks, b.n), 256, 0, as_stream(stream)>>>(b);
+        launch_k(pack_weights_multi_kernel, dim3(blocks, b.n), dim3(256), 0, as_stream(stream), b);
         VG_LAUNCHED();
     }
     return VG_OK;
@@ -793,7 +795,7 @@ extern "C" int vg_pack_weights_bf16(const VgConvGeom* g, const float* w, void* w
     b.item[0].big_c_valid = bc_valid(g) != g->big_c ? bc_valid(g) : 0;
     b.item[0].kk = g->kernel * g->kernel;
     const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(pack_work(b.item[0]), 148 * 6)));
-    pack_weights_multi_kernel<<<dim3(blocks, 1), 256, 0, as_stream(stream)>>>(b);
+    launch_k(pack_weights_multi_kernel, dim3(blocks, 1), dim3(256), 0, as_stream(stream), b);
     VG_LAUNCHED();
     return VG_OK;
 }

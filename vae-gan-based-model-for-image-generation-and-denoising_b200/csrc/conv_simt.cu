@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "conv_simt.cuh"
 
 namespace vg {
@@ -152,6 +153,7 @@ struct WgradOp {
 
 template <class Op>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const Op op) {
+    pdl_enter();
     __shared__ __align__(16) float As[TK][TM + 4];
     __shared__ __align__(16) float Bs[TK][TN + 4];
     const int tid = threadIdx.x;
@@ -224,7 +226,7 @@ int run_down(const VgConvGeom* g, const void* big, const void* w, const float* b
     else        { op.ws_sc = op.g.bcv * kk; op.ws_bc = kk; op.ws_tap = 1; }
     const long long M = static_cast<long long>(g->batch) * g->small_h * g->small_w;
     dim3 grid(cdiv(M, TM), cdiv(g->small_c, TN), 1);
-    simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
+    launch_k(simt_gemm_kernel<decltype(op)>, dim3(grid), dim3(256), 0, st, op);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -242,7 +244,7 @@ int run_up(const VgConvGeom* g, const void* small, const void* w, void* big, boo
     const int s = g->stride;
     const long long M = static_cast<long long>(g->batch) * ((g->big_h + s - 1) / s) * ((g->big_w + s - 1) / s);
     dim3 grid(cdiv(M, TM), cdiv(g->big_c, TN), s * s);
-    simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
+    launch_k(simt_gemm_kernel<decltype(op)>, dim3(grid), dim3(256), 0, st, op);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -261,7 +263,7 @@ int run_wgrad(const VgConvGeom* g, const void* small, const void* big, float* dw
     if (kk * splits > 65535) splits = std::max(1, 65535 / kk);
     op.splits = splits;
     dim3 grid(cdiv(g->small_c, TM), cdiv(g->big_c, TN), kk * splits);
-    simt_gemm_kernel<<<grid, 256, 0, st>>>(op);
+    launch_k(simt_gemm_kernel<decltype(op)>, dim3(grid), dim3(256), 0, st, op);
     VG_LAUNCHED();
     return VG_OK;
 }

@@ -9,6 +9,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "vec.cuh"
 
 namespace vg {
@@ -82,6 +83,7 @@ __device__ __forceinline__ float load1(const T* p) {
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 4) channel_reduce_kernel(const ReduceArgs a) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     __shared__ float red[kThreads][2 * V + 1];
     __shared__ bool is_last;
@@ -285,6 +287,7 @@ struct FusedArgs {
 
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(kThreads) bn_fused_kernel(const FusedArgs a) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;                            // rows in flight per thread
     __shared__ float red[kThreads][2 * V + 1];
@@ -507,8 +510,8 @@ int next_slot() {
 template <int MODE>
 int launch_reduce(VgDType dt, ReduceArgs a, int blocks, cudaStream_t st) {
     a.slot = next_slot();
-    if (dt == VG_BF16) channel_reduce_kernel<__nv_bfloat16, MODE><<<blocks, kThreads, 0, st>>>(a);
-    else channel_reduce_kernel<float, MODE><<<blocks, kThreads, 0, st>>>(a);
+    if (dt == VG_BF16) launch_k(channel_reduce_kernel<__nv_bfloat16, MODE>, dim3(blocks), dim3(kThreads), 0, st, a);
+    else launch_k(channel_reduce_kernel<float, MODE>, dim3(blocks), dim3(kThreads), 0, st, a);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -547,6 +550,7 @@ int launch_fused(VgDType dt, FusedArgs a, cudaStream_t st) {
 
 __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                       int C, float* scale, float* shift) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float rstd = 1.f / sqrtf(rv[c] + eps);
@@ -557,6 +561,7 @@ __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, con
 
 template <typename T>
 __global__ void colsum_generic_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict__ out) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s = 0.0;
@@ -571,6 +576,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads) scale_shift_act_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                                   long long n, int C, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, int act, float slope) {
+    pdl_enter();
     // generic scalar path (used for tiny tensors such as the [B] discriminator logits)
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -592,6 +598,7 @@ __global__ void __launch_bounds__(kThreads) scale_shift_act_vec_kernel(const T* 
                                                                       const float* __restrict__ scale,
                                                                       const float* __restrict__ shift, int act,
                                                                       float slope) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;
     const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -627,6 +634,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_apply_kernel(const T* __r
                                                                    const float* __restrict__ rstd,
                                                                    const float* __restrict__ c1,
                                                                    const float* __restrict__ c2, int act, float slope) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;
     const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -675,6 +683,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
     const T* __restrict__ x, T* __restrict__ y, long long nvec, int C, long long rows, const float* __restrict__ sums,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     long long* num_batches_tracked, float momentum, float eps, float* __restrict__ stats, int act, float slope) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;
     const int grp = blockIdx.y, groups = gridDim.y;
@@ -756,6 +765,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
     const T* __restrict__ dz, const T* __restrict__ x, T* __restrict__ dx, long long nvec, int C, long long rows,
     const float* __restrict__ stats, const float* __restrict__ sums, float* dgamma, float* dbeta) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;
     const int grp = blockIdx.y;
@@ -812,6 +822,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const TI* __restrict__ dy, const TI* __restrict__ x,
                                                           TO* __restrict__ dx, long long n, int act, float slope) {
+    pdl_enter();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float d, z;
@@ -831,6 +842,7 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_kernel(const float* __r
                                                                const float* __restrict__ aux, T* __restrict__ dst,
                                                                int B, int C, int Cd, long long HW, int mode,
                                                                float sigma, int clamp) {
+    pdl_enter();
     const long long total = static_cast<long long>(B) * HW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -883,6 +895,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst,
                                                                int B, int C, int Cs, long long HW, int act,
                                                                float slope) {
+    pdl_enter();
     const long long total = static_cast<long long>(B) * HW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -903,6 +916,7 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const float* __re
                                                               const float* __restrict__ aux,
                                                               __nv_bfloat16* __restrict__ dst, int B, int C, int H, int W,
                                                               int o, int mode, float sigma, int clamp) {
+    pdl_enter();
     const int bh = H / 2 + o, bw = W / 2 + o;
     const long long total = static_cast<long long>(B) * bh * bw;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -943,6 +957,7 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const float* __re
 __global__ void __launch_bounds__(kThreads) s2d_to_nchw_kernel(const __nv_bfloat16* __restrict__ src,
                                                               float* __restrict__ dst, int B, int C, int H, int W, int o,
                                                               int act, float slope) {
+    pdl_enter();
     const int bh = H / 2 + o, bw = W / 2 + o;
     const long long total = static_cast<long long>(B) * bh * bw;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -974,6 +989,7 @@ __global__ void __launch_bounds__(kThreads) s2d_to_nchw_kernel(const __nv_bfloat
 __global__ void __launch_bounds__(kThreads) u8_nhwc_to_nchw_kernel(const unsigned char* __restrict__ src,
                                                                   float* __restrict__ dst, int B, int C, long long HW,
                                                                   float mean, float inv_std) {
+    pdl_enter();
     const long long total = static_cast<long long>(B) * HW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -989,6 +1005,7 @@ __global__ void __launch_bounds__(kThreads) u8_nhwc_to_nchw_kernel(const unsigne
 // sides coalesced.  mode 0: dst = W' built from src = W;  mode 1: dst = dW (master layout) += src = dW'.
 __global__ void __launch_bounds__(256) linear_permute_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                             int n_valid, int C, int kk, int mode) {
+    pdl_enter();
     __shared__ float tile[32][33];
     const int n = blockIdx.z, tap0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
@@ -1021,6 +1038,7 @@ __global__ void __launch_bounds__(256) linear_permute_kernel(const float* __rest
 __global__ void __launch_bounds__(kThreads) gather_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                              const int* __restrict__ idx, long long n, int fan,
                                                              int accumulate) {
+    pdl_enter();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float acc = accumulate ? dst[i] : 0.f;
@@ -1082,7 +1100,7 @@ extern "C" int vg_bn_eval_coeffs(const float* gamma, const float* beta, const fl
                                  void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;
-    bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps,
+    launch_k(bn_eval_coeffs_kernel, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), gamma, beta, running_mean, running_var, eps,
                                                                           C, scale_out, shift_out);
     VG_LAUNCHED();
     return VG_OK;
@@ -1099,23 +1117,17 @@ extern "C" int vg_scale_shift_act(const void* x, VgDType in_dt, long long rows, 
     if (in_dt == out_dt && C % V == 0 && is_pow2(C / V)) {
         const long long nvec = n / V;
         if (in_dt == VG_BF16)
-            scale_shift_act_vec_kernel<__nv_bfloat16><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
-                static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, scale, shift, act, slope);
+            launch_k(scale_shift_act_vec_kernel<__nv_bfloat16>, dim3(grid_affine(nvec, C / V)), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, scale, shift, act, slope);
         else
-            scale_shift_act_vec_kernel<float><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
-                static_cast<const float*>(x), static_cast<float*>(y), nvec, C, scale, shift, act, slope);
+            launch_k(scale_shift_act_vec_kernel<float>, dim3(grid_affine(nvec, C / V)), dim3(kThreads), 0, st, static_cast<const float*>(x), static_cast<float*>(y), nvec, C, scale, shift, act, slope);
     } else if (in_dt == VG_BF16 && out_dt == VG_BF16) {
-        scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n), kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
+        launch_k(scale_shift_act_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid_for(n)), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
     } else if (in_dt == VG_BF16 && out_dt == VG_F32) {
-        scale_shift_act_kernel<__nv_bfloat16, float><<<grid_for(n), kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
+        launch_k(scale_shift_act_kernel<__nv_bfloat16, float>, dim3(grid_for(n)), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
     } else if (in_dt == VG_F32 && out_dt == VG_BF16) {
-        scale_shift_act_kernel<float, __nv_bfloat16><<<grid_for(n), kThreads, 0, st>>>(
-            static_cast<const float*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
+        launch_k(scale_shift_act_kernel<float, __nv_bfloat16>, dim3(grid_for(n)), dim3(kThreads), 0, st, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(y), n, C, scale, shift, act, slope);
     } else {
-        scale_shift_act_kernel<float, float><<<grid_for(n), kThreads, 0, st>>>(
-            static_cast<const float*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
+        launch_k(scale_shift_act_kernel<float, float>, dim3(grid_for(n)), dim3(kThreads), 0, st, static_cast<const float*>(x), static_cast<float*>(y), n, C, scale, shift, act, slope);
     }
     VG_LAUNCHED();
     return VG_OK;
@@ -1146,12 +1158,10 @@ extern "C" int vg_bn_act_bwd(const void* dy, const void* x, VgDType dt, long lon
     const int V = dt == VG_BF16 ? 8 : 4;
     const long long nvec = rows * C / V;
     if (dt == VG_BF16)
-        bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
+        launch_k(bn_act_bwd_apply_kernel<__nv_bfloat16>, dim3(grid_affine(nvec, C / V)), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
             static_cast<__nv_bfloat16*>(dx), nvec, C, scale, shift, mean, rstd, c1, c2, act, slope);
     else
-        bn_act_bwd_apply_kernel<float><<<grid_affine(nvec, C / V), kThreads, 0, st>>>(
-            static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
+        launch_k(bn_act_bwd_apply_kernel<float>, dim3(grid_affine(nvec, C / V)), dim3(kThreads), 0, st, static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, scale, shift,
             mean, rstd, c1, c2, act, slope);
     VG_LAUNCHED();
     return VG_OK;
@@ -1175,12 +1185,10 @@ extern "C" int vg_bn_apply_from_sums(const void* x, VgDType dt, long long rows, 
     const dim3 grid(grid_affine(nvec, C / V), groups);
     cudaStream_t st = as_stream(stream);
     if (dt == VG_BF16)
-        bn_apply_from_sums_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, rows, sums, gamma, beta,
+        launch_k(bn_apply_from_sums_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, rows, sums, gamma, beta,
             running_mean, running_var, num_batches_tracked, momentum, eps, stats, act, slope);
     else
-        bn_apply_from_sums_kernel<float><<<grid, kThreads, 0, st>>>(
-            static_cast<const float*>(x), static_cast<float*>(y), nvec, C, rows, sums, gamma, beta, running_mean,
+        launch_k(bn_apply_from_sums_kernel<float>, dim3(grid), dim3(kThreads), 0, st, static_cast<const float*>(x), static_cast<float*>(y), nvec, C, rows, sums, gamma, beta, running_mean,
             running_var, num_batches_tracked, momentum, eps, stats, act, slope);
     VG_LAUNCHED();
     return VG_OK;
@@ -1202,12 +1210,10 @@ extern "C" int vg_bn_bwd_apply_from_sums(const void* dz, const void* x, VgDType 
     const dim3 grid(grid_affine(nvec, C / V), groups);
     cudaStream_t st = as_stream(stream);
     if (dt == VG_BF16)
-        bn_bwd_apply_from_sums_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
+        launch_k(bn_bwd_apply_from_sums_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
             nvec, C, rows, stats, sums, dgamma, dbeta);
     else
-        bn_bwd_apply_from_sums_kernel<float><<<grid, kThreads, 0, st>>>(
-            static_cast<const float*>(dz), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, rows, stats,
+        launch_k(bn_bwd_apply_from_sums_kernel<float>, dim3(grid), dim3(kThreads), 0, st, static_cast<const float*>(dz), static_cast<const float*>(x), static_cast<float*>(dx), nvec, C, rows, stats,
             sums, dgamma, dbeta);
     VG_LAUNCHED();
     return VG_OK;
@@ -1226,18 +1232,17 @@ extern "C" int vg_act_bwd(const void* dy, const void* x, VgDType in_dt, long lon
     cudaStream_t st = as_stream(stream);
     const int g = grid_for(n);
     if (in_dt == VG_BF16 && out_dt == VG_BF16)
-        act_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, kThreads, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
+        launch_k(act_bwd_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
             n, act, slope);
     else if (in_dt == VG_F32 && out_dt == VG_BF16)
-        act_bwd_kernel<float, __nv_bfloat16><<<g, kThreads, 0, st>>>(static_cast<const float*>(dy),
+        launch_k(act_bwd_kernel<float, __nv_bfloat16>, dim3(g), dim3(kThreads), 0, st, static_cast<const float*>(dy),
                                                                      static_cast<const float*>(x),
                                                                      static_cast<__nv_bfloat16*>(dx), n, act, slope);
     else if (in_dt == VG_F32 && out_dt == VG_F32)
-        act_bwd_kernel<float, float><<<g, kThreads, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
+        launch_k(act_bwd_kernel<float, float>, dim3(g), dim3(kThreads), 0, st, static_cast<const float*>(dy), static_cast<const float*>(x),
                                                              static_cast<float*>(dx), n, act, slope);
     else
-        act_bwd_kernel<__nv_bfloat16, float><<<g, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
+        launch_k(act_bwd_kernel<__nv_bfloat16, float>, dim3(g), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(dy),
                                                                      static_cast<const __nv_bfloat16*>(x),
                                                                      static_cast<float*>(dx), n, act, slope);
     VG_LAUNCHED();
@@ -1253,11 +1258,9 @@ extern "C" int vg_colsum(const void* x, VgDType dt, long long rows, int C, float
         const int V = dt == VG_BF16 ? 8 : 4;
         if (C % V != 0 || !is_pow2(C / V)) {  // odd channel counts (e.g. latent_dim 100): one thread per channel
             if (dt == VG_BF16)
-                colsum_generic_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
-                    static_cast<const __nv_bfloat16*>(x), rows, C, out);
+                launch_k(colsum_generic_kernel<__nv_bfloat16>, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(x), rows, C, out);
             else
-                colsum_generic_kernel<float><<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
-                    static_cast<const float*>(x), rows, C, out);
+                launch_k(colsum_generic_kernel<float>, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), static_cast<const float*>(x), rows, C, out);
             VG_LAUNCHED();
             return VG_OK;
         }
@@ -1281,10 +1284,9 @@ extern "C" int vg_nchw_to_nhwc(const float* src, const float* aux, void* dst, Vg
     const long long HW = static_cast<long long>(H) * W;
     const int g = grid_for(B * HW);
     if (dt == VG_BF16)
-        nchw_to_nhwc_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
-            src, aux, static_cast<__nv_bfloat16*>(dst), B, C, Cd, HW, mode, sigma, clamp);
+        launch_k(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(g), dim3(kThreads), 0, as_stream(stream), src, aux, static_cast<__nv_bfloat16*>(dst), B, C, Cd, HW, mode, sigma, clamp);
     else
-        nchw_to_nhwc_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(src, aux, static_cast<float*>(dst), B, C, Cd,
+        launch_k(nchw_to_nhwc_kernel<float>, dim3(g), dim3(kThreads), 0, as_stream(stream), src, aux, static_cast<float*>(dst), B, C, Cd,
                                                                           HW, mode, sigma, clamp);
     VG_LAUNCHED();
     return VG_OK;
@@ -1299,8 +1301,7 @@ extern "C" int vg_nchw_to_s2d(const float* src, const float* aux, void* dst, int
         return fail(VG_ERR_SHAPE, "nchw_to_s2d: needs <= 16 channels, even H and W, origin 0 or 1");
     if (reinterpret_cast<uintptr_t>(dst) & 15) return fail(VG_ERR_ALIGN, "nchw_to_s2d: 16-byte alignment");
     const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
-    nchw_to_s2d_kernel<<<grid_for(blocks), kThreads, 0, as_stream(stream)>>>(
-        src, aux, static_cast<__nv_bfloat16*>(dst), B, C, H, W, origin, mode, sigma, clamp);
+    launch_k(nchw_to_s2d_kernel, dim3(grid_for(blocks)), dim3(kThreads), 0, as_stream(stream), src, aux, static_cast<__nv_bfloat16*>(dst), B, C, H, W, origin, mode, sigma, clamp);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1314,8 +1315,7 @@ extern "C" int vg_s2d_to_nchw(const void* src, float* dst, int B, int C, int H, 
         return fail(VG_ERR_SHAPE, "s2d_to_nchw: needs <= 16 channels, even H and W, origin 0 or 1");
     if (reinterpret_cast<uintptr_t>(src) & 15) return fail(VG_ERR_ALIGN, "s2d_to_nchw: 16-byte alignment");
     const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
-    s2d_to_nchw_kernel<<<grid_for(blocks), kThreads, 0, as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(src), dst, B, C, H, W, origin, act, slope);
+    launch_k(s2d_to_nchw_kernel, dim3(grid_for(blocks)), dim3(kThreads), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(src), dst, B, C, H, W, origin, act, slope);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1327,8 +1327,7 @@ extern "C" int vg_u8_nhwc_to_nchw(const void* src, float* dst, int B, int C, int
     if (src == nullptr || dst == nullptr) return fail(VG_ERR_ARG, "u8_nhwc_to_nchw: null pointer");
     if (std == 0.f) return fail(VG_ERR_ARG, "u8_nhwc_to_nchw: std must not be zero");
     const long long HW = static_cast<long long>(H) * W;
-    u8_nhwc_to_nchw_kernel<<<grid_for(B * HW), kThreads, 0, as_stream(stream)>>>(
-        static_cast<const unsigned char*>(src), dst, B, C, HW, mean, 1.f / std);
+    launch_k(u8_nhwc_to_nchw_kernel, dim3(grid_for(B * HW)), dim3(kThreads), 0, as_stream(stream), static_cast<const unsigned char*>(src), dst, B, C, HW, mean, 1.f / std);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1340,7 +1339,7 @@ extern "C" int vg_linear_permute(const float* src, float* dst, int n_valid, int 
     if (src == nullptr || dst == nullptr || n_valid < 1 || n_rows < n_valid || C < 1 || kk < 1 || (mode != 0 && mode != 1))
         return fail(VG_ERR_ARG, "linear_permute: bad argument");
     const dim3 grid((kk + 31) / 32, (C + 31) / 32, mode == 0 ? n_rows : n_valid);
-    linear_permute_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, n_valid, C, kk, mode);
+    launch_k(linear_permute_kernel, dim3(grid), dim3(256), 0, as_stream(stream), src, dst, n_valid, C, kk, mode);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1352,7 +1351,7 @@ extern "C" int vg_gather_f32(float* dst, const float* src, const int* idx, long 
     if (dst == nullptr || src == nullptr || idx == nullptr || n < 0 || fan < 1)
         return fail(VG_ERR_ARG, "gather_f32: bad argument");
     if (n == 0) return VG_OK;
-    gather_f32_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(dst, src, idx, n, fan, accumulate);
+    launch_k(gather_f32_kernel, dim3(grid_for(n)), dim3(kThreads), 0, as_stream(stream), dst, src, idx, n, fan, accumulate);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1366,10 +1365,9 @@ extern "C" int vg_nhwc_to_nchw(const void* src, VgDType dt, int Cs, float* dst, 
     const long long HW = static_cast<long long>(H) * W;
     const int g = grid_for(B * HW);
     if (dt == VG_BF16)
-        nhwc_to_nchw_kernel<__nv_bfloat16><<<g, kThreads, 0, as_stream(stream)>>>(
-            static_cast<const __nv_bfloat16*>(src), dst, B, C, Cs, HW, act, slope);
+        launch_k(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(g), dim3(kThreads), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(src), dst, B, C, Cs, HW, act, slope);
     else
-        nhwc_to_nchw_kernel<float><<<g, kThreads, 0, as_stream(stream)>>>(static_cast<const float*>(src), dst, B, C, Cs,
+        launch_k(nhwc_to_nchw_kernel<float>, dim3(g), dim3(kThreads), 0, as_stream(stream), static_cast<const float*>(src), dst, B, C, Cs,
                                                                           HW, act, slope);
     VG_LAUNCHED();
     return VG_OK;

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "gemv.cuh"
 
 namespace vg {
@@ -25,6 +26,7 @@ template <typename T, typename WT>
 __global__ void __launch_bounds__(256) gemv_down_kernel(const T* __restrict__ x, const WT* __restrict__ w,
                                                        const float* __restrict__ bias, void* __restrict__ out,
                                                        int out_f32, int kk, int cpad, int cvalid) {
+    pdl_enter();
     __shared__ float red[8];
     const int b = blockIdx.x;
     const long long K = static_cast<long long>(kk) * cpad;
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(256) gemv_down_kernel(const T* __restrict__ x,
 template <typename T, typename WT>
 __global__ void __launch_bounds__(256) gemv_up_kernel(const T* __restrict__ s, const WT* __restrict__ w,
                                                      T* __restrict__ dx, int batch, int kk, int cpad, int cvalid) {
+    pdl_enter();
     const long long K = static_cast<long long>(kk) * cpad, total = K * batch;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -66,6 +69,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemv_wgrad_kernel(const T* __restrict__ s, const T* __restrict__ x,
                                                         float* __restrict__ dw, int batch, int kk, int cpad,
                                                         int cvalid) {
+    pdl_enter();
     const long long K = static_cast<long long>(kk) * cpad;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < K;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(256) gemv_down_bf16_kernel(const __nv_bfloat16
                                                             const __nv_bfloat16* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ out,
                                                             int out_f32, int kvec) {
+    pdl_enter();
     __shared__ float red[8];
     const uint4* xb = reinterpret_cast<const uint4*>(x) + static_cast<long long>(blockIdx.x) * kvec;
     const uint4* wv = reinterpret_cast<const uint4*>(w);
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(256) gemv_down_bf16_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) gemv_up_bf16_kernel(const __nv_bfloat16* __restrict__ s,
                                                           const __nv_bfloat16* __restrict__ w,
                                                           __nv_bfloat16* __restrict__ dx, int batch, int kvec) {
+    pdl_enter();
     const long long total = static_cast<long long>(batch) * kvec;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(256) gemv_wgrad_bf16_kernel(const __nv_bfloat1
                                                              const __nv_bfloat16* __restrict__ x,
                                                              float* __restrict__ dw, int batch, int kk, int c, int kvec,
                                                              int chunk) {
+    pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= kvec) return;
     const int b0 = blockIdx.y * chunk, b1 = min(batch, b0 + chunk);
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(256) gemv_up_bnbwd_kernel(const __nv_bfloat16*
                                                            const float* __restrict__ stats, float* __restrict__ sums,
                                                            __nv_bfloat16* __restrict__ dz, int batch, int c, int kvec,
                                                            int group_batch, float neg_slope) {
+    pdl_enter();
     __shared__ float red[256][17];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;           // kvec is a multiple of 256 (checked by the launcher)
     const int b0 = blockIdx.y * kGemvChunk, b1 = min(batch, b0 + kGemvChunk);
@@ -247,15 +255,14 @@ int gemv_down(const VgConvGeom* g, VgDType dtype, const void* big, const void* w
               int out_f32, cudaStream_t stm) {
     const int kk = g->kernel * g->kernel;
     if (dtype == VG_BF16 && bf16_fast(g, big, w))
-        gemv_down_bf16_kernel<<<g->batch, 256, 0, stm>>>(static_cast<const __nv_bfloat16*>(big),
+        launch_k(gemv_down_bf16_kernel, dim3(g->batch), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(big),
                                                          static_cast<const __nv_bfloat16*>(w), bias, small, out_f32,
                                                          kk * g->big_c / 8);
     else if (dtype == VG_BF16)
-        gemv_down_kernel<__nv_bfloat16, __nv_bfloat16><<<g->batch, 256, 0, stm>>>(
-            static_cast<const __nv_bfloat16*>(big), static_cast<const __nv_bfloat16*>(w), bias, small, out_f32, kk,
+        launch_k(gemv_down_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g->batch), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(big), static_cast<const __nv_bfloat16*>(w), bias, small, out_f32, kk,
             g->big_c, valid_c(g));
     else
-        gemv_down_kernel<float, float><<<g->batch, 256, 0, stm>>>(static_cast<const float*>(big),
+        launch_k(gemv_down_kernel<float, float>, dim3(g->batch), dim3(256), 0, stm, static_cast<const float*>(big),
                                                                   static_cast<const float*>(w), bias, small, out_f32,
                                                                   kk, g->big_c, valid_c(g));
     VG_LAUNCHED();
@@ -268,15 +275,14 @@ int gemv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void* w
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
     if (dtype == VG_BF16 && bf16_fast(g, big, w)) {
         const int vblocks = static_cast<int>(std::min<long long>((total / 8 + 255) / 256, 148 * 8));
-        gemv_up_bf16_kernel<<<vblocks, 256, 0, stm>>>(static_cast<const __nv_bfloat16*>(small),
+        launch_k(gemv_up_bf16_kernel, dim3(vblocks), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(small),
                                                       static_cast<const __nv_bfloat16*>(w),
                                                       static_cast<__nv_bfloat16*>(big), g->batch, kk * g->big_c / 8);
     } else if (dtype == VG_BF16)
-        gemv_up_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stm>>>(
-            static_cast<const __nv_bfloat16*>(small), static_cast<const __nv_bfloat16*>(w),
+        launch_k(gemv_up_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(small), static_cast<const __nv_bfloat16*>(w),
             static_cast<__nv_bfloat16*>(big), g->batch, kk, g->big_c, valid_c(g));
     else
-        gemv_up_kernel<float, float><<<blocks, 256, 0, stm>>>(static_cast<const float*>(small),
+        launch_k(gemv_up_kernel<float, float>, dim3(blocks), dim3(256), 0, stm, static_cast<const float*>(small),
                                                               static_cast<const float*>(w), static_cast<float*>(big),
                                                               g->batch, kk, g->big_c, valid_c(g));
     VG_LAUNCHED();
@@ -297,7 +303,7 @@ int gemv_up_fused(const VgConvGeom* g, const void* small, const void* w, void* b
     const int c = g->big_c, kvec = g->kernel * g->kernel * c / 8, groups = ep->groups > 0 ? ep->groups : 1;
     const float neg_slope = ep->act == VG_ACT_RELU ? 0.f : (ep->act == VG_ACT_LEAKY ? ep->slope : 1.f);
     const dim3 grid(kvec / 256, (g->batch + kGemvChunk - 1) / kGemvChunk);
-    gemv_up_bnbwd_kernel<<<grid, 256, 0, stm>>>(static_cast<const __nv_bfloat16*>(small),
+    launch_k(gemv_up_bnbwd_kernel, dim3(grid), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(small),
                                                 static_cast<const __nv_bfloat16*>(w),
                                                 static_cast<const __nv_bfloat16*>(ep->x), ep->stats, ep->sums,
                                                 static_cast<__nv_bfloat16*>(big), g->batch, c, kvec, g->batch / groups,
@@ -313,15 +319,15 @@ int gemv_wgrad(const VgConvGeom* g, VgDType dtype, const void* small, const void
     if (dtype == VG_BF16 && bf16_fast(g, big, big)) {
         const int kvec = static_cast<int>(K / 8), chunk = 16;
         const dim3 grid((kvec + 255) / 256, (g->batch + chunk - 1) / chunk);
-        gemv_wgrad_bf16_kernel<<<grid, 256, 0, stm>>>(static_cast<const __nv_bfloat16*>(small),
+        launch_k(gemv_wgrad_bf16_kernel, dim3(grid), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(small),
                                                       static_cast<const __nv_bfloat16*>(big), dw, g->batch, kk, g->big_c,
                                                       kvec, chunk);
     } else if (dtype == VG_BF16)
-        gemv_wgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, stm>>>(static_cast<const __nv_bfloat16*>(small),
+        launch_k(gemv_wgrad_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stm, static_cast<const __nv_bfloat16*>(small),
                                                                   static_cast<const __nv_bfloat16*>(big), dw, g->batch,
                                                                   kk, g->big_c, valid_c(g));
     else
-        gemv_wgrad_kernel<float><<<blocks, 256, 0, stm>>>(static_cast<const float*>(small),
+        launch_k(gemv_wgrad_kernel<float>, dim3(blocks), dim3(256), 0, stm, static_cast<const float*>(small),
                                                           static_cast<const float*>(big), dw, g->batch, kk, g->big_c,
                                                           valid_c(g));
     VG_LAUNCHED();

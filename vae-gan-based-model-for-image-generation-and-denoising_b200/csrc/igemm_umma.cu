@@ -6,6 +6,7 @@
 //   warps 2..5         : epilogue - tcgen05.ld the fp32 accumulator (lane quadrant = warp % 4), convert, store
 #include "igemm_umma.cuh"
 #include "ptx.cuh"
+#include "pdl.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -95,16 +96,8 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
     const int fC = p.fuse_c;
     float* s_sums = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarrierBytes);
     float4* s_prm = reinterpret_cast<float4*>(s_sums + p.fuse_groups * 2 * fC);
-    if (fmode == 1 || fmode == 2) {
+    if (fmode == 1 || fmode == 2)
         for (int i = threadIdx.x; i < p.fuse_groups * 2 * fC; i += blockDim.x) s_sums[i] = 0.f;
-        if (fmode == 2) {
-            for (int i = threadIdx.x; i < p.fuse_groups * fC; i += blockDim.x) {
-                const int g = i / fC, c = i - g * fC;
-                const float* st = p.fuse_stats + static_cast<size_t>(g) * 4 * fC;
-                s_prm[i] = make_float4(__ldg(st + c), __ldg(st + fC + c), __ldg(st + 2 * fC + c), __ldg(st + 3 * fC + c));
-            }
-        }
-    }
 
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
@@ -139,6 +132,17 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // everything above (barriers, tensor memory, descriptor prefetch) overlapped the previous kernel's tail; from here
+    // on this grid reads what that kernel wrote (pdl.cuh)
+    pdl_enter();
+    if (fmode == 2) {
+        for (int i = threadIdx.x; i < p.fuse_groups * fC; i += blockDim.x) {
+            const int g = i / fC, c = i - g * fC;
+            const float* st = p.fuse_stats + static_cast<size_t>(g) * 4 * fC;
+            s_prm[i] = make_float4(__ldg(st + c), __ldg(st + fC + c), __ldg(st + 2 * fC + c), __ldg(st + 3 * fC + c));
+        }
+        __syncthreads();
+    }
 
     // item -> coordinates (m fastest: consecutive CTAs share the same weight tile)
     auto decode = [&](int item, int& i0, int& j0, int& b0, int& n0, int& phase, int& it_begin, int& iters) {
@@ -646,6 +650,7 @@ __device__ __forceinline__ void wgrad_body(const WgradParams& p) {
     if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_enter();                           // (pdl.cuh: the prologue above ran under the previous kernel's tail)
 
     const bool leader = lane == 0;        // see igemm_fprop_kernel: all lanes run the loops, lane 0 issues
     if (warp == 0) {
@@ -931,6 +936,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads)
 // split range is cut into gridDim.y chunks whose sums are combined with fp32 atomics (CHUNKED = true).
 template <int VEC, bool CHUNKED>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) {
+    pdl_enter();
     const int tap_units = p.num_taps / VEC;
     const long long total = static_cast<long long>(p.m_valid) * p.n_valid * tap_units;
     const int rows_per_tile = p.m_atoms * p.p_atom_c;
@@ -975,6 +981,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradParams p) 
 
 __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, void* out,
                                      int out_fp32, size_t n, int C) {
+    pdl_enter();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         float v = acc[i];
@@ -1021,25 +1028,25 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     }
     if (p.halo) {
         switch (p.fuse_mode) {
-            case 1: igemm_fprop_kernel<1, true><<<grid, threads, smem, stream>>>(p); break;
-            case 2: igemm_fprop_kernel<2, true><<<grid, threads, smem, stream>>>(p); break;
-            case 3: igemm_fprop_kernel<3, true><<<grid, threads, smem, stream>>>(p); break;
-            case 4: igemm_fprop_kernel<4, true><<<grid, threads, smem, stream>>>(p); break;
-            default: igemm_fprop_kernel<0, true><<<grid, threads, smem, stream>>>(p); break;
+            case 1: launch_k(igemm_fprop_kernel<1, true>, dim3(grid), dim3(threads), smem, stream, p); break;
+            case 2: launch_k(igemm_fprop_kernel<2, true>, dim3(grid), dim3(threads), smem, stream, p); break;
+            case 3: launch_k(igemm_fprop_kernel<3, true>, dim3(grid), dim3(threads), smem, stream, p); break;
+            case 4: launch_k(igemm_fprop_kernel<4, true>, dim3(grid), dim3(threads), smem, stream, p); break;
+            default: launch_k(igemm_fprop_kernel<0, true>, dim3(grid), dim3(threads), smem, stream, p); break;
         }
     } else
     switch (p.fuse_mode) {
-        case 1: igemm_fprop_kernel<1><<<grid, threads, smem, stream>>>(p); break;
-        case 2: igemm_fprop_kernel<2><<<grid, threads, smem, stream>>>(p); break;
-        case 3: igemm_fprop_kernel<3><<<grid, threads, smem, stream>>>(p); break;
-        case 4: igemm_fprop_kernel<4><<<grid, threads, smem, stream>>>(p); break;
-        default: igemm_fprop_kernel<0><<<grid, threads, smem, stream>>>(p); break;
+        case 1: launch_k(igemm_fprop_kernel<1>, dim3(grid), dim3(threads), smem, stream, p); break;
+        case 2: launch_k(igemm_fprop_kernel<2>, dim3(grid), dim3(threads), smem, stream, p); break;
+        case 3: launch_k(igemm_fprop_kernel<3>, dim3(grid), dim3(threads), smem, stream, p); break;
+        case 4: launch_k(igemm_fprop_kernel<4>, dim3(grid), dim3(threads), smem, stream, p); break;
+        default: launch_k(igemm_fprop_kernel<0>, dim3(grid), dim3(threads), smem, stream, p); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     if (ksplit > 1) {
         const int blocks = static_cast<int>(std::min<size_t>((out_elems + 255) / 256, 148 * 8));
-        splitk_finish_kernel<<<blocks, 256, 0, stream>>>(p.splitk_acc, p.bias, p.out, p.out_fp32, out_elems, p.out_C);
+        launch_k(splitk_finish_kernel, dim3(blocks), dim3(256), 0, stream, p.splitk_acc, p.bias, p.out, p.out_fp32, out_elems, p.out_C);
         e = cudaGetLastError();
     }
     return static_cast<int>(e);
@@ -1063,10 +1070,10 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     cudaError_t e;
     if (p.pair) {
         const dim3 pgrid(p.m_tiles * p.n_tiles, p.splits, tap_groups);          // cluster (2, 1, 1) from the kernel attribute
-        igemm_wgrad_pair_kernel<<<pgrid, kIgemmThreads, smem, stream>>>(p);
+        launch_k(igemm_wgrad_pair_kernel, dim3(pgrid), dim3(kIgemmThreads), smem, stream, p);
         e = cudaGetLastError();
     } else {
-        igemm_wgrad_kernel<<<grid, kIgemmThreads, smem, stream>>>(p);
+        launch_k(igemm_wgrad_kernel, dim3(grid), dim3(kIgemmThreads), smem, stream, p);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess || p.splits <= 1 || p.atomic_split) return static_cast<int>(e);
@@ -1075,11 +1082,11 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
     const dim3 rgrid(blocks, chunked ? std::min(p.splits / 4, 32) : 1);
     if (p.vec4_taps) {
-        if (chunked) wgrad_reduce_kernel<4, true><<<rgrid, 256, 0, stream>>>(p);
-        else wgrad_reduce_kernel<4, false><<<rgrid, 256, 0, stream>>>(p);
+        if (chunked) launch_k(wgrad_reduce_kernel<4, true>, dim3(rgrid), dim3(256), 0, stream, p);
+        else launch_k(wgrad_reduce_kernel<4, false>, dim3(rgrid), dim3(256), 0, stream, p);
     } else {
-        if (chunked) wgrad_reduce_kernel<1, true><<<rgrid, 256, 0, stream>>>(p);
-        else wgrad_reduce_kernel<1, false><<<rgrid, 256, 0, stream>>>(p);
+        if (chunked) launch_k(wgrad_reduce_kernel<1, true>, dim3(rgrid), dim3(256), 0, stream, p);
+        else launch_k(wgrad_reduce_kernel<1, false>, dim3(rgrid), dim3(256), 0, stream, p);
     }
     return static_cast<int>(cudaGetLastError());
 }

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "pdl.cuh"
 #include "vec.cuh"
 
 namespace vg {
@@ -50,6 +51,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                                                          const float* __restrict__ eps, int n, int batch,
                                                          T* __restrict__ z, float* __restrict__ kl_out) {
+    pdl_enter();
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) reparam_bwd_kernel(const T* __restri
                                                               const float* __restrict__ eps, int n, int batch,
                                                               const float* __restrict__ kl_weight_ptr, float kl_weight,
                                                               float* __restrict__ dmu, float* __restrict__ dlogvar) {
+    pdl_enter();
     const float w = (kl_weight_ptr ? *kl_weight_ptr : kl_weight) / batch;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float g;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(kThreads) reparam_bwd_kernel(const T* __restri
 __global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ p, int n, float target, float weight,
                                                   float* __restrict__ loss_out, int accumulate,
                                                   float* __restrict__ dp) {
+    pdl_enter();
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) mse_partial_kernel(const float* __re
                                                               const float* __restrict__ grad_in,
                                                               float* __restrict__ grad_out,
                                                               double* __restrict__ partial) {
+    pdl_enter();
     __shared__ double red[32];
     double acc = 0.0;
     const float gs = 2.f * weight / static_cast<float>(n);
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(kThreads) mse_partial_kernel(const float* __re
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 __global__ void mse_finalize_kernel(const double* partial, int blocks, long long n, float* loss_out) {
+    pdl_enter();
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < blocks; i += blockDim.x) acc += partial[i];
@@ -159,6 +165,7 @@ __global__ void mse_finalize_kernel(const double* partial, int blocks, long long
 __global__ void __launch_bounds__(1024) bce_pair_kernel(const float* __restrict__ p, int n, float t_real, float t_fake,
                                                        float weight, float* __restrict__ loss_out,
                                                        float* __restrict__ dp) {
+    pdl_enter();
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(kThreads) mse_total_kernel(const T* __restrict
                                                             const float* __restrict__ kl, const float* __restrict__ adv,
                                                             const float* __restrict__ w_kl_ptr, float w_adv,
                                                             float* __restrict__ total_out, MseAcc* __restrict__ ws) {
+    pdl_enter();
     constexpr int V = Vec<T>::N;
     __shared__ double red[32];
     double acc = 0.0;
@@ -235,17 +243,19 @@ __global__ void __launch_bounds__(kThreads) mse_total_kernel(const T* __restrict
 // total = recon + w_kl * kl + w_adv * adv   (vaegan_code.py:117), all scalars on the device
 __global__ void total_loss_kernel(const float* recon, const float* kl, const float* adv, const float* w_kl_ptr,
                                   float w_kl, float w_adv, float* total) {
+    pdl_enter();
     const float wk = w_kl_ptr ? *w_kl_ptr : w_kl;
     *total = *recon + wk * *kl + w_adv * *adv;
 }
 
 // ---- Adam (torch.optim.Adam defaults path: no amsgrad, no weight decay), one flat buffer per optimizer
-__global__ void adam_tick_kernel(long long* step) { *step += 1; }
+__global__ void adam_tick_kernel(long long* step) { pdl_enter(); *step += 1; }
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, long long n,
                                                        double lr_d, double b1_d, double b2_d, double eps_d,
                                                        const long long* __restrict__ step_ptr, float grad_scale) {
+    pdl_enter();
     // hyper-parameters arrive as doubles and are narrowed exactly where torch narrows its Python floats
     const double t = static_cast<double>(*step_ptr);
     const float b1 = static_cast<float>(b1_d), b2 = static_cast<float>(b2_d), eps = static_cast<float>(eps_d);
@@ -295,6 +305,7 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
 __global__ void __launch_bounds__(kThreads) randn_kernel(float* __restrict__ out, long long n, unsigned long long seed,
                                                         const unsigned long long* __restrict__ offset_ptr,
                                                         unsigned long long stream_id) {
+    pdl_enter();
     const unsigned long long off = offset_ptr ? *offset_ptr : 0ull;
     const long long nquad = (n + 3) / 4;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nquad;
@@ -320,7 +331,7 @@ __global__ void __launch_bounds__(kThreads) randn_kernel(float* __restrict__ out
             if (i * 4 + j < n) out[i * 4 + j] = z[j];
     }
 }
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { pdl_enter(); *c += inc; }
 
 int grid_for(long long n) {
     return static_cast<int>(std::max<long long>(1, std::min<long long>(148 * 8, (n + kThreads - 1) / kThreads)));
@@ -339,11 +350,9 @@ extern "C" int vg_reparam_fwd(const float* mu, const float* logvar, const float*
         return fail(VG_ERR_ARG, "reparam_fwd: null pointer");
     const int n = batch * nz;
     if (z_dt == VG_BF16)
-        reparam_fwd_kernel<__nv_bfloat16><<<std::max(1, std::min(148, (n + 255) / 256)), 256, 0, as_stream(stream)>>>(
-            mu, logvar, eps, n, batch, static_cast<__nv_bfloat16*>(z), kl_out);
+        launch_k(reparam_fwd_kernel<__nv_bfloat16>, dim3(std::max(1, std::min(148, (n + 255) / 256))), dim3(256), 0, as_stream(stream), mu, logvar, eps, n, batch, static_cast<__nv_bfloat16*>(z), kl_out);
     else
-        reparam_fwd_kernel<float><<<std::max(1, std::min(148, (n + 255) / 256)), 256, 0, as_stream(stream)>>>(
-            mu, logvar, eps, n, batch, static_cast<float*>(z), kl_out);
+        launch_k(reparam_fwd_kernel<float>, dim3(std::max(1, std::min(148, (n + 255) / 256))), dim3(256), 0, as_stream(stream), mu, logvar, eps, n, batch, static_cast<float*>(z), kl_out);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -357,11 +366,9 @@ extern "C" int vg_reparam_bwd(const void* dz, VgDType dz_dt, const float* mu, co
         return fail(VG_ERR_ARG, "reparam_bwd: null pointer");
     const int n = batch * nz;
     if (dz_dt == VG_BF16)
-        reparam_bwd_kernel<__nv_bfloat16><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(
-            static_cast<const __nv_bfloat16*>(dz), mu, logvar, eps, n, batch, kl_weight_dev, kl_weight, dmu, dlogvar);
+        launch_k(reparam_bwd_kernel<__nv_bfloat16>, dim3(grid_for(n)), dim3(kThreads), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(dz), mu, logvar, eps, n, batch, kl_weight_dev, kl_weight, dmu, dlogvar);
     else
-        reparam_bwd_kernel<float><<<grid_for(n), kThreads, 0, as_stream(stream)>>>(
-            static_cast<const float*>(dz), mu, logvar, eps, n, batch, kl_weight_dev, kl_weight, dmu, dlogvar);
+        launch_k(reparam_bwd_kernel<float>, dim3(grid_for(n)), dim3(kThreads), 0, as_stream(stream), static_cast<const float*>(dz), mu, logvar, eps, n, batch, kl_weight_dev, kl_weight, dmu, dlogvar);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -371,7 +378,7 @@ extern "C" int vg_bce(const float* p, int n, float target, float weight, float* 
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (p == nullptr) return fail(VG_ERR_ARG, "bce: null pointer");
-    bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(p, n, target, weight, loss_out, accumulate, dp);
+    launch_k(bce_kernel, dim3(1), dim3(1024), 0, as_stream(stream), p, n, target, weight, loss_out, accumulate, dp);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -381,7 +388,7 @@ extern "C" int vg_bce_pair(const float* p, int n, float target_real, float targe
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (p == nullptr) return fail(VG_ERR_ARG, "bce_pair: null pointer");
-    bce_pair_kernel<<<1, 1024, 0, as_stream(stream)>>>(p, n, target_real, target_fake, weight, loss_out, dp);
+    launch_k(bce_pair_kernel, dim3(1), dim3(1024), 0, as_stream(stream), p, n, target_real, target_fake, weight, loss_out, dp);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -400,13 +407,11 @@ extern "C" int vg_mse_total(const void* a, const void* b, VgDType dt, long long 
     if (n % V != 0) return fail(VG_ERR_SHAPE, "mse_total: element count must be a multiple of %d", V);
     const int blocks = grid_for(n / V);
     if (dt == VG_BF16)
-        mse_total_kernel<__nv_bfloat16><<<blocks, kThreads, 0, as_stream(stream)>>>(
-            static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), n, weight,
+        launch_k(mse_total_kernel<__nv_bfloat16>, dim3(blocks), dim3(kThreads), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), n, weight,
             static_cast<const __nv_bfloat16*>(grad_in), static_cast<__nv_bfloat16*>(grad_out), loss_out, kl, adv,
             w_kl_dev, w_adv, total_out, static_cast<MseAcc*>(ws));
     else
-        mse_total_kernel<float><<<blocks, kThreads, 0, as_stream(stream)>>>(
-            static_cast<const float*>(a), static_cast<const float*>(b), n, weight, static_cast<const float*>(grad_in),
+        launch_k(mse_total_kernel<float>, dim3(blocks), dim3(kThreads), 0, as_stream(stream), static_cast<const float*>(a), static_cast<const float*>(b), n, weight, static_cast<const float*>(grad_in),
             static_cast<float*>(grad_out), loss_out, kl, adv, w_kl_dev, w_adv, total_out, static_cast<MseAcc*>(ws));
     VG_LAUNCHED();
     return VG_OK;
@@ -424,10 +429,10 @@ extern "C" int vg_mse(const float* a, const float* b, long long n, float weight,
          reinterpret_cast<uintptr_t>(grad_out)) & 15)
         return fail(VG_ERR_ALIGN, "mse: 16-byte alignment");
     const int blocks = grid_for(n / 4 + 1);
-    mse_partial_kernel<<<blocks, kThreads, 0, as_stream(stream)>>>(a, b, n, weight, grad_in, grad_out,
+    launch_k(mse_partial_kernel, dim3(blocks), dim3(kThreads), 0, as_stream(stream), a, b, n, weight, grad_in, grad_out,
                                                                    static_cast<double*>(ws));
     VG_LAUNCHED();
-    mse_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(static_cast<const double*>(ws), blocks, n, loss_out);
+    launch_k(mse_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), static_cast<const double*>(ws), blocks, n, loss_out);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -436,7 +441,7 @@ extern "C" int vg_total_loss(const float* recon, const float* kl, const float* a
                              float w_adv, float* total, void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;
-    total_loss_kernel<<<1, 1, 0, as_stream(stream)>>>(recon, kl, adv, w_kl_dev, w_kl, w_adv, total);
+    launch_k(total_loss_kernel, dim3(1), dim3(1), 0, as_stream(stream), recon, kl, adv, w_kl_dev, w_kl, w_adv, total);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -450,9 +455,9 @@ extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long l
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
          reinterpret_cast<uintptr_t>(v)) & 15)
         return fail(VG_ERR_ALIGN, "adam: 16-byte alignment");
-    adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+    launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_dev);
     VG_LAUNCHED();
-    adam_kernel<<<grid_for(n / 4 + 1), kThreads, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
+    launch_k(adam_kernel, dim3(grid_for(n / 4 + 1)), dim3(kThreads), 0, as_stream(stream), p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
                                                                          grad_scale);
     VG_LAUNCHED();
     return VG_OK;
@@ -463,10 +468,10 @@ extern "C" int vg_randn(float* out, long long n, unsigned long long seed, unsign
     int rc = device_check();
     if (rc != VG_OK) return rc;
     if (out == nullptr) return fail(VG_ERR_ARG, "randn: null pointer");
-    randn_kernel<<<grid_for((n + 3) / 4), kThreads, 0, as_stream(stream)>>>(out, n, seed, offset_dev, stream_id);
+    launch_k(randn_kernel, dim3(grid_for((n + 3) / 4)), dim3(kThreads), 0, as_stream(stream), out, n, seed, offset_dev, stream_id);
     VG_LAUNCHED();
     if (offset_dev != nullptr) {
-        counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(offset_dev, 1ull);
+        launch_k(counter_add_kernel, dim3(1), dim3(1), 0, as_stream(stream), offset_dev, 1ull);
         VG_LAUNCHED();
     }
     return VG_OK;
