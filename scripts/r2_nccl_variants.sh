@@ -18,8 +18,6 @@ except Exception as e:
 PY
 }
 run ""
-run "VG_PDL=0"
 run "NCCL_ALGO=allreduce:nvls"
 run "NCCL_ALGO=allreduce:nvlstree"
 run "NCCL_ALGO=allreduce:ring NCCL_PROTO=Simple"
-run "NCCL_ALGO=allreduce:tree"
