@@ -297,14 +297,21 @@ def run_gpu_arm(args):
                      "gflop_per_launch": dom["gflop_per_launch"], "us_per_launch": dom["us_per_launch"],
                      "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                      "share_of_step": dom["share"], "share_basis": "sum of this kernel's event-bracketed launch times / "
-                     "sum over all %d C-ABI calls of the step (%.2f ms serialised; the graph overlaps the wgrad "
-                     "stream and replays in %.2f ms)" % (dom["timed_calls"], dom["timed_ms"], dom["graph_ms_per_step"]),
+                     "sum over all %d C-ABI calls of the step (%.2f ms %s; the graph overlaps the wgrad "
+                     "streams and replays in %.2f ms)" % (dom["timed_calls"], dom["timed_ms"],
+                                                         "serialised on one stream" if dom["serialised"] else
+                                                         "with the wgrad streams overlapping", dom["graph_ms_per_step"]),
                      "traffic_source": dom["traffic_source"],
                      "what": "dominant kernel = the tcgen05 implicit-GEMM kernel behind every forward / dgrad "
                              "contraction: algorithmic FLOPs (2 x MACs over the valid channels) of its launches in one "
-                             "step / their summed durations (CUDA events around each launch, eager replay of the same "
-                             "step, wgrad stream overlapping as in the graph); peak = sustained bf16, "
-                             + peaks["source"],
+                             "step / their summed durations (CUDA events around each launch on its stream, eager "
+                             "replay of the same step"
+                             + (", all kernels on one stream so that a launch is timed alone" if dom["serialised"] else
+                                ", wgrad streams overlapping as in the graph")
+                             + "; `in_step_overlapped` = the same launches while a weight-gradient kernel shares the "
+                             "SMs); peak = sustained bf16, " + peaks["source"],
+                     "in_step_overlapped": dom["overlapped"],
+                     "per_launch": dom["per_launch"],
                      "wgrad_kernel": dom["wgrad"],
                      "whole_step": {"achieved": achieved_tflops, "frac": achieved_tflops / peaks["sustained"],
                                     "what": "6.245 GFLOP/image x batch / step time"},
@@ -457,39 +464,62 @@ def _finish(world: int):
 
 def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):
     """Every C-ABI call of one eagerly replayed step bracketed by CUDA events on its launching stream
-    (vaegan_b200._lib.LaunchTimer); the tcgen05 fprop-type kernel's launches are summed for the roofline."""
+    (vaegan_b200._lib.LaunchTimer); the tcgen05 fprop-type kernel's launches are summed for the roofline.
+    Two passes: (a) every kernel on ONE stream - a launch's event pair then brackets that kernel alone, back to back
+    with its neighbours of the step (what the roofline fraction of a KERNEL means; only at world == 1, the bucketed
+    all-reduce needs its streams), (b) the product schedule, weight gradients on their side streams - the same launches
+    while they share the SMs with a concurrent wgrad kernel (what each launch costs on the step's critical path)."""
     from importlib import import_module
     lib = import_module("vaegan_b200._lib")
-    was_graph = step.use_graph
-    step.use_graph = False
-    try:
+
+    def one_pass():
         step.step(batch, epoch)                      # eager warm-up of this code path
         torch.cuda.synchronize()
         lib.LaunchTimer.start()
         step.step(batch, epoch)
         recs = lib.LaunchTimer.stop()
+        all_ms = sum(r[-1] for r in recs)
+        out = {"timed_calls": len(recs), "timed_ms": all_ms}
+        for kind in ("fprop", "wgrad"):
+            sel = [(f, nb, ms) for _, tag, f, nb, ms in recs if tag == kind]
+            n, flops, nb, ms = len(sel), sum(r[0] for r in sel), sum(r[1] for r in sel), sum(r[2] for r in sel)
+            out[kind] = {"launches": n, "gflop_per_launch": flops / n / 1e9, "us_per_launch": ms / n * 1e3,
+                         "tflops": flops / (ms * 1e-3) / 1e12, "ms_per_step": ms,
+                         "algorithmic_bytes_per_launch": nb / n, "share": ms / all_ms}
+        out["per_launch"] = [{"call": name, "kind": tag, "gflop": round(f / 1e9, 3), "us": round(ms * 1e3, 2),
+                              "tflops": round(f / (ms * 1e-3) / 1e12, 1)}
+                             for name, tag, f, nb, ms in recs if tag in ("fprop", "wgrad")]
+        return out
+
+    was_graph, sides = step.use_graph, step.wgrad_streams
+    step.use_graph = False
+    try:
+        overlapped = one_pass()
+        alone = None
+        if step.world == 1:
+            step.wgrad_streams = []
+            alone = one_pass()
     finally:
-        step.use_graph = was_graph
-    all_ms = sum(r[-1] for r in recs)
-    out = {}
-    for kind in ("fprop", "wgrad"):
-        sel = [(f, nb, ms) for _, tag, f, nb, ms in recs if tag == kind]
-        n, flops, nb, ms = len(sel), sum(r[0] for r in sel), sum(r[1] for r in sel), sum(r[2] for r in sel)
-        out[kind] = {"launches": n, "gflop_per_launch": flops / n / 1e9, "us_per_launch": ms / n * 1e3,
-                     "tflops": flops / (ms * 1e-3) / 1e12, "ms_per_step": ms, "algorithmic_bytes_per_launch": nb / n}
+        step.use_graph, step.wgrad_streams = was_graph, sides
     traffic, src = None, "no ncu capture committed"
     path = os.path.join(ROOT, "profiles", "fprop_traffic.json")
     if os.path.isfile(path):
         with open(path) as f:
             t = json.load(f)
         traffic, src = t["dram_bytes_per_launch"], t["source"]
-    d = out["fprop"]
+    main = alone or overlapped
+    d = main["fprop"]
     return {"tflops": d["tflops"], "launches": d["launches"], "gflop_per_launch": d["gflop_per_launch"],
-            "us_per_launch": d["us_per_launch"], "share": d["ms_per_step"] / all_ms,
+            "us_per_launch": d["us_per_launch"], "share": d["share"],
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
-            "timed_calls": len(recs), "timed_ms": all_ms, "graph_ms_per_step": graph_ms_per_step,
+            "timed_calls": main["timed_calls"], "timed_ms": main["timed_ms"], "graph_ms_per_step": graph_ms_per_step,
+            "serialised": alone is not None, "per_launch": main["per_launch"],
             "traffic": traffic, "traffic_source": src,
-            "wgrad": {k: out["wgrad"][k] for k in ("launches", "gflop_per_launch", "us_per_launch", "tflops")}}
+            "wgrad": {k: main["wgrad"][k] for k in ("launches", "gflop_per_launch", "us_per_launch", "tflops")},
+            "overlapped": {"fprop": {k: overlapped["fprop"][k] for k in ("launches", "us_per_launch", "tflops")},
+                           "wgrad": {k: overlapped["wgrad"][k] for k in ("launches", "us_per_launch", "tflops")},
+                           "what": "the same launches in the product schedule: weight gradients run on side streams "
+                                   "and share the SMs with the forward / dgrad launch that is timed"}}
 
 
 def _kernel_microbench(torch, vb, dev):

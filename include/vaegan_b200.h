@@ -110,13 +110,17 @@ int vg_conv_up(const VgConvGeom* g, VgDType dtype, const void* small, const void
  *   VG_EPI_ACT_BWD   out = dy*act'(x)                                                      (layer without BatchNorm)
  *   VG_EPI_ACT_FWD   out = act(conv)  (ReLU / LeakyReLU of a layer without BatchNorm; its backward takes act' from
  *                                      the sign of the activated output, so the raw output is never stored)
+ *   VG_EPI_AFFINE_ACT_FWD  out = act(conv*scale[c] + shift[c])  (eval-mode BatchNorm + activation of the generation /
+ *                                      validation passes, main_vae.py:348-374, vaegan_code.py:147-171: scale / shift =
+ *                                      rows 2 / 3 of `stats` as vg_bn_eval_coeffs writes them; no separate pass)
  * `groups` = independent sub-batches along the batch axis with separate statistics; `sums` = fp32
  * [groups][2][channels], zero-initialised by the caller, accumulated with atomics; `x` = the saved raw convolution
  * output (same NHWC shape as this call's output); `stats` = [groups][4][channels] (mean, rstd, scale, shift).
  * vg_conv_epilogue_supported() tells whether a geometry takes the fused form (1) or the caller has to use the
  * stand-alone reduction kernels below (0). */
 typedef enum VgEpilogueMode {
-    VG_EPI_NONE = 0, VG_EPI_BN_STATS = 1, VG_EPI_BN_BWD = 2, VG_EPI_ACT_BWD = 3, VG_EPI_ACT_FWD = 4
+    VG_EPI_NONE = 0, VG_EPI_BN_STATS = 1, VG_EPI_BN_BWD = 2, VG_EPI_ACT_BWD = 3, VG_EPI_ACT_FWD = 4,
+    VG_EPI_AFFINE_ACT_FWD = 5
 } VgEpilogueMode;
 typedef struct VgEpilogue {
     int32_t mode;      /* VgEpilogueMode */
@@ -270,6 +274,34 @@ int vg_mse_total(const void* a, const void* b, VgDType dt, long long n, float we
 /* total = recon + w_kl*kl + w_adv*adv  (vaegan_code.py:117); w_kl read from the device if w_kl_dev != NULL. */
 int vg_total_loss(const float* recon, const float* kl, const float* adv, const float* w_kl_dev, float w_kl,
                   float w_adv, float* total, void* stream);
+/* ---- data-parallel optimizer step over NVLink / NVSwitch peer memory (csrc/dp_comm.cu) -------------------------
+ * The reference trains on one device (vaegan_code.py:28); its data-parallel extension averages the gradients of N
+ * replicas before the three optim.Adam steps (vaegan_code.py:105,134-135).  The flat gradient / parameter buffers of
+ * a network live in symmetric memory: `peer_*[r]` = rank r's buffer mapped into this process, `mc_*` = the NVSwitch
+ * multicast mapping of the same buffers (both NULL: peer loads / stores instead of multimem instructions),
+ * `peer_sig[r]` = rank r's signal pad (vg_dp_max_blocks() * world uint32, zeroed once), `epoch` = 2 local uint32
+ * (zeroed once).  vg_dp_adam_bucket: elements [lo, lo + n) of the buffers - reduce-scatter of the gradients, Adam on
+ * this rank's 1/world slice (m, v: this rank's moment buffers, full length, only the slice is touched), all-gather
+ * of the new parameters, in ONE kernel.  Every rank must launch the same sequence of calls.  *step_dev as in
+ * vg_adam_step but NOT incremented here (the caller ticks it once per optimizer step).  write_grads != 0 also
+ * leaves the summed gradient in every replica (parity tests).  *err_flag is set if a cross-GPU barrier times out. */
+#define VG_DP_MAX_RANKS 8
+typedef struct VgDpComm {
+    float* mc_grads;
+    float* mc_params;
+    float* peer_grads[VG_DP_MAX_RANKS];
+    float* peer_params[VG_DP_MAX_RANKS];
+    unsigned int* peer_sig[VG_DP_MAX_RANKS];
+    unsigned int* epoch;
+    int rank;
+    int world;
+} VgDpComm;
+int vg_dp_max_blocks(void);
+int vg_dp_adam_bucket(const VgDpComm* comm, long long lo, long long n, float* m, float* v, double lr, double beta1,
+                      double beta2, double eps, const long long* step_dev, float grad_scale, int blocks,
+                      int write_grads, int* err_flag, void* stream);
+/* *step_dev += 1 (the tick vg_adam_step does itself). */
+int vg_adam_tick(long long* step_dev, void* stream);
 /* torch.optim.Adam.step (vaegan_code.py:42-44,105,134-135) over one flat fp32 buffer; *step_dev is incremented
  * first and drives the bias corrections, so the call can be replayed from a CUDA graph.  g is multiplied by
  * grad_scale (1/world_size under data parallelism). */

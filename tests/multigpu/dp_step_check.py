@@ -39,20 +39,30 @@ def main():
     real, eps, n_real, n_fake = (t.to(dev) for t in vo.make_inputs(per, hw, nz, seed=100 + rank))   # this rank's shard
     ok = True
     report = []
-    for graph in (False, True):
-        dp_step = VAEGANStep(*nets(7), use_cuda_graph=graph, capture_grads=True)
+    # transports: the peer-memory kernel (multimem instructions when the fabric has a multicast mapping), the same
+    # kernel restricted to peer loads / stores, and NCCL all-reduce + replicated Adam - all must give the same step
+    final_params = {}
+    for transport in ("peer", "peer-nomc", "nccl"):
+      for graph in (False, True):
+        dp_step = VAEGANStep(*nets(7), use_cuda_graph=graph, capture_grads=True, dp_transport=transport)
         assert dp_step.world == world and len(dp_step.buckets["G"].buckets) >= 2 and len(dp_step.buckets["D"].buckets) >= 2
+        if transport != "nccl":
+            assert dp_step.peer is not None and len(dp_step.peer_adam) == 3
+            if rank == 0 and not graph:
+                print(f"transport {transport}: multicast = {dp_step.peer_adam['G'].multicast}", flush=True)
         solo = VAEGANStep(*nets(7), use_cuda_graph=graph, capture_grads=True, process_group=solo_group)
         assert solo.world == 1
         l_dp = dp_step.step(real, 50, eps, n_real, n_fake)
         l_solo = solo.step(real, 50, eps, n_real, n_fake)
         torch.cuda.synchronize()
+        if dp_step.peer is not None:
+            dp_step.peer.check()
         # d_loss_0 / recon / kl are computed before any all-reduced update: identical to the solo replica's
         for k in ("d_loss_0", "recon", "kl"):
             a, b = float(l_dp[k]), float(l_solo[k])
             if not abs(a - b) <= 1e-3 * abs(b) + 1e-6:
                 ok = False
-                print(f"rank {rank} graph {graph}: loss {k} dp {a} solo {b}", flush=True)
+                print(f"rank {rank} {transport} graph {graph}: loss {k} dp {a} solo {b}", flush=True)
         g_dp, g_solo = dp_step.gradients(), solo.gradients()
         # first discriminator update: DP gradient (summed over ranks) == sum of the solo replicas' gradients
         mine = torch.cat([v.flatten() for v in g_solo["D"][0].values()])
@@ -61,18 +71,38 @@ def main():
         got = torch.cat([v.flatten() for v in g_dp["D"][0].values()])
         cos = float(torch.dot(got.double(), total.double()) / (got.double().norm() * total.double().norm()))
         rel = float((got - total).norm() / total.norm())
-        report.append((graph, cos, rel))
+        report.append((transport, graph, cos, rel))
         if not (cos > 0.999999 and rel < 1e-3):
             ok = False
-            print(f"rank {rank} graph {graph}: D gradient cos {cos} rel {rel}", flush=True)
+            print(f"rank {rank} {transport} graph {graph}: D gradient cos {cos} rel {rel}", flush=True)
         # replicas stay in lock-step: parameters identical on every rank after the step
         for opt in (dp_step.opt_E, dp_step.opt_G, dp_step.opt_D):
             ref = opt.params.clone()
             dist.broadcast(ref, 0)
             if not torch.equal(ref, opt.params):
                 ok = False
-                print(f"rank {rank} graph {graph}: parameters differ from rank 0 "
+                print(f"rank {rank} {transport} graph {graph}: parameters differ from rank 0 "
                       f"(max {float((ref - opt.params).abs().max())})", flush=True)
+        # ... and every transport takes the same step: Adam's first update is ~lr * sign(g), so all but the elements
+        # whose summed gradient is ~0 (its sign is summation-order noise) must agree far inside one lr
+        flat = torch.cat([o.params.clone() for o in (dp_step.opt_E, dp_step.opt_G, dp_step.opt_D)])
+        prev = final_params.setdefault(graph, (transport, flat))
+        if prev[0] != transport:
+            bad = int(((flat - prev[1]).abs() > 1e-4).sum())
+            if bad > 0.002 * flat.numel():
+                ok = False
+                print(f"rank {rank} graph {graph}: {bad}/{flat.numel()} parameters differ between transports "
+                      f"{prev[0]} and {transport}", flush=True)
+        # sharded optimizer state: after gather_moments every rank holds every slice
+        if transport != "nccl" and not graph:
+            sd = dp_step.state_dict()
+            mom = torch.cat([t.flatten() for t in sd["opt_G"]["exp_avg"]])
+            ref = mom.clone()
+            dist.broadcast(ref, 0)
+            if not torch.equal(ref, mom) or float(mom.abs().sum()) == 0.0:
+                ok = False
+                print(f"rank {rank} {transport}: gathered Adam moments differ across ranks", flush=True)
+        del dp_step, solo
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -34,8 +34,18 @@ class VgEpilogue(Structure):
                 ("sums", c_void_p), ("x", c_void_p), ("stats", c_void_p)]
 
 
+DP_MAX_RANKS = 8
+
+
+class VgDpComm(Structure):
+    """include/vaegan_b200.h: symmetric-memory mappings of one network's flat gradient / parameter buffers."""
+    _fields_ = [("mc_grads", c_void_p), ("mc_params", c_void_p), ("peer_grads", c_void_p * DP_MAX_RANKS),
+                ("peer_params", c_void_p * DP_MAX_RANKS), ("peer_sig", c_void_p * DP_MAX_RANKS), ("epoch", c_void_p),
+                ("rank", c_int32), ("world", c_int32)]
+
+
 WGRAD_OVERWRITE, WGRAD_DST_ZERO = 1, 2
-EPI_NONE, EPI_BN_STATS, EPI_BN_BWD, EPI_ACT_BWD, EPI_ACT_FWD = 0, 1, 2, 3, 4
+EPI_NONE, EPI_BN_STATS, EPI_BN_BWD, EPI_ACT_BWD, EPI_ACT_FWD, EPI_AFFINE_ACT_FWD = 0, 1, 2, 3, 4, 5
 
 # name -> (restype, argtypes); mirrors include/vaegan_b200.h one to one
 _G = POINTER(VgConvGeom)
@@ -89,6 +99,10 @@ PROTOTYPES = {
     "vg_mse_total": (c_int, [_P, _P, c_int, c_longlong, c_float, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, _P]),
     "vg_total_loss": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P]),
     "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_double, c_double, c_double, c_double, _P, c_float, _P]),
+    "vg_adam_tick": (c_int, [_P, _P]),
+    "vg_dp_max_blocks": (c_int, []),
+    "vg_dp_adam_bucket": (c_int, [_P, c_longlong, c_longlong, _P, _P, c_double, c_double, c_double, c_double, _P, c_float,
+                                  c_int, c_int, _P, _P]),
     "vg_randn": (c_int, [_P, c_longlong, c_ulonglong, _P, c_ulonglong, _P]),
 }
 

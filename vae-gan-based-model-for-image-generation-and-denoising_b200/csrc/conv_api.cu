@@ -184,7 +184,19 @@ static int fuse_check(const VgConvGeom* g, bool up, const VgEpilogue* ep) {
         return fail(VG_ERR_SHAPE, "fused epilogue: this geometry does not run on the tensor-core path");
     int tw, th, tb, n_tile, n_total = g->small_c;
     if (up) up_tiling(g, &tw, &th, &tb, &n_tile, &n_total); else down_tiling(g, &tw, &th, &tb, &n_tile);
-    if (ep->mode < VG_EPI_BN_STATS || ep->mode > VG_EPI_ACT_FWD) return fail(VG_ERR_ARG, "fused epilogue: bad mode %d", ep->mode);
+    if (ep->mode < VG_EPI_BN_STATS || ep->mode > VG_EPI_AFFINE_ACT_FWD) return fail(VG_ERR_ARG, "fused epilogue: bad mode %d", ep->mode);
+    if (ep->mode == VG_EPI_AFFINE_ACT_FWD) {
+        const int C = ep->channels;
+        if (ep->stats == nullptr) return fail(VG_ERR_ARG, "fused epilogue: null scale / shift table");
+        if (ep->act != VG_ACT_NONE && ep->act != VG_ACT_RELU && ep->act != VG_ACT_LEAKY)
+            return fail(VG_ERR_SHAPE, "fused epilogue: only ReLU / LeakyReLU / identity ride the forward epilogue");
+        if (ep->groups > 1) return fail(VG_ERR_SHAPE, "fused epilogue: the affine form has one parameter group");
+        if (C <= 0 || C % 32 != 0 || n_tile % 32 != 0 || n_total % C != 0)
+            return fail(VG_ERR_SHAPE, "fused epilogue: %d channels / N tile %d not multiples of 32", C, n_tile);
+        if (static_cast<long long>(C) * 24 > 48 * 1024)
+            return fail(VG_ERR_SHAPE, "fused epilogue: %d-channel table exceeds the shared-memory budget", C);
+        return VG_OK;
+    }
     if (ep->mode == VG_EPI_ACT_FWD) {
         if (ep->act != VG_ACT_RELU && ep->act != VG_ACT_LEAKY)
             return fail(VG_ERR_SHAPE, "fused epilogue: only ReLU / LeakyReLU ride the forward epilogue");

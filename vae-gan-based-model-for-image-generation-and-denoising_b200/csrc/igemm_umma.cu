@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
     // everything above (barriers, tensor memory, descriptor prefetch) overlapped the previous kernel's tail; from here
     // on this grid reads what that kernel wrote (pdl.cuh)
     pdl_enter();
-    if (fmode == 2) {
+    if (fmode == 2 || fmode == 5) {
         for (int i = threadIdx.x; i < p.fuse_groups * fC; i += blockDim.x) {
             const int g = i / fC, c = i - g * fC;
             const float* st = p.fuse_stats + static_cast<size_t>(g) * 4 * fC;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                 }
                 // fused statistics: fuse_c and n_tile are multiples of 32, so a chunk never wraps around the channels
                 int ch0 = 0;
-                if (fmode == 1 || fmode == 2) ch0 = (n0 + c) % fC;
+                if (fmode == 1 || fmode == 2 || fmode == 5) ch0 = (n0 + c) % fC;
                 float xv[32];
                 if (mode23) {
 #pragma unroll
@@ -452,6 +452,22 @@ __global__ void __launch_bounds__(kIgemmMaxThreads) igemm_fprop_kernel(const __g
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] *= xv[j] > 0.f ? 1.f : neg_slope;
+                    }
+                }
+                if (fmode == 5) {
+                    // eval-mode BatchNorm folded into the forward epilogue: out = act(conv * scale[c] + shift[c]) from
+                    // the fp32 accumulator (the stand-alone pass it replaces re-read a bf16-rounded conv output)
+                    const float4* pr_base = s_prm + ch0;
+#pragma unroll
+                    for (int jb = 0; jb < 32; jb += 8) {
+                        float4 pr[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pr[j] = pr_base[jb + j];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float z = fmaf(f[jb + j], pr[j].z, pr[j].w);
+                            f[jb + j] = z > 0.f ? z : z * neg_slope;
+                        }
                     }
                 }
                 if (fmode == 4) {
@@ -1008,7 +1024,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         for (auto fn : {igemm_fprop_kernel<0>, igemm_fprop_kernel<1>, igemm_fprop_kernel<2>, igemm_fprop_kernel<3>,
-                        igemm_fprop_kernel<4>, igemm_fprop_kernel<0, true>, igemm_fprop_kernel<1, true>,
+                        igemm_fprop_kernel<4>, igemm_fprop_kernel<5>, igemm_fprop_kernel<5, true>,
+                        igemm_fprop_kernel<0, true>, igemm_fprop_kernel<1, true>,
                         igemm_fprop_kernel<2, true>, igemm_fprop_kernel<3, true>, igemm_fprop_kernel<4, true>}) {
             const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) attr_err = e;
@@ -1032,6 +1049,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
             case 2: launch_k(igemm_fprop_kernel<2, true>, dim3(grid), dim3(threads), smem, stream, p); break;
             case 3: launch_k(igemm_fprop_kernel<3, true>, dim3(grid), dim3(threads), smem, stream, p); break;
             case 4: launch_k(igemm_fprop_kernel<4, true>, dim3(grid), dim3(threads), smem, stream, p); break;
+            case 5: launch_k(igemm_fprop_kernel<5, true>, dim3(grid), dim3(threads), smem, stream, p); break;
             default: launch_k(igemm_fprop_kernel<0, true>, dim3(grid), dim3(threads), smem, stream, p); break;
         }
     } else
@@ -1040,6 +1058,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
         case 2: launch_k(igemm_fprop_kernel<2>, dim3(grid), dim3(threads), smem, stream, p); break;
         case 3: launch_k(igemm_fprop_kernel<3>, dim3(grid), dim3(threads), smem, stream, p); break;
         case 4: launch_k(igemm_fprop_kernel<4>, dim3(grid), dim3(threads), smem, stream, p); break;
+        case 5: launch_k(igemm_fprop_kernel<5>, dim3(grid), dim3(threads), smem, stream, p); break;
         default: launch_k(igemm_fprop_kernel<0>, dim3(grid), dim3(threads), smem, stream, p); break;
     }
     cudaError_t e = cudaGetLastError();

@@ -90,7 +90,7 @@ struct alignas(64) IgemmParams {
 // shared memory the fused epilogue adds to a CTA
 inline int igemm_fuse_smem_bytes(const IgemmParams& p) {
     if (p.fuse_mode == 1) return p.fuse_groups * 2 * p.fuse_c * 4;
-    if (p.fuse_mode == 2) return p.fuse_groups * p.fuse_c * (2 * 4 + 16);
+    if (p.fuse_mode == 2 || p.fuse_mode == 5) return p.fuse_groups * p.fuse_c * (2 * 4 + 16);
     return 0;
 }
 // shared memory of the TMA epilogue's staging slabs (+ the padding that aligns them to 1024 B)

@@ -463,6 +463,15 @@ extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long l
     return VG_OK;
 }
 
+extern "C" int vg_adam_tick(long long* step_dev, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (step_dev == nullptr) return fail(VG_ERR_ARG, "adam_tick: null pointer");
+    launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_dev);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
 extern "C" int vg_randn(float* out, long long n, unsigned long long seed, unsigned long long* offset_dev,
                         unsigned long long stream_id, void* stream) {
     int rc = device_check();

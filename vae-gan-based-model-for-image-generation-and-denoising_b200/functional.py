@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_ACT_BWD, EPI_ACT_FWD, EPI_BN_BWD,
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_ACT_BWD, EPI_ACT_FWD, EPI_AFFINE_ACT_FWD, EPI_BN_BWD,
                    EPI_BN_STATS, VG_BF16, VG_F32, VgConvGeom, VgEpilogue, call)
 
 _DT = {torch.float32: VG_F32, torch.bfloat16: VG_BF16}
@@ -129,7 +129,7 @@ def conv_down(big: torch.Tensor, w: torch.Tensor, g: VgConvGeom, bias: Optional[
     small = torch.empty((g.batch, g.small_h, g.small_w, g.small_c), dtype=out_dtype, device=big.device)
     if ep is not None:
         call("vg_conv_down_ex", ctypes.byref(g), _DT[big.dtype], _p(big), _p(w), _p(bias), _p(small), ctypes.byref(ep),
-             _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, 0, int(ep.mode >= 2)))
+             _stream(), flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, 0, int(ep.mode in (2, 3))))
         return small
     ws, nbytes = None, 0
     if big.dtype == torch.bfloat16 and g.batch * g.small_h * g.small_w <= 1024:      # few output tiles: allow split-K
@@ -144,7 +144,7 @@ def conv_up(small: torch.Tensor, w: torch.Tensor, g: VgConvGeom, ep: Optional[Vg
     big = torch.empty((g.batch, g.big_h, g.big_w, g.big_c), dtype=small.dtype, device=small.device)
     if ep is not None:
         call("vg_conv_up_ex", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), ctypes.byref(ep), _stream(),
-             flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, int(ep.mode >= 2), 0))
+             flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g, int(ep.mode in (2, 3)), 0))
     else:
         call("vg_conv_up", ctypes.byref(g), _DT[small.dtype], _p(small), _p(w), _p(big), _stream(),
              flops=conv_flops(g), tag=_conv_tag(g, "fprop"), nbytes=conv_bytes(g))
@@ -744,6 +744,17 @@ class ConvLayerFn(torch.autograd.Function):
             ep_act = make_epilogue(EPI_ACT_FWD, 1, 0, act, slope)
             if epilogue_supported(g, spec.kind == "up", ep_act):
                 ep, act_in_epilogue = ep_act, True
+        # eval-mode BatchNorm (+ activation) of a pass that needs no gradients (generation / validation under
+        # torch.no_grad(), main_vae.py:348-374, vaegan_code.py:147-171): scale / shift are known before the launch and
+        # ride the epilogue - act(conv * scale + shift) straight from the fp32 accumulator, no separate pass
+        eval_stats, eval_fused = None, False
+        if (bn is not None and not training and x.dtype == torch.bfloat16 and not out_f32
+                and act in (ACT_NONE, ACT_RELU, ACT_LEAKY) and not any(ctx.needs_input_grad)):
+            C = spec.small_c if spec.kind == "down" else g.big_c
+            eval_stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
+            ep_aff = make_epilogue(EPI_AFFINE_ACT_FWD, 1, C, act, slope, stats=eval_stats)
+            if epilogue_supported(g, spec.kind == "up", ep_aff):
+                ep, eval_fused = ep_aff, True
         bias_k = bias.detach() if bias is not None else None
         if bias_k is not None and bias_k.numel() < spec.small_c:           # padded GEMM rows (LinearGemmMap)
             padded = torch.zeros(spec.small_c, dtype=torch.float32, device=x.device)
@@ -777,8 +788,11 @@ class ConvLayerFn(torch.autograd.Function):
                     for i in range(groups):
                         scale_shift_act(rg[i], per[i][2], per[i][3], act, slope, out=yg[i])
                     stats = torch.stack(per)
+            elif eval_fused:
+                stats, y = eval_stats, raw
             else:
-                stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
+                stats = eval_stats if eval_stats is not None else \
+                    bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
                 y = scale_shift_act(raw, stats[2], stats[3], act, slope)
         elif act != ACT_NONE and not act_in_epilogue:
             y = scale_shift_act(raw, None, None, act, slope)

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from .dp import BucketedAllReduce
+from .dp import BucketedAllReduce, PeerAdam, PeerShared
 from ._lib import ACT_TANH, call
 from .functional import _p, _stream
 
@@ -31,7 +31,9 @@ LOSS_KEYS = ("d_loss_0", "d_loss_1", "recon", "kl", "adv", "total")
 class _FlatAdam:
     """All parameters of one network in one fp32 buffer + matching gradient / moment buffers."""
 
-    def __init__(self, net: nn.Module, lr, betas, eps):
+    def __init__(self, net: nn.Module, lr, betas, eps, symmetric: bool = False):
+        """`symmetric`: parameters and gradients live in symmetric memory (peer-mapped across the ranks of the data-
+        parallel group; dp.PeerAdam reduces / updates / broadcasts them with one kernel per bucket)."""
         params = [p for p in net.parameters()]
         self.names = [k for k, _ in net.named_parameters()]
         dev = params[0].device
@@ -42,8 +44,13 @@ class _FlatAdam:
         self.n = total
         self.offsets, self.sizes, self.shapes = offs, [p.numel() for p in params], [tuple(p.shape) for p in params]
         self.param_ids = [id(p) for p in params]
-        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.params = symm_mem.empty(total, dtype=torch.float32, device=dev).zero_()
+            self.grads = symm_mem.empty(total, dtype=torch.float32, device=dev).zero_()
+        else:
+            self.params = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
@@ -169,7 +176,7 @@ class VAEGANStep:
                  denoise_sigma: float = 0.0, n_dis: int = 2, real_label: float = 0.9, fake_label: float = 0.1,
                  process_group=None, use_cuda_graph: bool = True, seed: int = 0, overlap_wgrad: bool = True,
                  capture_grads: bool = False, bucket_bytes: Optional[Dict[str, int]] = None,
-                 recon_mode: str = "pixel", dis_layer: int = -2):
+                 recon_mode: str = "pixel", dis_layer: int = -2, dp_transport: Optional[str] = None):
         self.E, self.G, self.D = encoder, decoder, discriminator
         self.dtype = encoder._dtype()
         self.dev = next(encoder.parameters()).device
@@ -189,9 +196,27 @@ class VAEGANStep:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
             self.rank = torch.distributed.get_rank(process_group)
-        self.opt_E = _FlatAdam(encoder, lr, betas, eps)
-        self.opt_G = _FlatAdam(decoder, lr, betas, eps)
-        self.opt_D = _FlatAdam(discriminator, lr, betas, eps)
+        # data-parallel transport: "peer" = one kernel per gradient bucket over NVLink / NVSwitch peer memory
+        # (reduce-scatter + sharded Adam + all-gather, csrc/dp_comm.cu); "nccl" = bucketed ncclAllReduce + replicated
+        # Adam.  Default: peer when symmetric memory can be set up for the group, NCCL otherwise (environment override
+        # VG_DP_TRANSPORT=peer|peer-nomc|nccl; peer-nomc keeps to peer loads / stores, no multimem instructions)
+        import os as _os
+        transport = dp_transport or _os.environ.get("VG_DP_TRANSPORT", "auto")
+        if transport not in ("auto", "peer", "peer-nomc", "nccl"):
+            raise ValueError("dp_transport must be auto, peer, peer-nomc or nccl")
+        self.peer = None
+        if self.world > 1 and transport != "nccl":
+            try:
+                self.peer = PeerShared(self.dev, process_group, allow_multicast=(transport != "peer-nomc"))
+            except Exception as exc:        # no peer access / no symmetric-memory support on this box
+                if transport != "auto":
+                    raise
+                import warnings
+                warnings.warn(f"vaegan_b200: symmetric memory unavailable ({exc}); gradients go through NCCL")
+        sym = self.peer is not None
+        self.opt_E = _FlatAdam(encoder, lr, betas, eps, symmetric=sym)
+        self.opt_G = _FlatAdam(decoder, lr, betas, eps, symmetric=sym)
+        self.opt_D = _FlatAdam(discriminator, lr, betas, eps, symmetric=sym)
         if self.world > 1:
             # replicas must start from the same state (DDP's constructor does the same): rank 0's parameters and
             # BatchNorm buffers go to everyone
@@ -222,11 +247,17 @@ class VAEGANStep:
         bb = dict(E=2 << 20, G=8 << 20, D=4 << 20)
         bb.update(bucket_bytes or {})
         self.buckets = {}
+        self.peer_adam = {}
         if self.world > 1:
             for key, opt in (("E", self.opt_E), ("G", self.opt_G), ("D", self.opt_D)):
                 padded = [(n + 3) // 4 * 4 for n in opt.sizes]
+                reducer = None
+                if self.peer is not None:
+                    pa = PeerAdam(opt.grads, opt.params, opt.exp_avg, opt.exp_avg_sq, opt.step_count,
+                                  (lr, betas, eps), process_group, self.peer, write_grads=capture_grads)
+                    self.peer_adam[key], reducer = pa, pa.reduce_and_step
                 self.buckets[key] = BucketedAllReduce(opt.grads, opt.offsets, padded, process_group, bb[key],
-                                                      self.comm_stream, self.wgrad_streams)
+                                                      self.comm_stream, self.wgrad_streams, reducer=reducer)
         self._graph = None
         self._static = None
         self._copy_stream = None            # prefetch(): host -> device copies of the next batch
@@ -347,7 +378,8 @@ class VAEGANStep:
             self._finish_buckets("D")
             if self.capture_grads and self.world > 1:
                 self._d_grad_copies[it].copy_(self.opt_D.grads)
-            self.opt_D.step(1.0 / self.world)
+            if self.peer is None:              # (peer transport: the bucket kernels have already applied Adam)
+                self.opt_D.step(1.0 / self.world)
             D.repack_weights()
 
         # ---- generator / encoder update                                               (:110-135)
@@ -371,9 +403,20 @@ class VAEGANStep:
             for p in d_params:
                 p.requires_grad_(True)
         F_.WgradOverlap.join()
-        self._finish_buckets("G", "E")
-        self.opt_E.step(1.0 / self.world)
-        self.opt_G.step(1.0 / self.world)
+        if self.world > 1:
+            # the generator's buckets left first and are (nearly) done; the encoder's tail bucket is launched now and
+            # its latency (~40 us of ring all-reduce at 8 GPUs) hides under the generator's HBM-bound Adam
+            self.buckets["G"].flush()
+            self.buckets["E"].flush()
+            self.buckets["G"].wait()             # (only for G's own last bucket: dp.BucketedAllReduce.last_event)
+            if self.peer is None:
+                self.opt_G.step(1.0 / self.world)
+            self.buckets["E"].wait()
+            if self.peer is None:
+                self.opt_E.step(1.0 / self.world)
+        else:
+            self.opt_E.step(1.0 / self.world)
+            self.opt_G.step(1.0 / self.world)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
 
     def _arm_buckets(self, *keys):
@@ -527,6 +570,8 @@ class VAEGANStep:
         """State of the fused step beyond the three modules' own (reference-keyed) state_dicts: the three Adam states
         and the device noise counter.  Save it next to encoder / decoder / discriminator .state_dict()."""
         rng = int(self._static["rng_offset"]) if self._static is not None else getattr(self, "_pending_rng", 0)
+        for key, pa in self.peer_adam.items():     # sharded optimizer state: collect every slice from its owner
+            pa.gather_moments(self.buckets[key].buckets)
         return {"opt_E": self.opt_E.state_dict(), "opt_G": self.opt_G.state_dict(), "opt_D": self.opt_D.state_dict(),
                 "rng_offset": rng, "seed": self.seed}
 
