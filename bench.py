@@ -255,6 +255,15 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_u8_value = world * B * args.steps / float(t)
 
+    if world == 1:
+        transport = None
+    elif step.peer is None:
+        transport = "nccl all-reduce per gradient bucket + replicated Adam"
+    else:
+        transport = ("peer-memory kernel per gradient bucket (reduce-scatter + sharded Adam + all-gather, "
+                     + ("multimem instructions over the NVSwitch multicast mapping)" if step.peer_adam["G"].multicast
+                        else "peer loads / stores)"))
+        step.peer.check()
     extra = None
     del step, losses
     torch.cuda.empty_cache()
@@ -279,7 +288,7 @@ def run_gpu_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2", "nets": "64x64-derived VAE-GAN (SURVEY A.1), latent 128",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "dp_transport": transport,
                    "cuda_graph": not args.no_graph,
                    "l2_policy": "per-step working set (~3 GB of activations/gradients) far exceeds the 126 MB L2; "
                                 "4 rotating input batches"},

@@ -245,6 +245,45 @@ def test_fused_activation_forward_epilogue(case, act, slope):
     assert torch.equal(fused, ref)
 
 
+@pytest.mark.parametrize("act,slope", [(0, 0.0), (1, 0.0), (2, 0.2)])
+@pytest.mark.parametrize("case", [FUSE_CASES[0], FUSE_CASES[2], FUSE_CASES[3], FUSE_CASES[4]],
+                         ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}")
+def test_fused_eval_batchnorm_epilogue(case, act, slope):
+    """VG_EPI_AFFINE_ACT_FWD (eval-mode BatchNorm + activation in the epilogue, generation / validation passes)
+    against the fp32 reference act(conv * scale + shift) - tighter than, and within one bf16 ulp of, the two-pass form
+    it replaces (convolution rounded to bf16, then vg_scale_shift_act)."""
+    fn = _fn()
+    kind, B, H, W, cin, cout, k, s, p, _, _ = case
+    gen = torch.Generator().manual_seed(B * 7 + cout)
+    x = torch.randn(B, H, W, cin, generator=gen).cuda().bfloat16()
+    if kind == "down":
+        spec, w = fn.ConvSpec("down", cout, cin, k, s, p), torch.randn(cout, cin, k, k, generator=gen).cuda() * 0.1
+    else:
+        spec, w = fn.ConvSpec("up", cin, cout, k, s, p), torch.randn(cin, cout, k, k, generator=gen).cuda() * 0.1
+    g = spec.geom(B, H, W)
+    wd, wu = fn.pack_weights(w, g)
+    C = cout
+    gamma, beta = torch.rand(C, generator=gen).cuda() + 0.5, torch.randn(C, generator=gen).cuda()
+    rm, rv = torch.randn(C, generator=gen).cuda() * 0.1, torch.rand(C, generator=gen).cuda() + 0.5
+    stats = fn.bn_eval_coeffs(gamma, beta, rm, rv, 1e-5)
+    ep = fn.make_epilogue(fn.EPI_AFFINE_ACT_FWD, 1, C, act, slope, stats=stats)
+    assert fn.epilogue_supported(g, kind == "up", ep)
+    conv = (lambda e=None: fn.conv_down(x, wd, g, ep=e)) if kind == "down" else (lambda e=None: fn.conv_up(x, wu, g, ep=e))
+    raw, fused = conv(), conv(ep)
+    two_pass = fn.scale_shift_act(raw, stats[2], stats[3], act, slope)
+    # fp32 reference on the CPU from the same bf16 operands
+    xc, wc = x.float().cpu().permute(0, 3, 1, 2), w.bfloat16().float().cpu()
+    ref = F.conv2d(xc, wc, None, s, p) if kind == "down" else F.conv_transpose2d(xc, wc, None, s, p)
+    if kind == "up" and H == 1 and W == 1:
+        ref = ref                                      # dense first generator layer: [B, cout, k, k]
+    ref = ref * stats[2].cpu().view(1, -1, 1, 1) + stats[3].cpu().view(1, -1, 1, 1)
+    ref = ref if act == 0 else (ref.clamp_min(0) if act == 1 else torch.where(ref > 0, ref, ref * slope))
+    ref = ref.permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel_err(fused.float().cpu(), ref) < 5e-3                       # half a bf16 ulp of the largest value
+    assert rel_err(fused.float().cpu(), two_pass.float().cpu()) < 1.2e-2    # the old path carries one more rounding
+
+
 @pytest.mark.parametrize("act,slope", [(1, 0.0), (2, 0.2)])
 @pytest.mark.parametrize("case", FUSE_CASES[:3] + [FUSE_CASES[4], ("down", 64, 4, 4, 512, 1, 4, 1, 0, 2, False)],
                          ids=lambda c: f"{c[0]}-B{c[1]}-{c[2]}x{c[3]}-{c[4]}to{c[5]}-g{c[9]}")

@@ -245,6 +245,10 @@ class VAEGANStep:
         # dgrad / wgrad launches; the generator's 53 MB leave in three buckets under its own and the encoder's backward.
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         bb = dict(E=2 << 20, G=8 << 20, D=4 << 20)
+        if self.peer is not None:
+            # a peer-memory bucket costs two cross-GPU barriers on the communication stream and nothing on the main
+            # stream; only the LAST bucket of a backward pass is exposed, so it is kept small (D: first + second layer)
+            bb["D"] = 2 << 20
         bb.update(bucket_bytes or {})
         self.buckets = {}
         self.peer_adam = {}
