@@ -699,7 +699,7 @@ class ConvLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, spec: ConvSpec, act: int, slope: float, bn, training: bool,
                 cache: PackedWeights, out_f32: bool, groups: int = 1, link_in: Optional[LayerLink] = None,
-                link_out: Optional[LayerLink] = None, wmap: Optional[S2DWeightMap] = None):
+                link_out: Optional[LayerLink] = None, wmap: Optional[S2DWeightMap] = None, no_grad: bool = False):
         """`wmap`: the layer runs in space-to-depth form - `spec` is then the EQUIVALENT convolution (S2DWeightMap),
         `weight` still the reference-layout master."""
         """`groups` > 1: the batch holds that many independent sub-batches (e.g. the discriminator's real and fake
@@ -745,11 +745,12 @@ class ConvLayerFn(torch.autograd.Function):
             if epilogue_supported(g, spec.kind == "up", ep_act):
                 ep, act_in_epilogue = ep_act, True
         # eval-mode BatchNorm (+ activation) of a pass that needs no gradients (generation / validation under
-        # torch.no_grad(), main_vae.py:348-374, vaegan_code.py:147-171): scale / shift are known before the launch and
+        # torch.no_grad(), main_vae.py:348-374, vaegan_code.py:147-171; `no_grad` is the CALLER's grad mode - inside
+        # forward() it is always off and needs_input_grad ignores it): scale / shift are known before the launch and
         # ride the epilogue - act(conv * scale + shift) straight from the fp32 accumulator, no separate pass
         eval_stats, eval_fused = None, False
         if (bn is not None and not training and x.dtype == torch.bfloat16 and not out_f32
-                and act in (ACT_NONE, ACT_RELU, ACT_LEAKY) and not any(ctx.needs_input_grad)):
+                and act in (ACT_NONE, ACT_RELU, ACT_LEAKY) and no_grad):
             C = spec.small_c if spec.kind == "down" else g.big_c
             eval_stats = bn_eval_coeffs(gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.eps)
             ep_aff = make_epilogue(EPI_AFFINE_ACT_FWD, 1, C, act, slope, stats=eval_stats)
@@ -929,7 +930,7 @@ class ConvLayerFn(torch.autograd.Function):
         GradReady.notify(weight, bias, gamma, beta)
         return (dx, _accumulate_or_return(weight, dw), _accumulate_or_return(bias, dbias),
                 _accumulate_or_return(gamma, dgamma), _accumulate_or_return(beta, dbeta),
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 class ToNHWCFn(torch.autograd.Function):

@@ -98,7 +98,7 @@ class _Layer:
         self.s2d_active, self.active_wmap = wmap is not None, wmap
         return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, bn.weight if bn is not None else None,
                                     bn.bias if bn is not None else None, spec, act, self.slope, bn, training,
-                                    self.cache, out_f32, groups, link_in, link_out, wmap)
+                                    self.cache, out_f32, groups, link_in, link_out, wmap, not torch.is_grad_enabled())
 
 
 def _run_chain(layers, h, training: bool, groups: int = 1, link=None):
@@ -250,11 +250,11 @@ class _LinearAsConv(_Layer):
         if self.wmap is None or x.dtype != torch.bfloat16:
             self.s2d_active = False
             return F_.ConvLayerFn.apply(x, self.conv.weight, self.conv.bias, None, None, self.spec, ACT_NONE, 0.0, None,
-                                        training, self.cache, out_f32, 1, None, None, None)
+                                        training, self.cache, out_f32, 1, None, None, None, False)
         self.s2d_active = True                       # pack_layers: pack the GEMM operand, not the conv form
         flat = x.reshape(x.shape[0], 1, 1, -1)       # NHWC flatten = (h, w, c) order, what LinearGemmMap packs for
         y = F_.ConvLayerFn.apply(flat, self.conv.weight, self.conv.bias, None, None, self.wmap.eq_spec, ACT_NONE, 0.0,
-                                 None, training, self.cache, out_f32, 1, None, None, self.wmap)
+                                 None, training, self.cache, out_f32, 1, None, None, self.wmap, False)
         return y[..., :self.spec.small_c]
 
 
