@@ -209,3 +209,22 @@ def test_prefetched_host_batch_is_the_same_step(u8):
     sb.step(other, 50, *noise[0])
     torch.cuda.synchronize()
     assert torch.equal(sa._static["real"], sb._static["real"])
+
+
+def test_losses_lagged_returns_the_previous_step():
+    """VAEGANStep.losses_lagged(): asynchronous read-back of every step's losses, one step late, equal to a direct
+    read of the same step; losses_flush() returns the last one."""
+    from oracle import vaegan_oracle as vo
+    hw, nz, batch = 64, 128, 8
+    _, nets = make_pair(hw, nz, "bf16")
+    step = _step_cls()(*nets, use_cuda_graph=True)
+    direct, lagged = [], []
+    for it in range(4):
+        real, eps, n_real, n_fake = vo.make_inputs(batch, hw, nz, seed=300 + it)
+        losses = step.step(real.cuda(), 10, eps.cuda(), n_real.cuda(), n_fake.cuda())
+        lagged.append(step.losses_lagged())
+        direct.append({k: float(v) for k, v in losses.items()})
+    assert lagged[0] is None
+    for it in range(1, 4):
+        assert lagged[it] == direct[it - 1], it
+    assert step.losses_flush() == direct[3] and step.losses_flush() is None

@@ -335,6 +335,14 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
     call("vg_colsum", _p(x), _DT[x.dtype], rows, C, _p(out), _p(ws), nbytes, _stream())
 
 
+def image_nhwc_shape(B: int, C: int, H: int, W: int, dtype, s2d_origin: Optional[int] = None):
+    """Shape / dtype of what nchw_to_nhwc produces for a [B, C, H, W] image (to pre-allocate its `out`)."""
+    if s2d_origin is not None:
+        o = int(s2d_origin)
+        return (B, H // 2 + o, W // 2 + o, 64), torch.bfloat16
+    return (B, H, W, padded_channels(C, dtype)), dtype
+
+
 def nchw_to_nhwc(src: torch.Tensor, dtype, aux: Optional[torch.Tensor] = None, mode: int = 0, sigma: float = 0.0,
                  clamp: bool = False, out: Optional[torch.Tensor] = None, s2d_origin: Optional[int] = None) -> torch.Tensor:
     """fp32 NCHW -> internal NHWC (channel-padded per `padded_channels`), or, with `s2d_origin` in {0, 1}, the

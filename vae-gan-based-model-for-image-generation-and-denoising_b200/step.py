@@ -123,20 +123,21 @@ class _ReconHubFn(torch.autograd.Function):
     when the backward pass gets here).  `terms` = None in Dis_l mode (the feature tap owns the reconstruction term)."""
 
     @staticmethod
-    def forward(ctx, recon, real, n_fake, sigma, dtype, terms, s2d_origin=None):
+    def forward(ctx, recon, real, n_fake, sigma, dtype, terms, s2d_origin=None, out=None):
+        """`out`: where to write (the fake half of the discriminator's stacked input batch - no copy afterwards)."""
         ctx.save_for_backward(recon, real)
         ctx.s2d_origin, ctx.terms = s2d_origin, terms
-        return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma, s2d_origin=s2d_origin)
+        return F_.nchw_to_nhwc(recon, dtype, aux=n_fake, mode=1, sigma=sigma, s2d_origin=s2d_origin, out=out)
 
     @staticmethod
     def backward(ctx, dy):
         recon, real = ctx.saved_tensors
         d_adv = F_.nhwc_to_nchw(dy.contiguous(), channels=recon.shape[1], s2d_origin=ctx.s2d_origin)
         if ctx.terms is None:
-            return d_adv, None, None, None, None, None, None
+            return d_adv, None, None, None, None, None, None, None
         d_total = torch.empty_like(recon)
         ctx.terms.mse_total(recon, real, d_adv, d_total)
-        return d_total, None, None, None, None, None, None
+        return d_total, None, None, None, None, None, None, None
 
 
 class _FeatureMatchFn(torch.autograd.Function):
@@ -309,9 +310,10 @@ class VAEGANStep:
         B = real.shape[0]
         # every replay starts from freshly packed bf16 weights (one launch per net): the encoder's are needed at once,
         # the generator's and the discriminator's are packed on the second stream under the encoder's forward pass
-        E.repack_weights()
         sides = self.wgrad_streams
         cur = torch.cuda.current_stream()
+        if not sides:
+            E.repack_weights()
 
         def noise():                   # torch.randn_like of vaegan_code.py:77,91,92 -> Philox kernel
             self._randn_into(s["eps"], 1)
@@ -323,6 +325,8 @@ class VAEGANStep:
         if sides:
             for st in sides:                    # fork every side stream here: all of them belong to the capture
                 st.wait_stream(cur)
+            with torch.cuda.stream(sides[2]):   # the encoder's copies: needed first, packed next to the input conversion
+                E.repack_weights()
             with torch.cuda.stream(sides[0]):
                 G.repack_weights()
                 D.repack_weights()
@@ -347,6 +351,8 @@ class VAEGANStep:
                                      s2d_origin=e_fmt)
         else:
             enc_in = F_.nchw_to_nhwc(real, self.dtype, s2d_origin=e_fmt)
+        if sides:
+            cur.wait_stream(sides[2])                                # packed encoder weights
         mu, logvar = E.forward_nhwc(enc_in)
         z = _ReparamFn.apply(mu, logvar, s["eps"], loss[3:4], s["kl_w"], self.dtype)
         for st in sides[:2]:
@@ -356,13 +362,14 @@ class VAEGANStep:
         # ---- instance noise                                                           (:88-92)
         terms = _LossTerms(loss, s["kl_w"], self.alpha_adv, s["mse_ws"])
         dis_l = self.recon_mode == "dis_l"
-        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype,
-                                        None if dis_l else terms, d_fmt)
         # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
-        # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2)
-        pair = torch.empty((2 * B,) + tuple(recon_noisy.shape[1:]), dtype=self.dtype, device=self.dev)
+        # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2); the
+        # noisy reconstruction is written straight into the stack's second half
+        shape, dt = F_.image_nhwc_shape(B, real.shape[1], real.shape[2], real.shape[3], self.dtype, d_fmt)
+        pair = torch.empty((2 * B,) + tuple(shape[1:]), dtype=dt, device=self.dev)
+        recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype,
+                                        None if dis_l else terms, d_fmt, pair[B:])
         F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B], s2d_origin=d_fmt)
-        pair[B:].copy_(recon_noisy.detach())
         dp = s["dp_pair"]
 
         # ---- discriminator updates                                                    (:95-105)
@@ -520,6 +527,39 @@ class VAEGANStep:
         self.E.invalidate_packed_weights()
         self.G.invalidate_packed_weights()
         return {k: s["losses"][i] for i, k in enumerate(LOSS_KEYS)}
+
+    # ------------------------------------------------------------------------------------------ loss read-back
+    def losses_lagged(self) -> Optional[Dict[str, float]]:
+        """Host values of the losses WITHOUT stalling the device: enqueues an asynchronous device -> host copy of the
+        step that was just launched (24 bytes into a pinned double buffer) and returns the PREVIOUS step's six losses
+        as Python floats (None after the first step).  The `.item()` reads of vaegan_code.py:119-127 drain the queue
+        every step - the host then prepares the next launch while the GPU idles; read one step late and the next
+        replay is already queued when the host blocks.  `losses_flush()` returns the last step's values."""
+        if self._static is None:
+            return None
+        if getattr(self, "_lag", None) is None:
+            self._lag = {"buf": [torch.empty(len(LOSS_KEYS), dtype=torch.float32).pin_memory() for _ in range(2)],
+                         "ev": [torch.cuda.Event(), torch.cuda.Event()], "cur": 0, "have": False}
+        lag = self._lag
+        prev = None
+        if lag["have"]:
+            j = lag["cur"] ^ 1
+            lag["ev"][j].synchronize()
+            prev = {k: float(lag["buf"][j][i]) for i, k in enumerate(LOSS_KEYS)}
+        i = lag["cur"]
+        lag["buf"][i].copy_(self._static["losses"], non_blocking=True)
+        lag["ev"][i].record(torch.cuda.current_stream())
+        lag["cur"], lag["have"] = i ^ 1, True
+        return prev
+
+    def losses_flush(self) -> Optional[Dict[str, float]]:
+        lag = getattr(self, "_lag", None)
+        if lag is None or not lag["have"]:
+            return None
+        j = lag["cur"] ^ 1
+        lag["ev"][j].synchronize()
+        lag["have"] = False
+        return {k: float(lag["buf"][j][i]) for i, k in enumerate(LOSS_KEYS)}
 
     # ------------------------------------------------------------------------------------------ input prefetch
     def prefetch(self, real: torch.Tensor) -> None:
