@@ -217,6 +217,8 @@ def run_gpu_arm(args):
     # loader's double buffering - and therefore runs under that step; every batch still crosses PCIe inside the loop)
     for i in range(3):
         step.step(host_pool[i % n_pool], epoch)
+        step.losses_lagged()                             # (also allocates the pinned read-back buffers once)
+    step.losses_flush()
     barrier()
     t0 = time.perf_counter()
     step.prefetch(host_pool[0])

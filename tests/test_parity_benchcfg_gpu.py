@@ -39,7 +39,10 @@ LOSS_TOL = 2e-2
 # "bf16 pipelines with identical rounding points", and 1-ulp differences avalanche through the ReLU masks / BatchNorm
 # statistics of the adversarial path.  TWIN_MARGIN is the slack on that comparison; tensors whose twin agreement is
 # itself above 0.999 must reach 0.999 - TWIN_MARGIN.
-TWIN_MARGIN = 4e-3
+# (run-to-run spread of the CUDA path itself - fp32 atomics in the weight-gradient / statistics epilogues arrive in a
+# different order every run - is ~2e-3 on the smallest tensors: the encoder's 64-element first BatchNorm gamma at cfg 4,
+# B = 64, read 0.9884 and 0.9862 in two runs of the same build against a twin value of 0.9909)
+TWIN_MARGIN = 6e-3
 # without a twin: the floors measured for these nets (printed values of the twin cases), per network
 PER_TENSOR_FLOOR = {"E": 0.99, "G": 0.98, "D": 0.99}
 FLAT_FP32_FLOOR = {"E": 0.995, "G": 0.99, "D": 0.995}
