@@ -88,6 +88,36 @@ def _worker(rank, world, port, out):
         ar.mark_ready(i)
     ar.finish()
     ok = ok and torch.allclose(flat, want, **tol)
+    # a custom per-bucket reducer (what the peer-memory transport plugs in): sharded "optimizer step" on CPU - every
+    # rank reduces all buckets, applies p -= lr * g on ITS slice only and broadcasts the slice; flush() / wait() split
+    flat.copy_(local)
+    p_flat = torch.arange(flat.numel(), dtype=torch.float32) * 1e-3
+    firsts, order = [], []
+
+    def reducer(bucket, first):
+        firsts.append(first)
+        order.append(bucket.lo)
+        view = flat[bucket.lo:bucket.hi]
+        dist.all_reduce(view)
+        n = bucket.hi - bucket.lo
+        per = (n + world - 1) // world
+        for r in range(world):
+            a, b = bucket.lo + min(n, per * r), bucket.lo + min(n, per * (r + 1))
+            if b > a:
+                if r == rank:
+                    p_flat[a:b] -= 0.1 * flat[a:b] / world
+                dist.broadcast(p_flat[a:b], r)
+
+    ar2 = dp.BucketedAllReduce(flat, offsets, sizes, bucket_bytes=1 << 20, reducer=reducer)
+    for i in reversed(range(len(params))[1:]):   # the first parameter never reports: flush() must launch its bucket
+        ar2.mark_ready(i)
+    n_before = len(order)
+    ar2.flush()
+    ar2.wait()
+    ok = ok and len(order) == len(ar2.buckets) and n_before == len(ar2.buckets) - 1
+    ok = ok and firsts == [True] + [False] * (len(ar2.buckets) - 1) and order == sorted(order, reverse=True)
+    want_p = torch.arange(flat.numel(), dtype=torch.float32) * 1e-3 - 0.1 * want / world
+    ok = ok and torch.allclose(p_flat, want_p, **tol) and ar2.pending == [len(b.params) for b in ar2.buckets]
     out.put((rank, bool(ok), len(ar.buckets)))
     dist.destroy_process_group()
 

@@ -111,6 +111,8 @@ class BucketedAllReduce:
                 # consumers wait for THIS buffer's last bucket, not for whatever else shares the communication stream
                 self.last_event = torch.cuda.Event()
                 self.last_event.record(self.comm_stream)
+        elif self.reducer is not None:
+            self.reducer(b, sum(self.launched) == 1)
         else:
             dist.all_reduce(view, group=self.group)
 
