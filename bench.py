@@ -215,9 +215,11 @@ def run_gpu_arm(args):
     # ---- e2e: same step through the public API from pinned host memory, losses read back every step
     # (the next batch's host -> device copy is started on the copy stream right after a step is launched - the data
     # loader's double buffering - and therefore runs under that step; every batch still crosses PCIe inside the loop)
-    for i in range(3):
-        step.step(host_pool[i % n_pool], epoch)
-        step.losses_lagged()                             # (also allocates the pinned read-back buffers once)
+    step.prefetch(host_pool[0])                          # warm-up through the very code path that is timed (copy
+    for i in range(3):                                   # stream, staging buffer, pinned read-back buffers: one-time
+        step.step(host_pool[i % n_pool], epoch)          # allocations that do not belong to a steady-state step)
+        step.prefetch(host_pool[(i + 1) % n_pool])
+        step.losses_lagged()
     step.losses_flush()
     barrier()
     t0 = time.perf_counter()
@@ -247,8 +249,12 @@ def run_gpu_arm(args):
     # ---- e2e with the images shipped as decoded uint8 NHWC (1 byte per value) and normalised on the device
     u8_pool = [((h.permute(0, 2, 3, 1) * 0.5 + 0.5) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
                for h in host_pool]
+    step.prefetch(u8_pool[0])
     for i in range(3):
         step.step(u8_pool[i % n_pool], epoch)
+        step.prefetch(u8_pool[(i + 1) % n_pool])
+        step.losses_lagged()
+    step.losses_flush()
     barrier()
     t0 = time.perf_counter()
     step.prefetch(u8_pool[0])
