@@ -521,16 +521,17 @@ def _dominant_kernel(torch, step, batch, epoch, graph_ms_per_step):
                              for name, tag, f, nb, ms in recs if tag in ("fprop", "wgrad")]
         return out
 
-    was_graph, sides = step.use_graph, step.wgrad_streams
+    was_graph, sides, local, buckets = step.use_graph, step.wgrad_streams, step.local_adam, step.buckets
     step.use_graph = False
     try:
         overlapped = one_pass()
         alone = None
         if step.world == 1:
-            step.wgrad_streams = []
+            # one stream for everything: no weight-gradient side streams, Adam as one launch after the backward pass
+            step.wgrad_streams, step.local_adam, step.buckets = [], set(), {}
             alone = one_pass()
     finally:
-        step.use_graph, step.wgrad_streams = was_graph, sides
+        step.use_graph, step.wgrad_streams, step.local_adam, step.buckets = was_graph, sides, local, buckets
     traffic, src = None, "no ncu capture committed"
     path = os.path.join(ROOT, "profiles", "fprop_traffic.json")
     if os.path.isfile(path):

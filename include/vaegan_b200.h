@@ -302,6 +302,10 @@ int vg_dp_adam_bucket(const VgDpComm* comm, long long lo, long long n, float* m,
                       int write_grads, int* err_flag, void* stream);
 /* *step_dev += 1 (the tick vg_adam_step does itself). */
 int vg_adam_tick(long long* step_dev, void* stream);
+/* vg_adam_step without the tick: the update of one RANGE of a flat buffer (pointers already offset), for optimizer
+ * steps issued bucket by bucket from inside the backward pass; the caller ticks *step_dev once per step first. */
+int vg_adam_apply(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                  double eps, const long long* step_dev, float grad_scale, void* stream);
 /* torch.optim.Adam.step (vaegan_code.py:42-44,105,134-135) over one flat fp32 buffer; *step_dev is incremented
  * first and drives the bias corrections, so the call can be replayed from a CUDA graph.  g is multiplied by
  * grad_scale (1/world_size under data parallelism). */

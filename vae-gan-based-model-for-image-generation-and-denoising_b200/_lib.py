@@ -100,6 +100,7 @@ PROTOTYPES = {
     "vg_total_loss": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P]),
     "vg_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_double, c_double, c_double, c_double, _P, c_float, _P]),
     "vg_adam_tick": (c_int, [_P, _P]),
+    "vg_adam_apply": (c_int, [_P, _P, _P, _P, c_longlong, c_double, c_double, c_double, c_double, _P, c_float, _P]),
     "vg_dp_max_blocks": (c_int, []),
     "vg_dp_adam_bucket": (c_int, [_P, c_longlong, c_longlong, _P, _P, c_double, c_double, c_double, c_double, _P, c_float,
                                   c_int, c_int, _P, _P]),

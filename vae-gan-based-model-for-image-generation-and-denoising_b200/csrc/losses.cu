@@ -463,6 +463,22 @@ extern "C" int vg_adam_step(float* p, const float* g, float* m, float* v, long l
     return VG_OK;
 }
 
+extern "C" int vg_adam_apply(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                             double beta2, double eps, const long long* step_dev, float grad_scale, void* stream) {
+    int rc = device_check();
+    if (rc != VG_OK) return rc;
+    if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || step_dev == nullptr)
+        return fail(VG_ERR_ARG, "adam: null pointer");
+    if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+         reinterpret_cast<uintptr_t>(v)) & 15)
+        return fail(VG_ERR_ALIGN, "adam: 16-byte alignment");
+    if (n <= 0) return VG_OK;
+    launch_k(adam_kernel, dim3(grid_for(n / 4 + 1)), dim3(kThreads), 0, as_stream(stream), p, g, m, v, n, lr, beta1, beta2,
+             eps, step_dev, grad_scale);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
 extern "C" int vg_adam_tick(long long* step_dev, void* stream) {
     int rc = device_check();
     if (rc != VG_OK) return rc;

@@ -96,7 +96,7 @@ class BucketedAllReduce:
     def _launch(self, b_idx: int):
         b = self.buckets[b_idx]
         self.launched[b_idx] = True
-        if self.world == 1:
+        if self.world == 1 and self.reducer is None:
             return
         view = self.flat[b.lo:b.hi]
         if self.comm_stream is not None:
@@ -132,7 +132,7 @@ class BucketedAllReduce:
 
     def wait(self):
         """Make the current stream wait for every launched bucket and reset the state for the next backward pass."""
-        if self.comm_stream is not None and self.world > 1 and self.last_event is not None:
+        if self.comm_stream is not None and self.last_event is not None:
             torch.cuda.current_stream().wait_event(self.last_event)
         self.last_event = None
         self.reset()
@@ -228,3 +228,25 @@ class PeerShared:
         if int(self.err) != 0:
             raise RuntimeError("peer-memory optimizer step: a cross-GPU barrier timed out (a rank is missing or "
                                "launched a different sequence of buckets)")
+
+
+class LocalAdam:
+    """One GPU: the optimizer step of a network issued bucket by bucket from inside its backward pass (the reducer hook
+    of BucketedAllReduce with nothing to reduce) - Adam on the ranges whose gradients are complete runs on a side
+    stream under the remaining dgrad / wgrad launches; only the last bucket's update is left when backward ends."""
+
+    def __init__(self, opt):
+        from . import _lib
+        self._lib, self.opt = _lib, opt
+
+    def reduce_and_step(self, bucket: Bucket, first: bool):
+        import ctypes
+        o, lib = self.opt, self._lib
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t, off=0: ctypes.c_void_p(t.data_ptr() + 4 * off)
+        if first:
+            lib.call("vg_adam_tick", P(o.step_count), stream)
+        lo, n = bucket.lo, bucket.hi - bucket.lo
+        lib.call("vg_adam_apply", P(o.params, lo), P(o.grads, lo), P(o.exp_avg, lo), P(o.exp_avg_sq, lo), n,
+                 float(o.lr), float(o.betas[0]), float(o.betas[1]), float(o.eps), ctypes.c_void_p(o.step_count.data_ptr()),
+                 1.0, stream)

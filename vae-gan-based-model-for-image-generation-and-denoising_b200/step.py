@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from .dp import BucketedAllReduce, PeerAdam, PeerShared
+from .dp import BucketedAllReduce, LocalAdam, PeerAdam, PeerShared
 from ._lib import ACT_TANH, call
 from .functional import _p, _stream
 
@@ -253,6 +253,20 @@ class VAEGANStep:
         bb.update(bucket_bytes or {})
         self.buckets = {}
         self.peer_adam = {}
+        # one GPU, experiment switch (off): networks whose Adam is issued per bucket from inside the backward pass
+        # (dp.LocalAdam), VG_LOCAL_ADAM = comma list out of E,G,D.  Measured (40 steps each): none 3.633 ms, D 3.653,
+        # D,E 3.646, D,E,G 3.631 - the 14 / 9 / 56 us of Adam it hides come back as contention and extra launches
+        local = _os.environ.get("VG_LOCAL_ADAM", "")
+        self.local_adam = set(k for k in local.split(",") if k in ("E", "G", "D")) \
+            if (self.world == 1 and overlap_wgrad) else set()
+        if self.local_adam:
+            self.comm_stream = torch.cuda.Stream(device=self.dev)
+            for key, opt in (("E", self.opt_E), ("G", self.opt_G), ("D", self.opt_D)):
+                if key in self.local_adam:
+                    padded = [(n + 3) // 4 * 4 for n in opt.sizes]
+                    self.buckets[key] = BucketedAllReduce(opt.grads, opt.offsets, padded, process_group, bb[key],
+                                                          self.comm_stream, self.wgrad_streams,
+                                                          reducer=LocalAdam(opt).reduce_and_step)
         if self.world > 1:
             for key, opt in (("E", self.opt_E), ("G", self.opt_G), ("D", self.opt_D)):
                 padded = [(n + 3) // 4 * 4 for n in opt.sizes]
@@ -346,6 +360,20 @@ class VAEGANStep:
         # bf16 path: 128-byte TMA rows instead of 32-byte padded pixels)
         e_fmt = E.input_s2d_origin(real.shape[2], real.shape[3])
         d_fmt = D.input_s2d_origin(real.shape[2], real.shape[3])
+        # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
+        # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2).
+        # The real half (:91) depends on nothing the encoder / generator compute: it is converted on a side stream
+        # under the encoder's forward pass; the noisy reconstruction is later written straight into the second half
+        shape, dt = F_.image_nhwc_shape(B, real.shape[1], real.shape[2], real.shape[3], self.dtype, d_fmt)
+        pair = torch.empty((2 * B,) + tuple(shape[1:]), dtype=dt, device=self.dev)
+        if sides:
+            sides[1].wait_stream(cur)               # (the noise, when it was drawn on the main stream)
+            with torch.cuda.stream(sides[1]):
+                F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B],
+                                s2d_origin=d_fmt)
+        else:
+            F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B],
+                            s2d_origin=d_fmt)
         if self.denoise_sigma > 0:
             enc_in = F_.nchw_to_nhwc(real, self.dtype, aux=s["n_den"], mode=1, sigma=self.denoise_sigma, clamp=True,
                                      s2d_origin=e_fmt)
@@ -362,14 +390,8 @@ class VAEGANStep:
         # ---- instance noise                                                           (:88-92)
         terms = _LossTerms(loss, s["kl_w"], self.alpha_adv, s["mse_ws"])
         dis_l = self.recon_mode == "dis_l"
-        # D(real_noisy) and D(recon_noisy.detach()) of :96-97 share every convolution launch: the two batches are
-        # stacked, BatchNorm statistics / running-stat updates stay per batch, real first (ConvLayerFn groups=2); the
-        # noisy reconstruction is written straight into the stack's second half
-        shape, dt = F_.image_nhwc_shape(B, real.shape[1], real.shape[2], real.shape[3], self.dtype, d_fmt)
-        pair = torch.empty((2 * B,) + tuple(shape[1:]), dtype=dt, device=self.dev)
         recon_noisy = _ReconHubFn.apply(recon, real, s["n_fake"], self.sigma_inst, self.dtype,
                                         None if dis_l else terms, d_fmt, pair[B:])
-        F_.nchw_to_nhwc(real, self.dtype, aux=s["n_real"], mode=1, sigma=self.sigma_inst, out=pair[:B], s2d_origin=d_fmt)
         dp = s["dp_pair"]
 
         # ---- discriminator updates                                                    (:95-105)
@@ -389,7 +411,7 @@ class VAEGANStep:
             self._finish_buckets("D")
             if self.capture_grads and self.world > 1:
                 self._d_grad_copies[it].copy_(self.opt_D.grads)
-            if self.peer is None:              # (peer transport: the bucket kernels have already applied Adam)
+            if self.peer is None and "D" not in self.local_adam:   # (else the bucket kernels have applied Adam)
                 self.opt_D.step(1.0 / self.world)
             D.repack_weights()
 
@@ -426,17 +448,20 @@ class VAEGANStep:
             if self.peer is None:
                 self.opt_E.step(1.0 / self.world)
         else:
-            self.opt_E.step(1.0 / self.world)
-            self.opt_G.step(1.0 / self.world)
+            self._finish_buckets("G", "E")
+            if "E" not in self.local_adam:
+                self.opt_E.step(1.0)
+            if "G" not in self.local_adam:
+                self.opt_G.step(1.0)
         self._last = dict(mu=mu.detach(), logvar=logvar.detach(), recon=recon.detach())
 
     def _arm_buckets(self, *keys):
         """Register dp.BucketedAllReduce.mark_ready for every parameter of the named networks: the layer backward
         that has just issued a parameter's gradient kernels calls it (functional.GradReady)."""
-        if self.world == 1:
-            return
         handlers = {}
         for key in keys:
+            if key not in self.buckets:
+                continue
             opt, bk = {"E": self.opt_E, "G": self.opt_G, "D": self.opt_D}[key], self.buckets[key]
             bk.reset()
             for i, pid in enumerate(opt.param_ids):
@@ -445,10 +470,9 @@ class VAEGANStep:
 
     def _finish_buckets(self, *keys):
         """Launch what the backward pass did not trigger and make the current stream wait for the communication."""
-        if self.world == 1:
-            return
         for key in keys:
-            self.buckets[key].finish()
+            if key in self.buckets:
+                self.buckets[key].finish()
 
     # ------------------------------------------------------------------------------------------ public API
     def step(self, real: torch.Tensor, epoch: int, eps: Optional[torch.Tensor] = None,
