@@ -144,6 +144,13 @@ def test_reference_loop_unchanged_fp32():
     _check_grads(res.g_grads, res_o.g_grads, 1.5e-2, "G(step)", min_cos=0.9999, l2=True)
     for it in range(2):
         _check_grads(res.d_grads[it], res_o.d_grads[it], 1.5e-2, f"D(step,{it})", min_cos=0.9999, l2=True)
+    # ... and per NETWORK the flattened gradient points the same way to five nines (a sparse flip moves single elements)
+    from tests.util import cosine
+    for name, mine_g, ref_g in (("E", res.e_grads, res_o.e_grads), ("G", res.g_grads, res_o.g_grads),
+                                ("D0", res.d_grads[0], res_o.d_grads[0]), ("D1", res.d_grads[1], res_o.d_grads[1])):
+        a = torch.cat([mine_g[k].flatten().cpu() for k in ref_g])
+        b = torch.cat([ref_g[k].flatten() for k in ref_g])
+        assert cosine(a, b) > 0.99999, (name, cosine(a, b))
     from tests.test_step_gpu import _compare_post_step
     _compare_post_step(nets, o_nets)
 

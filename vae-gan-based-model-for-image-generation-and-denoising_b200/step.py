@@ -638,6 +638,8 @@ class VAEGANStep:
         """State of the fused step beyond the three modules' own (reference-keyed) state_dicts: the three Adam states
         and the device noise counter.  Save it next to encoder / decoder / discriminator .state_dict()."""
         rng = int(self._static["rng_offset"]) if self._static is not None else getattr(self, "_pending_rng", 0)
+        if self.peer is not None:
+            self.peer.check()                      # a cross-GPU barrier that timed out would have corrupted the step
         for key, pa in self.peer_adam.items():     # sharded optimizer state: collect every slice from its owner
             pa.gather_moments(self.buckets[key].buckets)
         return {"opt_E": self.opt_E.state_dict(), "opt_G": self.opt_G.state_dict(), "opt_D": self.opt_D.state_dict(),
@@ -656,10 +658,18 @@ class VAEGANStep:
         if self._static is not None:
             self._static["rng_offset"].fill_(self._pending_rng)
 
+    def check_comm(self) -> None:
+        """Peer transport: raise if a cross-GPU barrier of the optimizer kernels ever timed out (reads one device
+        integer, i.e. synchronises - call it at checkpoints / epoch ends, not every step)."""
+        if self.peer is not None:
+            self.peer.check()
+
     def gradients(self):
         """Gradients of the most recent step as {name: tensor} per network: "E" / "G" (what their Adam consumed, i.e.
         after the all-reduce, before the 1/world scale) and "D" = a list with one dict per discriminator update (all of
-        them with `capture_grads=True`, else only the last).  Views of the flat buffers: clone to keep."""
+        them with `capture_grads=True`, else only the last).  Views of the flat buffers: clone to keep.  With the peer
+        transport the summed gradient is only written back with `capture_grads=True`; otherwise these are the rank's
+        own, un-reduced gradients (the sum exists in registers of the optimizer kernel only)."""
         d = [self.opt_D.named_views(c) for c in self._d_grad_copies] or [self.opt_D.named_views(self.opt_D.grads)]
         return {"E": self.opt_E.named_views(self.opt_E.grads), "G": self.opt_G.named_views(self.opt_G.grads), "D": d}
 
