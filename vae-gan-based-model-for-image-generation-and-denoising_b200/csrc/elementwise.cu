@@ -917,38 +917,40 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const float* __re
                                                               __nv_bfloat16* __restrict__ dst, int B, int C, int H, int W,
                                                               int o, int mode, float sigma, int clamp) {
     pdl_enter();
-    // One thread per 16-byte unit of a 128-byte row (8 consecutive threads = one 2x2 block, a warp = four whole rows:
-    // every store instruction writes 512 contiguous bytes).  Unit j = slots 8j .. 8j+7 = sub-pixel j / 2, channels
-    // (j % 2) * 8 .. +7; with the 3-channel images of this path the odd units are all zero.
     const int bh = H / 2 + o, bw = W / 2 + o;
-    const long long total = static_cast<long long>(B) * bh * bw * 8;
-    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
-         t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long i = t >> 3;
-        const int j = static_cast<int>(t & 7), sub = j >> 1, c0 = (j & 1) * 8;
+    const long long total = static_cast<long long>(B) * bh * bw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int X = static_cast<int>(i % bw);
         const int Y = static_cast<int>((i / bw) % bh);
         const long long b = i / (static_cast<long long>(bw) * bh);
-        const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
-        const bool in = py >= 0 && py < H && px >= 0 && px < W;
-        float v[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            v[c] = 0.f;
-            if (in && c0 + c < C) {
-                const long long s = ((b * C + c0 + c) * H + py) * W + px;
-                float x = src[s];
-                if (mode == 1) {
-                    x = fmaf(sigma, aux[s], x);
-                    if (clamp) x = fminf(1.f, fmaxf(-1.f, x));
-                } else if (mode == 2) {
-                    const float y = aux[s];
-                    x *= (1.f - y * y);
+        for (int sub = 0; sub < 4; ++sub) {
+            const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
+            const bool in = py >= 0 && py < H && px >= 0 && px < W;
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = 0.f;
+                if (in && c < C) {
+                    const long long s = ((b * C + c) * H + py) * W + px;
+                    float t = src[s];
+                    if (mode == 1) {
+                        t = fmaf(sigma, aux[s], t);
+                        if (clamp) t = fminf(1.f, fmaxf(-1.f, t));
+                    } else if (mode == 2) {
+                        const float y = aux[s];
+                        t *= (1.f - y * y);
+                    }
+                    v[c] = t;
                 }
-                v[c] = x;
             }
+            float lo[8], hi[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi[c] = v[8 + c]; }
+            Vec<__nv_bfloat16>::store(dst + i * 64 + sub * 16, lo);
+            Vec<__nv_bfloat16>::store(dst + i * 64 + sub * 16 + 8, hi);
         }
-        Vec<__nv_bfloat16>::store(dst + t * 8, v);
     }
 }
 
@@ -1299,7 +1301,7 @@ extern "C" int vg_nchw_to_s2d(const float* src, const float* aux, void* dst, int
         return fail(VG_ERR_SHAPE, "nchw_to_s2d: needs <= 16 channels, even H and W, origin 0 or 1");
     if (reinterpret_cast<uintptr_t>(dst) & 15) return fail(VG_ERR_ALIGN, "nchw_to_s2d: 16-byte alignment");
     const long long blocks = static_cast<long long>(B) * (H / 2 + origin) * (W / 2 + origin);
-    launch_k(nchw_to_s2d_kernel, dim3(grid_for(blocks * 8)), dim3(kThreads), 0, as_stream(stream), src, aux, static_cast<__nv_bfloat16*>(dst), B, C, H, W, origin, mode, sigma, clamp);
+    launch_k(nchw_to_s2d_kernel, dim3(grid_for(blocks)), dim3(kThreads), 0, as_stream(stream), src, aux, static_cast<__nv_bfloat16*>(dst), B, C, H, W, origin, mode, sigma, clamp);
     VG_LAUNCHED();
     return VG_OK;
 }
