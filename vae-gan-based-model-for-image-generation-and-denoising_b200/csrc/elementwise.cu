@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_apply_kernel(const T* __r
 // block (0, group) publishes the per-channel results, block (0, 0) walks the running statistics through all groups
 // in order (momentum updates do not commute).  blockIdx.y = statistics group (sub-batch of `rows` rows).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
+__global__ void __launch_bounds__(kThreads, 3) bn_apply_from_sums_kernel(
     const T* __restrict__ x, T* __restrict__ y, long long nvec, int C, long long rows, const float* __restrict__ sums,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     long long* num_batches_tracked, float momentum, float eps, float* __restrict__ stats, int act, float slope) {
@@ -696,10 +697,10 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
     const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
     // the first batch of activation loads is issued BEFORE the finalisation below waits on the sums: short passes were
     // paying a full dependent round trip (sums -> math -> first load) on top of ~3 us of streaming
-    float v[U][V];
+    typename Vec<T>::Raw raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (tid + u * stride < nvec) Vec<T>::load(x + (tid + u * stride) * V, v[u]);
+        if (tid + u * stride < nvec) raw[u] = Vec<T>::load_raw(x + (tid + u * stride) * V);
     float sc[V], sh[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -747,14 +748,16 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
         if (i != tid) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i + u * stride < nvec) Vec<T>::load(x + (i + u * stride) * V, v[u]);
+                if (i + u * stride < nvec) raw[u] = Vec<T>::load_raw(x + (i + u * stride) * V);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (i + u * stride >= nvec) continue;
+            float v[V];
+            Vec<T>::unpack(raw[u], v);
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
-            Vec<T>::store(y + (i + u * stride) * V, v[u]);
+            for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+            Vec<T>::store(y + (i + u * stride) * V, v);
         }
     }
 }
@@ -762,7 +765,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_from_sums_kernel(
 // dx = scale*(dz - c1 - xhat*c2) with c1 = sum(dz)/n, c2 = sum(dz*xhat)/n taken from `sums`; dz already carries the
 // activation derivative (VG_EPI_BN_BWD).  dgamma += sum(dz*xhat), dbeta += sum(dz) (atomics: groups share them).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_from_sums_kernel(
     const T* __restrict__ dz, const T* __restrict__ x, T* __restrict__ dx, long long nvec, int C, long long rows,
     const float* __restrict__ stats, const float* __restrict__ sums, float* dgamma, float* dbeta) {
     pdl_enter();
@@ -779,12 +782,12 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
     const int c0 = static_cast<int>((tid * V) % C);
     const float inv_n = 1.f / static_cast<float>(rows);
     const bool publisher = blockIdx.x == 0 && threadIdx.x < C / V;
-    float xv[U][V], dv[U][V];           // first batch in flight while the per-channel coefficients are fetched
+    typename Vec<T>::Raw xr[U], dr[U];   // first batch in flight (packed) while the per-channel coefficients are fetched
 #pragma unroll
     for (int u = 0; u < U; ++u)
         if (tid + u * stride < nvec) {
-            Vec<T>::load(x + (tid + u * stride) * V, xv[u]);
-            Vec<T>::load(dz + (tid + u * stride) * V, dv[u]);
+            xr[u] = Vec<T>::load_raw(x + (tid + u * stride) * V);
+            dr[u] = Vec<T>::load_raw(dz + (tid + u * stride) * V);
         }
     float sc[V], kx[V], k0[V];
 #pragma unroll
@@ -805,16 +808,19 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_from_sums_kernel(
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (i + u * stride < nvec) {
-                    Vec<T>::load(x + (i + u * stride) * V, xv[u]);
-                    Vec<T>::load(dz + (i + u * stride) * V, dv[u]);
+                    xr[u] = Vec<T>::load_raw(x + (i + u * stride) * V);
+                    dr[u] = Vec<T>::load_raw(dz + (i + u * stride) * V);
                 }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (i + u * stride >= nvec) continue;
+            float xv[V], dv[V];
+            Vec<T>::unpack(xr[u], xv);
+            Vec<T>::unpack(dr[u], dv);
 #pragma unroll
-            for (int j = 0; j < V; ++j) dv[u][j] = fmaf(sc[j], dv[u][j], fmaf(kx[j], xv[u][j], k0[j]));
-            Vec<T>::store(dx + (i + u * stride) * V, dv[u]);
+            for (int j = 0; j < V; ++j) dv[j] = fmaf(sc[j], dv[j], fmaf(kx[j], xv[j], k0[j]));
+            Vec<T>::store(dx + (i + u * stride) * V, dv);
         }
     }
 }
@@ -1055,8 +1061,18 @@ int grid_for(long long n) {
 }
 
 // Grid for the channel-affine apply kernels: ~nvec/4 threads, total thread count a multiple of `vec_per_row`.
-int grid_affine(long long nvec, int vec_per_row) {
-    long long blocks = std::max<long long>(1, std::min<long long>(148 * 8, (nvec / 4 + kThreads - 1) / kThreads));
+// block cap of the from-sums BatchNorm passes: one resident wave split over the statistics groups (experiment switch
+// VG_BN_WAVE=0: the older 148 * 8 cap, several waves of short-lived blocks)
+int bn_wave_blocks(int groups) {
+    static const bool wave = [] {
+        const char* v = getenv("VG_BN_WAVE");
+        return v == nullptr || v[0] != '0';
+    }();
+    return wave ? std::max(1, 148 * 3 / groups) : 148 * 8;
+}
+
+int grid_affine(long long nvec, int vec_per_row, int max_blocks = 148 * 8) {
+    long long blocks = std::max<long long>(1, std::min<long long>(max_blocks, (nvec / 4 + kThreads - 1) / kThreads));
     const int mult = std::max(1, vec_per_row / kThreads);          // vec_per_row is a power of two
     blocks = (blocks + mult - 1) / mult * mult;
     return static_cast<int>(blocks);
@@ -1182,7 +1198,9 @@ extern "C" int vg_bn_apply_from_sums(const void* x, VgDType dt, long long rows, 
     if (groups < 1 || groups > 64) return fail(VG_ERR_SHAPE, "bn_apply_from_sums: bad group count %d", groups);
     if (rows < 2) return fail(VG_ERR_SHAPE, "Expected more than 1 value per channel when training");
     const long long nvec = rows * C / V;
-    const dim3 grid(grid_affine(nvec, C / V), groups);
+    // one resident wave (3 blocks of 256 threads per SM at 80 registers) shared by the groups: every thread pays the
+    // per-channel finalisation once and then streams with a grid-stride loop
+    const dim3 grid(grid_affine(nvec, C / V, bn_wave_blocks(groups)), groups);
     cudaStream_t st = as_stream(stream);
     if (dt == VG_BF16)
         launch_k(bn_apply_from_sums_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), nvec, C, rows, sums, gamma, beta,
@@ -1207,7 +1225,7 @@ extern "C" int vg_bn_bwd_apply_from_sums(const void* dz, const void* x, VgDType 
     if (C / V > kThreads) return fail(VG_ERR_SHAPE, "bn_bwd_apply_from_sums: at most %d channels", kThreads * V);
     if (groups < 1 || groups > 64) return fail(VG_ERR_SHAPE, "bn_bwd_apply_from_sums: bad group count %d", groups);
     const long long nvec = rows * C / V;
-    const dim3 grid(grid_affine(nvec, C / V), groups);
+    const dim3 grid(grid_affine(nvec, C / V, bn_wave_blocks(groups)), groups);
     cudaStream_t st = as_stream(stream);
     if (dt == VG_BF16)
         launch_k(bn_bwd_apply_from_sums_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx),
