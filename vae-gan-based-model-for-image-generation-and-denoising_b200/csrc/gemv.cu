@@ -198,10 +198,21 @@ __global__ void __launch_bounds__(256) gemv_up_bnbwd_kernel(const __nv_bfloat16*
         a0[j] = a1[j] = 0.f;
     }
     unpack8(__ldg(reinterpret_cast<const uint4*>(w) + k), wv);
-    for (int b = b0; b < b1; ++b) {
+    // the batch loop used to issue ONE 16-byte load per iteration and wait for it (16 dependent round trips per
+    // thread on a 128-block grid: 17 us for 17 MB); eight saved-tensor vectors are now in flight per thread
+    constexpr int PF = 8;
+    for (int bb = b0; bb < b1; bb += PF) {
+      uint4 xr[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u)
+          if (bb + u < b1) xr[u] = __ldg(reinterpret_cast<const uint4*>(x) + static_cast<long long>(bb + u) * kvec + k);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int b = bb + u;
+        if (b >= b1) break;
         const long long i = static_cast<long long>(b) * kvec + k;
         float xv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+        unpack8(xr[u], xv);
         const float sb = __bfloat162float(s[b]);
         uint32_t o[4];
         float d[8];
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(256) gemv_up_bnbwd_kernel(const __nv_bfloat16*
             a0[j] += d[j];
             a1[j] = fmaf(d[j], (xv[j] - mean[j]) * rstd[j], a1[j]);
         }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = a0[j]; red[threadIdx.x][8 + j] = a1[j]; }
