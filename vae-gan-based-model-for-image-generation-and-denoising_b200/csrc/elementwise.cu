@@ -927,9 +927,20 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const float* __re
     const long long total = static_cast<long long>(B) * bh * bw;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int X = static_cast<int>(i % bw);
-        const int Y = static_cast<int>((i / bw) % bh);
-        const long long b = i / (static_cast<long long>(bw) * bh);
+        // (32-bit index arithmetic whenever the block count allows it: three 64-bit divisions per thread cost more
+        // instructions than the rest of this kernel)
+        int X, Y;
+        long long b;
+        if (total <= 0x7fffffffLL) {
+            const unsigned ii = static_cast<unsigned>(i), q = ii / static_cast<unsigned>(bw);
+            X = static_cast<int>(ii - q * bw);
+            Y = static_cast<int>(q % static_cast<unsigned>(bh));
+            b = q / static_cast<unsigned>(bh);
+        } else {
+            X = static_cast<int>(i % bw);
+            Y = static_cast<int>((i / bw) % bh);
+            b = i / (static_cast<long long>(bw) * bh);
+        }
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
             const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
@@ -968,9 +979,20 @@ __global__ void __launch_bounds__(kThreads) s2d_to_nchw_kernel(const __nv_bfloat
     const long long total = static_cast<long long>(B) * bh * bw;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int X = static_cast<int>(i % bw);
-        const int Y = static_cast<int>((i / bw) % bh);
-        const long long b = i / (static_cast<long long>(bw) * bh);
+        // (32-bit index arithmetic whenever the block count allows it: three 64-bit divisions per thread cost more
+        // instructions than the rest of this kernel)
+        int X, Y;
+        long long b;
+        if (total <= 0x7fffffffLL) {
+            const unsigned ii = static_cast<unsigned>(i), q = ii / static_cast<unsigned>(bw);
+            X = static_cast<int>(ii - q * bw);
+            Y = static_cast<int>(q % static_cast<unsigned>(bh));
+            b = q / static_cast<unsigned>(bh);
+        } else {
+            X = static_cast<int>(i % bw);
+            Y = static_cast<int>((i / bw) % bh);
+            b = i / (static_cast<long long>(bw) * bh);
+        }
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
             const int py = 2 * Y - o + (sub >> 1), px = 2 * X - o + (sub & 1);
