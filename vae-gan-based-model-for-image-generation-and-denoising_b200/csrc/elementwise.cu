@@ -702,10 +702,10 @@ __global__ void __launch_bounds__(kThreads, 3) bn_apply_from_sums_kernel(
     for (int u = 0; u < U; ++u)
         if (tid + u * stride < nvec) raw[u] = Vec<T>::load_raw(x + (tid + u * stride) * V);
     float sc[V], sh[V];
+    const float* sg = sums + static_cast<long long>(grp) * 2 * C;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const int c = c0 + j;
-        const float* sg = sums + static_cast<long long>(grp) * 2 * C;
         // The fp32 sums carry ~1e-7 relative error already; a double-precision divide + square root per channel in every
         // thread's prologue was a multi-microsecond latency in front of each (short) apply pass.  fp32 with one
         // Newton step on rsqrt is within 2 ulp of the double result.
@@ -720,12 +720,24 @@ __global__ void __launch_bounds__(kThreads, 3) bn_apply_from_sums_kernel(
         const float g = gamma ? __ldg(gamma + c) : 1.f, bt = beta ? __ldg(beta + c) : 0.f;
         sc[j] = g * rstd;
         sh[j] = bt - mf * sc[j];
-        if (publisher) {
-            float* st = stats + static_cast<long long>(grp) * 4 * C;
+    }
+    if (publisher) {
+        // (block (0, group) only, kept out of the unrolled loop above: its fp64 running-statistics walk would otherwise
+        // set the register count of every thread of the pass)
+        float* st = stats + static_cast<long long>(grp) * 4 * C;
+#pragma unroll 1
+        for (int j = 0; j < V; ++j) {
+            const int c = c0 + j;
+            const double m = static_cast<double>(sg[c]) * inv_n;
+            const float var_f = static_cast<float>(fmax(fma(-m, m, static_cast<double>(sg[C + c]) * inv_n), 0.0));
+            float rstd = rsqrtf(var_f + eps);
+            rstd = rstd * fmaf(-0.5f * (var_f + eps) * rstd, rstd, 1.5f);
+            const float g = gamma ? __ldg(gamma + c) : 1.f, bt = beta ? __ldg(beta + c) : 0.f;
+            const float scj = g * rstd;
             st[c] = static_cast<float>(m);
             st[C + c] = rstd;
-            st[2 * C + c] = sc[j];
-            st[3 * C + c] = sh[j];
+            st[2 * C + c] = scj;
+            st[3 * C + c] = bt - static_cast<float>(m) * scj;
             if (grp == 0 && running_mean != nullptr) {
                 const double n = static_cast<double>(rows);
                 float rm = running_mean[c], rv = running_var[c];
