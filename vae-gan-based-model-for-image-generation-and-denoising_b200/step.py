@@ -244,7 +244,7 @@ class VAEGANStep:
         # (functional.GradReady, reverse parameter order) and runs under the rest of the backward pass.  The
         # discriminator's 256->512 weight (76 % of its bytes) is ready first and travels under its remaining
         # dgrad / wgrad launches; the generator's 53 MB leave in three buckets under its own and the encoder's backward.
-        self.comm_stream = torch.cuda.Stream(device=self.dev, priority=-1) if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         bb = dict(E=2 << 20, G=8 << 20, D=4 << 20)
         if self.peer is not None:
             # a peer-memory bucket costs two cross-GPU barriers on the communication stream and nothing on the main
@@ -526,13 +526,9 @@ class VAEGANStep:
             key = (not injected)
             if self._graph is None or self._graph[0] != key:
                 # warm-up run outside capture (allocator, lazy module plans), then capture
-                # The main chain is captured on a HIGH-priority stream (kernel nodes keep the priority of the stream
-                # they were captured on): when a main-chain kernel and a weight gradient from a side stream are both
-                # waiting for SMs, the main chain goes first and the weight gradient fills in under the memory-bound
-                # BatchNorm passes that follow.  VG_MAIN_PRIORITY=0 captures on a default-priority stream.
-                import os as _os
-                hi = _os.environ.get("VG_MAIN_PRIORITY", "1") != "0"
-                side = torch.cuda.Stream(device=self.dev, priority=-1) if hi else torch.cuda.Stream(device=self.dev)
+                # (measured and dropped: capturing the main chain on a high-priority stream so that it wins SMs over the
+                # weight-gradient side streams - 3.50-3.54 ms against 3.42-3.44 ms on the same box)
+                side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     self._snapshot = self._save_state()
@@ -543,7 +539,7 @@ class VAEGANStep:
                 g = torch.cuda.CUDAGraph()
                 lib = F_._lib.load()
                 n0 = lib.vg_launch_count()
-                with torch.cuda.graph(g, stream=side):
+                with torch.cuda.graph(g):
                     self._run(gen_noise=key)
                 self.launches_per_step = int(lib.vg_launch_count() - n0)   # kernel nodes of ours in the graph
                 self._graph = (key, g)
