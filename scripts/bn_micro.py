@@ -44,5 +44,5 @@ for name, rows, C, groups in SHAPES:
     t_f = timeit(lambda: fn.bn_apply_from_sums(x, sums, groups, g, b, rm, rv, nbt, 0.1, 1e-5, 1, 0.0))
     t_b = timeit(lambda: fn.bn_bwd_apply_from_sums(dz, x, stats, bsums, groups, dg, db))
     mb = rows * C * 2 / 1e6
-    print(f"{name:18s} {mb:7.1f} MB   apply {t_f:6.1f} us {2 * mb / t_f * 1e-3:5.2f} TB/s   bwd apply {t_b:6.1f} us "
-          f"{3 * mb / t_b * 1e-3:5.2f} TB/s")
+    print(f"{name:18s} {mb:7.1f} MB   apply {t_f:6.1f} us {2 * mb / t_f:5.2f} TB/s   bwd apply {t_b:6.1f} us "
+          f"{3 * mb / t_b:5.2f} TB/s")
