@@ -679,7 +679,9 @@ struct PackBatch {
     int n;
 };
 
-constexpr int kPackT = 32, kPackK = 16, kPackRow = kPackT + 2, kPackPlane = kPackT * kPackRow + 2;
+// (4 taps per tile: the discriminator's largest layer then has 512 tiles instead of 128 - with 16 taps per tile one
+// block per SM moved the whole 17 MB and the launch sat on the critical path for 16 us after every discriminator Adam)
+constexpr int kPackT = 32, kPackK = 4, kPackRow = kPackT + 2, kPackPlane = kPackT * kPackRow + 2;
 
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackBatch b) {
     pdl_enter();
@@ -712,14 +714,15 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackBatch
         const int ts = static_cast<int>(t / (static_cast<long long>(kchunks) * tiles_b));
         const int s0 = ts * kPackT, b0 = tb * kPackT, k0 = kc * kPackK, nk = min(kPackK, kk - k0);
         if (kk == 16 && (reinterpret_cast<uintptr_t>(it.w) & 15) == 0) {
-            // 4x4 kernels (every stride-2 layer): 16-byte loads of four taps, no integer division
-            for (int e = threadIdx.x; e < kPackT * kPackT * 4; e += blockDim.x) {
-                const int s_l = e >> 7, bi_l = (e >> 2) & 31, q4 = e & 3;
+            // 4x4 kernels (every stride-2 layer): one 16-byte load = the tile's four taps, no integer division
+            static_assert(kPackK == 4, "the 16-byte path takes one float4 (four taps) per (small_c, big_c) pair");
+            for (int e = threadIdx.x; e < kPackT * kPackT; e += blockDim.x) {
+                const int s_l = e >> 5, bi_l = e & 31;
                 const int s = s0 + s_l, bi = b0 + bi_l;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (s < sc && bi < bcv)
-                    v = __ldg(reinterpret_cast<const float4*>(it.w + (static_cast<long long>(s) * bcv + bi) * 16) + q4);
-                __nv_bfloat16* t4 = tile + (q4 * 4) * kPackPlane + s_l * kPackRow + bi_l;
+                    v = __ldg(reinterpret_cast<const float4*>(it.w + (static_cast<long long>(s) * bcv + bi) * 16) + kc);
+                __nv_bfloat16* t4 = tile + s_l * kPackRow + bi_l;
                 t4[0] = __float2bfloat16_rn(v.x);
                 t4[kPackPlane] = __float2bfloat16_rn(v.y);
                 t4[2 * kPackPlane] = __float2bfloat16_rn(v.z);
